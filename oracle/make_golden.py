@@ -1,0 +1,236 @@
+"""Generate tests/golden/*.npz by running the REAL reference from /root/reference.
+
+Run in the authoring container only (the reference checkout does not travel to
+the GPU box):   python oracle/make_golden.py
+Everything is seeded; fixtures are small (a few hundred KB in total).  The
+fixtures pin oracle/posfeat_oracle.py (tests/test_oracle_golden.py) and are
+used directly by the GPU parity tests.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = os.environ.get("POSFEAT_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+import losses.preprocess_utils as pu          # noqa: E402
+import losses.preprocess as pp                # noqa: E402
+from losses.epipolarloss import EpipolarLoss_full  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(1)
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def ref_detect(kp_map, **cfg):
+    """Reference detector plus the topk index it used internally."""
+    kps, sc = pu.generate_kpts_single(kp_map, **cfg)
+    b = kp_map.shape[0]
+    inter = kp_map[:, :, 1:-1, 1:-1]
+    use_nms = cfg.get("use_nms", True)
+    if use_nms == "softnms":
+        mask = pu.soft_nms(inter, cfg["nms_radius"])
+    elif use_nms:
+        mask = pu.nms(inter, cfg["nms_radius"])
+    else:
+        mask = torch.ones_like(inter)
+    nms_only = mask.clone()
+    thr = cfg.get("thr", False)
+    if thr:
+        mod = cfg.get("thr_mod", "mean")
+        if mod == "max":
+            t = inter.reshape(b, 1, -1).max(2)[0]
+        elif mod == "mean":
+            t = inter.reshape(b, 1, -1).mean(2)
+        else:
+            t = torch.tensor(1.).repeat(b)
+        mask = (inter > thr * t.view(b, 1, 1, 1)) * mask
+    key = (mask * inter).reshape(b, -1)
+    n = kps.shape[1]
+    _, idx = key.topk(n)
+    return dict(kps=kps.numpy(), score=sc.numpy(), idx=idx.numpy(),
+                key=key.numpy(), nms_mask=nms_only.numpy().astype(np.float32),
+                count=np.asarray(mask.reshape(b, -1).sum(1).numpy()))
+
+
+def golden_detect():
+    cases = {}
+    g = gen(101)
+    base = F.softplus(torch.randn(2, 1, 48, 64, generator=g))
+    cases["r1_abs"] = (base, dict(nms_radius=1, num_pts=300, thr=0.9, thr_mod="abs"))
+    cases["r3_abs"] = (base, dict(nms_radius=3, num_pts=False, thr=0.5, thr_mod="abs"))
+    cases["r2_max"] = (base, dict(nms_radius=2, num_pts=200, thr=0.3, thr_mod="max"))
+    cases["r1_mean"] = (base, dict(nms_radius=1, num_pts=150, thr=1.2, thr_mod="mean"))
+    cases["r1_nothr"] = (base, dict(nms_radius=1, num_pts=400))
+    cases["nonms_abs"] = (base, dict(nms_radius=1, num_pts=256, use_nms=False, thr=1.5,
+                                     thr_mod="abs"))
+    # heavy ties: quantised scores create plateaus and equal maxima
+    q = torch.round(base * 4) / 4 + 0.25
+    cases["ties_r1"] = (q, dict(nms_radius=1, num_pts=200, thr=0.9, thr_mod="abs"))
+    cases["ties_r2"] = (q, dict(nms_radius=2, num_pts=False))
+    # few survivors -> the num_pts<128 floor pads with masked-out pixels
+    cases["few"] = (base, dict(nms_radius=4, num_pts=500, thr=2.5, thr_mod="abs"))
+    const = torch.full((1, 1, 20, 24), 0.7)
+    cases["const"] = (const, dict(nms_radius=1, num_pts=False))
+    # odd sizes (not multiples of 4) and a wide image
+    odd = F.softplus(torch.randn(1, 1, 37, 131, generator=g))
+    cases["odd_r1"] = (odd, dict(nms_radius=1, num_pts=256, thr=0.9, thr_mod="abs"))
+    cases["odd_r5"] = (odd, dict(nms_radius=5, num_pts=False))
+    out = {}
+    for name, (m, cfg) in cases.items():
+        r = ref_detect(m, **cfg)
+        out[name + "/map"] = m.numpy()
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+        out[name + "/cfg"] = np.array(repr(cfg))
+    np.savez_compressed(os.path.join(OUT, "detect.npz"), **out)
+    print("detect:", list(cases))
+
+
+def golden_sample():
+    g = gen(202)
+    x = torch.randn(2, 24, 12, 15, generator=g)
+    c = torch.rand(2, 200, 2, generator=g) * 2.2 - 1.1       # some fall outside
+    c[0, :4] = torch.tensor([[-1., -1.], [1., 1.], [-1., 1.], [0.999, -0.999]])
+    out = dict(x=x.numpy(), coord=c.numpy(),
+               raw=pu.sample_feat_by_coord(x, c, False).numpy(),
+               normed=pu.sample_feat_by_coord(x, c, True).numpy())
+    x128 = torch.randn(1, 128, 16, 20, generator=g)
+    c128 = torch.rand(1, 300, 2, generator=g) * 2 - 1
+    out.update(x128=x128.numpy(), coord128=c128.numpy(),
+               normed128=pu.sample_feat_by_coord(x128, c128, True).numpy())
+    np.savez_compressed(os.path.join(OUT, "sample.npz"), **out)
+    print("sample ok")
+
+
+def golden_mnn():
+    sys.path.insert(0, os.path.join(REF, "evaluations", "aachen"))
+    import matchers as am
+    g = gen(303)
+    a = F.normalize(torch.randn(257, 128, generator=g), dim=1)
+    b = F.normalize(a[torch.randperm(257, generator=g)][:201] + 0.4 * torch.randn(201, 128, generator=g), dim=1)
+    b = torch.cat([b, F.normalize(torch.randn(100, 128, generator=g), dim=1)])
+    out = dict(a=a.numpy(), b=b.numpy(), mnn=pu.mnn_matcher(a, b),
+               mutual_nn=am.mutual_nn_matcher(a, b),
+               ratio=am.ratio_matcher(a, b, 0.95),
+               mutual_ratio=am.mutual_nn_ratio_matcher(a, b, 0.9))
+    # duplicates: exact ties must resolve to the first index
+    ad = a[:64].clone()
+    bd = torch.cat([a[:32], a[:32], a[32:64]])
+    out.update(ad=ad.numpy(), bd=bd.numpy(), mnn_dup=pu.mnn_matcher(ad, bd),
+               mnn_dup_t=pu.mnn_matcher(bd, ad))
+    np.savez_compressed(os.path.join(OUT, "mnn.npz"), **out)
+    print("mnn:", out["mnn"].shape, out["mnn_dup"].shape, out["ratio"].shape, out["mutual_ratio"].shape)
+
+
+def golden_corr():
+    g = gen(404)
+    f1 = F.normalize(torch.randn(2, 40, 32, generator=g), dim=-1) * 3
+    fm = torch.randn(2, 32, 10, 12, generator=g)
+    e, std, kurt, prob = pu.get_expected_correspondence_locs(f1, fm, with_std=True)
+    out = dict(f1=f1.numpy(), fm=fm.numpy(), exp=e.numpy(), std=std.numpy(), prob=prob.numpy())
+    fmw = 6 * F.normalize(torch.randn(2, 32, 40, 60, generator=g), dim=1)
+    c2 = torch.rand(2, 40, 2, generator=g) * 2.1 - 1.05
+    f1w = F.normalize(torch.randn(2, 40, 32, generator=g), dim=-1)
+    ew, cg, stdw, probw = pu.get_expected_correspondence_within_window(f1w, fmw, c2, 0.1, with_std=True)
+    out.update(f1w=f1w.numpy(), fmw=fmw.numpy(), c2=c2.numpy(), expw=ew.numpy(), cgw=cg.numpy(),
+               stdw=stdw.numpy(), probw=probw.numpy())
+    np.savez_compressed(os.path.join(OUT, "corr.npz"), **out)
+    print("corr ok", cg.shape)
+
+
+def random_fundamental(b, h, w, g):
+    Fs = []
+    for _ in range(b):
+        ang = (torch.rand(3, generator=g) - 0.5) * 0.5
+        Rx = torch.tensor([[1, 0, 0], [0, torch.cos(ang[0]), -torch.sin(ang[0])], [0, torch.sin(ang[0]), torch.cos(ang[0])]])
+        Ry = torch.tensor([[torch.cos(ang[1]), 0, torch.sin(ang[1])], [0, 1, 0], [-torch.sin(ang[1]), 0, torch.cos(ang[1])]])
+        Rz = torch.tensor([[torch.cos(ang[2]), -torch.sin(ang[2]), 0], [torch.sin(ang[2]), torch.cos(ang[2]), 0], [0, 0, 1]])
+        R = Rz @ Ry @ Rx
+        t = F.normalize(torch.randn(3, generator=g), dim=0)
+        tx = torch.tensor([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        K = torch.tensor([[float(w), 0, w / 2], [0, float(w), h / 2], [0, 0, 1]])
+        Ki = torch.linalg.inv(K)
+        Fm = Ki.t() @ tx @ R @ Ki
+        Fs.append(Fm / Fm.norm())
+    return torch.stack(Fs).float()
+
+
+def golden_preprocess():
+    """Full Preprocess_Line2Window.forward + EpipolarLoss_full with gradients."""
+    g = gen(505)
+    B, d, H, W = 2, 32, 128, 160
+    cfg = dict(kps_generator="generate_kpts_regular_grid_random",
+               kps_generator_config=dict(grid_size=16, map_init="identity", keep_spatial=True,
+                                         random_select="random"),
+               window_size=0.1, loss_distance="cos", use_nn_grid=False, use_line_search=True,
+               line_search_config=dict(line_step=100, use_nn=True, loc_rand=True),
+               temperature_base=60, temperature_max=60)
+    P = pp.Preprocess_Line2Window(cfg)
+    xf1 = torch.randn(B, d, H // 4, W // 4, generator=g).requires_grad_()
+    xf2 = torch.randn(B, d, H // 4, W // 4, generator=g).requires_grad_()
+    inputs = dict(im1=torch.zeros(B, 3, H, W), im2=torch.zeros(B, 3, H, W),
+                  F1=random_fundamental(B, H, W, g))
+    inputs["F2"] = inputs["F1"].transpose(1, 2).contiguous()
+    preds1 = dict(global_map=torch.zeros(B, d, H // 16, W // 16), local_map=xf1,
+                  local_point=torch.ones(B, 1, H, W))
+    preds2 = dict(global_map=torch.zeros(B, d, H // 16, W // 16), local_map=xf2,
+                  local_point=torch.ones(B, 1, H, W))
+    outputs = dict(preds1=preds1, preds2=preds2, epoch=0)
+
+    rec = {}
+    orig_gen = P.kps_generator
+
+    def gen_wrap(*a, **k):
+        r = orig_gen(*a, **k)
+        rec["coord1_n"], rec["coord2_n"] = r[0].clone(), r[1].clone()
+        return r
+    P.kps_generator = gen_wrap
+    rands = []
+    orig_rand = torch.rand
+
+    def rand_wrap(*a, **k):
+        t = orig_rand(*a, **k)
+        rands.append(t.clone())
+        return t
+    torch.manual_seed(7)
+    torch.rand = rand_wrap
+    try:
+        processed = P(inputs, outputs)
+    finally:
+        torch.rand = orig_rand
+    assert len(rands) == 2, len(rands)
+    loss_cfg = dict(grid_cost_thr=0.5, win_cost_thr=0.1, use_std_as_weight=True,
+                    weight_grid=0.3, weight_window=1)
+    L = EpipolarLoss_full(loss_cfg)
+    loss, comp = L(inputs, outputs, processed)
+    loss.backward()
+    out = dict(xf1=xf1.detach().numpy(), xf2=xf2.detach().numpy(),
+               F1=inputs["F1"].numpy(), F2=inputs["F2"].numpy(),
+               coord1_n=rec["coord1_n"].numpy(), coord2_n=rec["coord2_n"].numpy(),
+               jitter1=rands[0].numpy(), jitter2=rands[1].numpy(),
+               loss=loss.detach().numpy(), gxf1=xf1.grad.numpy(), gxf2=xf2.grad.numpy(),
+               H=np.array(H), W=np.array(W))
+    for k, v in processed.items():
+        if torch.is_tensor(v):
+            out["p_" + k] = v.detach().numpy()
+    for k, v in comp.items():
+        out["c_" + k] = v.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
+    print("preprocess ok; loss", float(loss), "valid", processed["valid_epi1"].float().mean().item())
+
+
+if __name__ == "__main__":
+    golden_detect()
+    golden_sample()
+    golden_mnn()
+    golden_corr()
+    golden_preprocess()
+    tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print("golden bytes:", tot)

@@ -1,0 +1,128 @@
+"""Pin oracle/posfeat_oracle.py against outputs of the real reference
+(fixtures made by oracle/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+
+from oracle import posfeat_oracle as O
+
+DETECT_CASES = ["r1_abs", "r3_abs", "r2_max", "r1_mean", "r1_nothr", "nonms_abs",
+                "ties_r1", "ties_r2", "few", "const", "odd_r1", "odd_r5"]
+
+
+def _cfg(g, name):
+    return eval(str(g[name + "/cfg"]))
+
+
+def check_detect_against(g, name, kps, sc, idx, counts):
+    """Shared checker: (kps, sc, idx, counts) vs the reference fixture.
+
+    Keypoint indices must match exactly where the reference's scores are
+    distinct and as sets inside equal-score groups (torch.topk leaves that
+    order open); entries whose key is 0 are filler chosen arbitrarily by topk.
+    """
+    rkey, ridx = g[name + "/key"], g[name + "/idx"]
+    assert kps.shape == g[name + "/kps"].shape
+    np.testing.assert_array_equal(np.asarray(counts, dtype=np.float64),
+                                  g[name + "/count"].astype(np.float64))
+    for b in range(ridx.shape[0]):
+        rv = rkey[b][ridx[b]]
+        ov = rkey[b][idx[b]]
+        np.testing.assert_array_equal(rv, ov)           # same score sequence
+        real = rv > 0
+        above = real & (rv > rv[-1])        # the cut-off group may be split differently
+        assert set(ridx[b][above]) == set(idx[b][above])
+        assert len(set(idx[b].tolist())) == idx.shape[1]
+        # exact position match wherever the score is unique in the list
+        vals, cnt = np.unique(rv, return_counts=True)
+        uniq = np.isin(rv, vals[cnt == 1]) & real
+        np.testing.assert_array_equal(ridx[b][uniq], idx[b][uniq])
+        # centroid / score of each selected pixel: compare through the index
+        order_r = np.argsort(ridx[b][above], kind="stable")
+        order_o = np.argsort(idx[b][above], kind="stable")
+        np.testing.assert_allclose(kps[b][above][order_o], g[name + "/kps"][b][above][order_r],
+                                   rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(sc[b][above][order_o], g[name + "/score"][b][above][order_r])
+        # our tie policy: index ascending inside an equal-score group
+        for v in vals[cnt > 1]:
+            if v > 0:
+                grp = idx[b][rv == v]
+                assert np.all(np.diff(grp) > 0)
+
+
+@pytest.mark.parametrize("name", DETECT_CASES)
+def test_detect(golden, name):
+    g = golden("detect")
+    cfg = _cfg(g, name)
+    m = g[name + "/map"]
+    if cfg.get("use_nms", True) is True:
+        for b in range(m.shape[0]):
+            keep = O.nms_keep_mask(m[b, 0, 1:-1, 1:-1], cfg["nms_radius"])
+            np.testing.assert_array_equal(keep, g[name + "/nms_mask"][b, 0] > 0)
+    kps, sc, idx, counts = O.generate_kpts_single(m, return_idx=True, **cfg)
+    check_detect_against(g, name, kps, sc, idx, counts)
+
+
+def test_linspace_matches_torch():
+    import torch
+    for n in (2, 3, 8, 13, 640, 898, 1200, 1600):
+        np.testing.assert_array_equal(O.linspace_f32(-1, 1, n), torch.linspace(-1, 1, n).numpy())
+    np.testing.assert_array_equal(O.linspace_f32(-0.1, 0.1, 12), torch.linspace(-0.1, 0.1, 12).numpy())
+
+
+def test_sample(golden):
+    g = golden("sample")
+    raw = O.sample_feat_by_coord(g["x"], g["coord"], False)
+    np.testing.assert_allclose(raw, g["raw"], rtol=1e-5, atol=1e-6)
+    nr = O.sample_feat_by_coord(g["x"], g["coord"], True)
+    np.testing.assert_allclose(nr, g["normed"], rtol=1e-5, atol=1e-6)
+    n128 = O.sample_feat_by_coord(g["x128"], g["coord128"], True)
+    np.testing.assert_allclose(n128, g["normed128"], rtol=1e-5, atol=1e-6)
+
+
+def test_mnn(golden):
+    g = golden("mnn")
+    for exact in (False, True):
+        np.testing.assert_array_equal(O.mnn_matcher(g["a"], g["b"], exact), g["mnn"])
+    np.testing.assert_array_equal(g["mnn"], g["mutual_nn"])
+    np.testing.assert_array_equal(O.mnn_matcher(g["ad"], g["bd"], True), g["mnn_dup"])
+    np.testing.assert_array_equal(O.mnn_matcher(g["bd"], g["ad"], True), g["mnn_dup_t"])
+    np.testing.assert_array_equal(O.ratio_matchers(g["a"], g["b"], 0.95, mutual=False), g["ratio"])
+    np.testing.assert_array_equal(O.ratio_matchers(g["a"], g["b"], 0.9, mutual=True), g["mutual_ratio"])
+
+
+def test_mnn_edge():
+    a = np.eye(4, 8, dtype=np.float32)
+    m = O.mnn_matcher(a, a[::-1].copy())
+    np.testing.assert_array_equal(m, np.array([[0, 3], [1, 2], [2, 1], [3, 0]]))
+    assert O.mnn_matcher(a, a[:1]).tolist() == [[0, 0]]
+
+
+def test_corr(golden):
+    g = golden("corr")
+    e, std, prob = O.get_expected_correspondence_locs(g["f1"], g["fm"], with_std=True)
+    np.testing.assert_allclose(e, g["exp"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(std, g["std"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(prob, g["prob"], rtol=2e-5, atol=1e-8)
+    ew, cg, stdw, probw = O.get_expected_correspondence_within_window(g["f1w"], g["fmw"], g["c2"], 0.1)
+    np.testing.assert_allclose(cg, g["cgw"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(probw, g["probw"], rtol=5e-5, atol=1e-7)
+    np.testing.assert_allclose(ew, g["expw"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(stdw, g["stdw"], rtol=1e-4, atol=5e-6)
+
+
+def test_grid_stage(golden):
+    g = golden("preprocess")
+    H, W = int(g["H"]), int(g["W"])
+    c1n = g["coord1_n"].reshape(2, -1, 2)
+    c2n = g["coord2_n"].reshape(2, -1, 2)
+    f1 = O.sample_feat_by_coord(g["xf1"], c1n, True)
+    f2 = O.sample_feat_by_coord(g["xf2"], c2n, True)
+    c1 = O.denormalize_coords(c1n, H, W)
+    c2 = O.denormalize_coords(c2n, H, W)
+    np.testing.assert_allclose(c1, g["p_coord1"], rtol=1e-6, atol=1e-4)
+    l1, l2, s1, s2 = O.grid_softmax_expectation(f1, f2, c1, c2, c1n, c2n, 60.0, H, W, H, W,
+                                                dtype=np.float64)
+    np.testing.assert_allclose(l1, g["p_feat1g_corloc"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(l2, g["p_feat2g_corloc"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(s1, g["p_feat1g_std"], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(s2, g["p_feat2g_std"], rtol=2e-3, atol=1e-4)
