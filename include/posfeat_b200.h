@@ -1,0 +1,190 @@
+/* posfeat_b200 -- C ABI of the B200 (sm_100a) post-backbone feature pipeline.
+ *
+ * Drop-in boundary for the hot path of PoSFeat (reference paths are relative
+ * to the reference checkout).  The reference has no FFI: its "plugin API" is
+ * name-based dispatch on Python callables (managers/extractor.py:87,
+ * evaluations/ETH_local_feature/reconstruction_pipeline.py:99).  Each entry
+ * point below is what a ctypes binding behind one of those callables needs;
+ * the binding itself lives in posfeat_b200/_lib.py and INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name
+ *    ends in _host; the library never allocates or retains device memory;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *    entry point synchronises the host unless documented;
+ *  - return value 0 = OK, otherwise a POSFEAT_E* code; the message is
+ *    available from posfeat_last_error() (thread local);
+ *  - no C++ exceptions cross this boundary.
+ */
+#ifndef POSFEAT_B200_H_
+#define POSFEAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POSFEAT_OK 0
+#define POSFEAT_EINVAL 1     /* bad argument / unsupported option combination */
+#define POSFEAT_ECUDA 2      /* a CUDA runtime call failed                     */
+#define POSFEAT_EWORKSPACE 3 /* workspace too small                            */
+#define POSFEAT_EUNSUPPORTED 4
+
+/* nms_mode: use_nms=False / True of generate_kpts_single
+ * (losses/preprocess_utils.py:225-230). */
+#define POSFEAT_NMS_NONE 0
+#define POSFEAT_NMS_HARD 1
+/* thr_mode: thr=False, thr_mod='abs'|'max'|'mean' (:232-240). */
+#define POSFEAT_THR_NONE 0
+#define POSFEAT_THR_ABS 1
+#define POSFEAT_THR_MAX 2
+#define POSFEAT_THR_MEAN 3
+/* descriptor-map layouts for the sampler are expressed as element strides. */
+
+int posfeat_version(void);
+/* Copies the calling thread's last error message (NUL terminated). */
+int posfeat_last_error(char* buf, int n);
+/* Number of SMs of the current device (grid sizing for callers), <0 on error. */
+int posfeat_device_sm_count(void);
+
+/* ---- (1) score-map keypoint selection -------------------------------------
+ * Replaces generate_kpts_single(..., stable=True), losses/preprocess_utils.py:215-267
+ * (nms :449-464, threshold :232-240, centroid/score :243-247, count clamp
+ * :249-261, topk+gather :263-267).
+ *
+ * score      [B,1,H,W] float32, element strides (stride_b, stride_y, 1)
+ * num_pts    requested keypoints; 0 = "False" (all survivors)
+ * min_pts    the reference's floor (128, :260-261)
+ * cap_pts    capacity of the per-image output rows (>= the n that results)
+ * n_fixed    >=0: caller already decided n (two-phase use); -1: decide on
+ *            device as max(min(num_pts or inf, min_b count_b), min_pts)
+ * counts     [B] int32 out: survivors per image (what :251-259 sums)
+ * n_out      [1] int32 out: the n used (same for every image of the batch)
+ * idx_out    [B,cap_pts] int64: linear index into the (H-2)x(W-2) interior grid
+ * kps_out    [B,cap_pts,2] float32 normalised (x,y); kpscore_out [B,cap_pts]
+ * Rows [n, cap_pts) are left untouched.  Order: score descending, index
+ * ascending inside an equal-score group.
+ */
+size_t posfeat_detect_workspace_bytes(int B, int H, int W, int cap_pts);
+
+int posfeat_detect_candidates_f32(const float* score, int B, int H, int W,
+                                  int64_t stride_b, int64_t stride_y,
+                                  int nms_mode, int radius, int thr_mode, float thr,
+                                  int32_t* counts, void* workspace, size_t ws_bytes,
+                                  void* stream);
+
+int posfeat_detect_select_f32(const float* score, int B, int H, int W,
+                              int64_t stride_b, int64_t stride_y,
+                              int num_pts, int min_pts, int cap_pts, int n_fixed,
+                              const int32_t* counts, int32_t* n_out,
+                              int64_t* idx_out, float* kps_out, float* kpscore_out,
+                              void* workspace, size_t ws_bytes, void* stream);
+
+/* candidates + select in one call (n decided on device, no host sync). */
+int posfeat_detect_topk_f32(const float* score, int B, int H, int W,
+                            int64_t stride_b, int64_t stride_y,
+                            int nms_mode, int radius, int thr_mode, float thr,
+                            int num_pts, int min_pts, int cap_pts,
+                            int32_t* counts, int32_t* n_out,
+                            int64_t* idx_out, float* kps_out, float* kpscore_out,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* Reads the device-side status of the last select on this workspace
+ * (synchronises `stream`): POSFEAT_OK, or POSFEAT_EINVAL when n exceeded
+ * cap_pts / the number of interior pixels (torch.topk would raise there). */
+int posfeat_detect_status(void* workspace, int B, int H, int W, int cap_pts, void* stream);
+
+/* ---- (2) bilinear descriptor sampling + L2 normalisation -------------------
+ * Replaces sample_feat_by_coord, losses/preprocess_utils.py:40-53
+ * (grid_sample bilinear/zeros/align_corners=False, then F.normalize, eps 1e-12).
+ * fmap element strides (sb, sc, sy, sx) describe NCHW (sx=1) or NHWC (sc=1).
+ * coord_n [B,n,2] normalised (x,y), contiguous; out [B,n,D] contiguous.
+ * n_valid: optional device int32 (may be NULL) -- only the first *n_valid of
+ * the n points are processed (lets the detector's n stay on the device).
+ * out_bf16: optional [B,n,D] bf16 copy of the result (may be NULL), the
+ * operand format of the tensor-core matcher.
+ */
+int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h, int w,
+                              int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                              const float* coord_n, int n, const int32_t* n_valid,
+                              int do_norm, float* out, void* out_bf16, void* stream);
+
+/* ---- (3) mutual nearest neighbour matching ---------------------------------
+ * Replaces mnn_matcher / mutual_nn_matcher: evaluations/hpatches/evaluation.py:27-38,
+ * evaluations/aachen/matchers.py:5-13, evaluations/ETH_local_feature/custom_matcher.py:5-13,
+ * losses/preprocess_utils.py:795-803.
+ * A [N,D], Bm [M,D] float32 row-major (row stride lda/ldb elements).
+ * nn12 [N] int32 = argmax_j <A_i,B_j>, nn21 [M] int32 = argmax_i (first index
+ * on exact ties); matches [N,2] int64 holds the K mutual pairs (i, nn12[i]) in
+ * ascending i; n_matches [1] int32.  The N x M similarity is never written to
+ * memory.  algo: 0 = auto, 1 = exact SIMT kernel (fp64 accumulation),
+ * 2 = tcgen05 tensor-core kernel (bf16 operands, candidate rescoring in fp64;
+ * requires D == 128).  Both give the same nn12/nn21.
+ */
+#define POSFEAT_MNN_AUTO 0
+#define POSFEAT_MNN_SIMT 1
+#define POSFEAT_MNN_TC 2
+size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo);
+
+int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb,
+                    int D, int algo, int32_t* nn12, int32_t* nn21, int64_t* matches,
+                    int32_t* n_matches, void* workspace, size_t ws_bytes, void* stream);
+
+/* Same, operands and results in HOST memory (pageable or pinned): copies in,
+ * runs, copies back and synchronises `stream`.  This is the call a reader of
+ * .npz descriptor files makes (evaluations/hpatches/evaluation.py:64-67).
+ * Device scratch [dev_scratch, +scratch_bytes) is supplied by the caller;
+ * query the size with posfeat_mnn_host_scratch_bytes. */
+size_t posfeat_mnn_host_scratch_bytes(int N, int M, int D, int algo);
+int posfeat_mnn_host_f32(const float* A_host, int N, const float* B_host, int M, int D, int algo,
+                         int64_t* matches_host, int32_t* n_matches_host,
+                         void* dev_scratch, size_t scratch_bytes, void* stream);
+
+/* ---- (4) training-side correlation + softmax expectation -------------------
+ * Dense variant: get_expected_correspondence_locs, losses/preprocess_utils.py:55-82,
+ * and the grid<->grid stage of Preprocess_Line2Window.forward,
+ * losses/preprocess.py:59-81 (both are softmax(scale*<q,k>) expectations of a
+ * coordinate table).
+ *   q [B,n,D], k [B,m,D] (row strides D), v [B or 1, m, C] value table
+ *   (C <= 4: e.g. x, y, x^2, y^2); out [B,n,C] = sum_j softmax_j(scale*q.k_j) v_j;
+ *   lse [B,n] = log-sum-exp of the scaled logits (saved for backward).
+ * Backward: given g_out [B,n,C] produces g_q [B,n,D] and g_k [B,m,D]
+ * (g_k is accumulated with atomics into a zero-initialised buffer).
+ */
+int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, int v_batched,
+                                int B, int n, int m, int D, int C, float scale,
+                                float* out, float* lse, void* stream);
+int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, int v_batched,
+                                int B, int n, int m, int D, int C, float scale,
+                                const float* out, const float* lse, const float* g_out,
+                                float* g_q, float* g_k, void* stream);
+
+/* Window variant: get_expected_correspondence_within_window,
+ * losses/preprocess_utils.py:721-758.  fmap [B,D,h,w] with element strides
+ * (sb,sc,sy,sx); q [B,n,D]; centre [B,n,2] normalised; offsets [m,2] (the
+ * gen_grid(-ws,ws,...) table).  The [B,n,m,D] gathered tensor is never
+ * materialised.  Outputs: exp_xy [B,n,2], std [B,n] (sum_xy sqrt(clamp(var,
+ * 1e-10))), prob [B,n,m] (optional, may be NULL), lse [B,n].
+ * Backward gets g_exp [B,n,2], g_std [B,n] and produces g_q [B,n,D] and
+ * g_fmap (same strides as fmap, zero-initialised by the caller, atomics).
+ */
+int posfeat_window_expect_fwd_f32(const float* fmap, int B, int D, int h, int w,
+                                  int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                                  const float* q, const float* centre, int n,
+                                  const float* offsets, int m,
+                                  float* exp_xy, float* std_out, float* prob, float* lse,
+                                  void* stream);
+int posfeat_window_expect_bwd_f32(const float* fmap, int B, int D, int h, int w,
+                                  int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                                  const float* q, const float* centre, int n,
+                                  const float* offsets, int m,
+                                  const float* exp_xy, const float* lse,
+                                  const float* g_exp, const float* g_std,
+                                  float* g_q, float* g_fmap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSFEAT_B200_H_ */

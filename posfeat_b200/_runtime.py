@@ -1,0 +1,47 @@
+"""Device plumbing shared by the host-side wrappers: torch is used only for
+device memory, streams and workspace caching."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_workspaces = {}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("posfeat_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def to_device(t: torch.Tensor, dtype=torch.float32):
+    """Return (cuda tensor, original device)."""
+    require_cuda()
+    dev = t.device
+    if dev.type != "cuda":
+        t = t.to("cuda", non_blocking=True)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t, dev
+
+
+def workspace(key: str, nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (uint8)."""
+    k = (key, torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[k] = buf
+    return buf
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+lib = _lib.load
+check = _lib.check

@@ -1,0 +1,146 @@
+// C-ABI plumbing: version, thread-local error string, device query, and the
+// matcher entry points that dispatch between the exact SIMT kernel and the
+// tcgen05 tensor-core kernel.
+#include <string.h>
+
+#include "common.cuh"
+#include "mnn_common.cuh"
+
+namespace posfeat {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+struct MnnScratch {
+  float *A, *B;
+  int32_t *nn12, *nn21, *n_matches;
+  int64_t* matches;
+  void* ws;
+  size_t ws_bytes, total;
+};
+
+static MnnScratch carve_host_scratch(void* base, int N, int M, int D, int algo) {
+  MnnScratch s;
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  s.A = (float*)take(sizeof(float) * (size_t)N * D);
+  s.B = (float*)take(sizeof(float) * (size_t)M * D);
+  s.nn12 = (int32_t*)take(sizeof(int32_t) * N);
+  s.nn21 = (int32_t*)take(sizeof(int32_t) * M);
+  s.n_matches = (int32_t*)take(sizeof(int32_t));
+  s.matches = (int64_t*)take(sizeof(int64_t) * 2 * (size_t)N);
+  s.ws_bytes = posfeat_mnn_workspace_bytes(N, M, D, algo);
+  s.ws = take(s.ws_bytes);
+  s.total = off;
+  return s;
+}
+
+}  // namespace posfeat
+
+using namespace posfeat;
+
+extern "C" int posfeat_version(void) { return 100; }
+
+extern "C" int posfeat_last_error(char* buf, int n) {
+  if (!buf || n <= 0) return POSFEAT_EINVAL;
+  strncpy(buf, g_err, (size_t)n - 1);
+  buf[n - 1] = 0;
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+
+static int resolve_algo(int N, int M, int D, int algo) {
+  if (algo == POSFEAT_MNN_AUTO) return (tc_supported(N, M, D) && (int64_t)N * M >= (int64_t)1024 * 1024) ? POSFEAT_MNN_TC : POSFEAT_MNN_SIMT;
+  return algo;
+}
+
+extern "C" size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo) {
+  if (N < 1 || M < 1 || D < 1) return 0;
+  size_t need = simt_workspace_bytes(N, M);
+  const int a = resolve_algo(N, M, D, algo);
+  if (a == POSFEAT_MNN_TC && tc_supported(N, M, D)) {
+    const size_t t = tc_workspace_bytes(N, M);
+    if (t > need) need = t;
+  }
+  return need;
+}
+
+extern "C" int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D,
+                               int algo, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches,
+                               void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(A && Bm && nn12 && nn21 && matches && n_matches && workspace, "NULL pointer");
+  PF_CHECK_ARG(N >= 1 && M >= 1 && D >= 1, "empty operand (N=%d M=%d D=%d): the reference's torch.max raises on an empty reduction too", N, M, D);
+  PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
+  PF_CHECK_ARG(algo >= POSFEAT_MNN_AUTO && algo <= POSFEAT_MNN_TC, "unknown algo %d", algo);
+  const int a = resolve_algo(N, M, D, algo);
+  const size_t need = posfeat_mnn_workspace_bytes(N, M, D, a);
+  if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "mnn workspace: need %zu bytes, got %zu", need, ws_bytes);
+  int e;
+  if (a == POSFEAT_MNN_TC) {
+    if (!tc_supported(N, M, D))
+      return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
+    e = mnn_tc(A, N, lda, Bm, M, ldb, D, nn12, nn21, workspace, ws_bytes, stream);
+  } else {
+    e = mnn_simt(A, N, lda, Bm, M, ldb, D, nn12, nn21, workspace, stream);
+  }
+  if (e) return e;
+  return launch_mutual_compact(nn12, nn21, N, M, matches, n_matches, stream);
+}
+
+extern "C" size_t posfeat_mnn_host_scratch_bytes(int N, int M, int D, int algo) {
+  if (N < 1 || M < 1 || D < 1) return 0;
+  return carve_host_scratch(nullptr, N, M, D, algo).total;
+}
+
+extern "C" int posfeat_mnn_host_f32(const float* A_host, int N, const float* B_host, int M, int D, int algo,
+                                    int64_t* matches_host, int32_t* n_matches_host, void* dev_scratch,
+                                    size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(A_host && B_host && matches_host && n_matches_host && dev_scratch, "NULL pointer");
+  PF_CHECK_ARG(N >= 1 && M >= 1 && D >= 1, "empty operand (N=%d M=%d D=%d)", N, M, D);
+  MnnScratch s = carve_host_scratch(dev_scratch, N, M, D, algo);
+  if (scratch_bytes < s.total) return set_error(POSFEAT_EWORKSPACE, "mnn host scratch: need %zu bytes, got %zu", s.total, scratch_bytes);
+  PF_CUDA(cudaMemcpyAsync(s.A, A_host, sizeof(float) * (size_t)N * D, cudaMemcpyHostToDevice, stream));
+  PF_CUDA(cudaMemcpyAsync(s.B, B_host, sizeof(float) * (size_t)M * D, cudaMemcpyHostToDevice, stream));
+  int e = posfeat_mnn_f32(s.A, N, D, s.B, M, D, D, algo, s.nn12, s.nn21, s.matches, s.n_matches, s.ws, s.ws_bytes, stream);
+  if (e) return e;
+  PF_CUDA(cudaMemcpyAsync(n_matches_host, s.n_matches, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  PF_CUDA(cudaStreamSynchronize(stream));
+  const int k = *n_matches_host;
+  if (k > 0) {
+    PF_CUDA(cudaMemcpyAsync(matches_host, s.matches, sizeof(int64_t) * 2 * (size_t)k, cudaMemcpyDeviceToHost, stream));
+    PF_CUDA(cudaStreamSynchronize(stream));
+  }
+  return POSFEAT_OK;
+}

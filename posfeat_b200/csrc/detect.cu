@@ -1,0 +1,518 @@
+// Subsystem (1): score-map keypoint selection for sm_100a.
+//
+// Replaces generate_kpts_single(stable=True), reference
+// losses/preprocess_utils.py:215-267:
+//   nms (:449-464)  -> nms_candidates_kernel (shared-memory halo tile, closed-form
+//                      "first maximum in scan order" predicate, warp-ballot
+//                      compaction of survivors into 64-bit keys)
+//   thr (:232-240)  -> fused into the same kernel (thr_val prepared on device)
+//   topk (:264)     -> select_kernel: radix select over the candidate keys only,
+//                      bitonic sort of the winners in shared memory
+//   centroid/score (:243-247), gather (:266-267) -> evaluated only at the winners
+//   gen_grid (:84-87, :217-221) -> computed in-kernel (bit exact linspace)
+// HBM-bound: the score map is read once (4 B/pixel); survivors cost 8 B each.
+#include "common.cuh"
+
+namespace posfeat {
+
+typedef unsigned long long u64;
+
+constexpr int kTileW = 128;
+constexpr int kTileH = 16;
+constexpr int kNmsThreads = 256;
+constexpr int kSelThreads = 1024;
+constexpr int kSortSmemKeys = 16384;      // 128 KB of 64-bit keys
+constexpr int kFillBitmapWords = 2048;    // filler search covers the first 65536 pixels
+constexpr int kFillMax = 4096;
+
+struct DetectWs {
+  int32_t* cand_count;   // [B] positive-score survivors written to cand
+  float* thr_val;        // [B]
+  double* red_sum;       // [B]
+  unsigned* red_max;     // [B] order-preserving uint of the max
+  int32_t* status;       // [1] device-side error flag
+  u64* cand;             // [B, cand_cap]
+  u64* sortbuf;          // [B, sort_cap] (only when cap_pts > kSortSmemKeys)
+  int64_t cand_cap;
+  int64_t sort_cap;
+  size_t total;
+};
+
+static inline int64_t next_pow2(int64_t v) {
+  int64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static DetectWs carve(void* base, int B, int H, int W, int cap_pts) {
+  DetectWs w;
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  w.cand_count = (int32_t*)take(sizeof(int32_t) * B);
+  w.thr_val = (float*)take(sizeof(float) * B);
+  w.red_sum = (double*)take(sizeof(double) * B);
+  w.red_max = (unsigned*)take(sizeof(unsigned) * B);
+  w.status = (int32_t*)take(sizeof(int32_t));
+  w.cand_cap = (int64_t)(H - 2) * (W - 2);
+  w.cand = (u64*)take(sizeof(u64) * (size_t)B * w.cand_cap);
+  w.sort_cap = cap_pts > kSortSmemKeys ? next_pow2(cap_pts) : 0;
+  w.sortbuf = (u64*)take(sizeof(u64) * (size_t)B * w.sort_cap);
+  w.total = off;
+  return w;
+}
+
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---- threshold preparation ------------------------------------------------
+__global__ void reduce_interior_kernel(const float* __restrict__ score, int H, int W, int64_t sb,
+                                       int64_t sy, double* red_sum, unsigned* red_max) {
+  const int b = blockIdx.y;
+  const int hi = H - 2, wi = W - 2;
+  const int64_t total = (int64_t)hi * wi;
+  const float* img = score + b * sb;
+  double s = 0.0;
+  float m = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / wi), x = (int)(i - (int64_t)y * wi);
+    float v = __ldg(img + (int64_t)(y + 1) * sy + x + 1);
+    s += (double)v;
+    m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(red_sum + b, s);
+    atomicMax(red_max + b, float_to_ordered(m));
+  }
+}
+
+__global__ void finalize_thr_kernel(int B, int thr_mode, float thr, int64_t n_interior,
+                                    const double* red_sum, const unsigned* red_max, float* thr_val) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float t;
+  if (thr_mode == POSFEAT_THR_ABS) {
+    t = thr * 1.0f;
+  } else if (thr_mode == POSFEAT_THR_MAX) {
+    t = thr * ordered_to_float(red_max[b]);
+  } else if (thr_mode == POSFEAT_THR_MEAN) {
+    t = thr * (float)(red_sum[b] / (double)n_interior);
+  } else {
+    t = -INFINITY;
+  }
+  thr_val[b] = t;
+}
+
+// ---- phase 1: NMS + threshold + compaction --------------------------------
+// One CTA = kTileH x kTileW interior pixels.  The padded tile (halo r, reflect
+// about the INTERIOR map, as F.pad(mode='reflect') on kp_map[:,:,1:-1,1:-1])
+// lives in shared memory.  keep(y,x) <=> c > v for every window entry that
+// precedes the centre in row-major scan order, c >= v for every later entry.
+__global__ void __launch_bounds__(kNmsThreads)
+nms_candidates_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int64_t sy,
+                      int nms_mode, int r, int has_thr, const float* __restrict__ thr_val,
+                      int32_t* __restrict__ counts, int32_t* __restrict__ cand_count,
+                      u64* __restrict__ cand, int64_t cand_cap) {
+  extern __shared__ float tile[];
+  __shared__ u64 s_list[kTileH * kTileW];
+  __shared__ int s_n, s_nall, s_base;
+
+  const int b = blockIdx.z;
+  const int hi = H - 2, wi = W - 2;
+  const int ty0 = blockIdx.y * kTileH, tx0 = blockIdx.x * kTileW;
+  const int pw = kTileW + 2 * r, ph = kTileH + 2 * r;
+  const int pitch = pw | 1;  // odd pitch: column walks hit distinct banks
+  const float* img = score + b * sb;
+
+  if (threadIdx.x == 0) { s_n = 0; s_nall = 0; }
+  for (int i = threadIdx.x; i < ph * pw; i += kNmsThreads) {
+    int py = i / pw, px = i - py * pw;
+    int iy = ty0 + py - r, ix = tx0 + px - r;
+    float v = -INFINITY;
+    if (iy < hi + r && ix < wi + r) {
+      iy = reflect_idx(iy, hi);
+      ix = reflect_idx(ix, wi);
+      v = __ldg(img + (int64_t)(iy + 1) * sy + ix + 1);
+    }
+    tile[py * pitch + px] = v;
+  }
+  __syncthreads();
+
+  const float tv = has_thr ? thr_val[b] : 0.f;
+  const int lane = threadIdx.x & 31;
+  int n_all = 0;
+  for (int i = threadIdx.x; i < kTileH * kTileW; i += kNmsThreads) {
+    const int ly = i / kTileW, lx = i - ly * kTileW;
+    const int y = ty0 + ly, x = tx0 + lx;
+    bool keep = (y < hi) && (x < wi);
+    float c = 0.f;
+    if (keep) {
+      c = tile[(ly + r) * pitch + lx + r];
+      if (has_thr) keep = c > tv;
+    }
+    if (keep && nms_mode == POSFEAT_NMS_HARD) {
+      const float* base = tile + ly * pitch + lx;  // window top-left
+      for (int dy = 0; dy <= 2 * r && keep; ++dy) {
+        const float* row = base + dy * pitch;
+        if (dy < r) {
+          for (int dx = 0; dx <= 2 * r; ++dx) keep &= c > row[dx];
+        } else if (dy == r) {
+          for (int dx = 0; dx < r; ++dx) keep &= c > row[dx];
+          for (int dx = r + 1; dx <= 2 * r; ++dx) keep &= c >= row[dx];
+        } else {
+          for (int dx = 0; dx <= 2 * r; ++dx) keep &= c >= row[dx];
+        }
+      }
+    }
+    n_all += keep ? 1 : 0;
+    const bool emit = keep && c > 0.f;
+    const unsigned bal = __ballot_sync(0xffffffffu, emit);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (emit) {
+        const unsigned idx = (unsigned)y * (unsigned)wi + (unsigned)x;
+        s_list[base + __popc(bal & ((1u << lane) - 1u))] =
+            ((u64)__float_as_uint(c) << 32) | (u64)(0xffffffffu - idx);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_all += __shfl_xor_sync(0xffffffffu, n_all, o);
+  if (lane == 0 && n_all) atomicAdd(&s_nall, n_all);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_base = s_n ? atomicAdd(cand_count + b, s_n) : 0;
+    if (s_nall) atomicAdd(counts + b, s_nall);
+  }
+  __syncthreads();
+  const int n = s_n;
+  u64* dst = cand + (int64_t)b * cand_cap + s_base;
+  for (int i = threadIdx.x; i < n; i += kNmsThreads) dst[i] = s_list[i];
+}
+
+// ---- phase 2: select + sort + centroid ------------------------------------
+__device__ void bitonic_steps(u64* a, int P, int k, int j_from, int j_to, int64_t gbase) {
+  // descending bitonic network steps j = j_from, j_from/2, ..., j_to for stage k
+  // on the P elements a[0..P); gbase = global index of a[0] (direction bit).
+  for (int j = j_from; j >= j_to; j >>= 1) {
+    for (int p = threadIdx.x; p < P / 2; p += blockDim.x) {
+      const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+      const int l = i | j;
+      const u64 x = a[i], y = a[l];
+      const bool up = (((int64_t)i + gbase) & k) != 0;  // ascending block of the network
+      if (up ? (x > y) : (x < y)) { a[i] = y; a[l] = x; }
+    }
+    __syncthreads();
+  }
+}
+
+// Sort P (power of two) keys descending.  If `g` is shared memory (P <= CH) the
+// whole network runs there; otherwise steps with stride >= CH run in global
+// memory and the rest chunk by chunk through the shared buffer `s`.
+__device__ void bitonic_sort_desc(u64* g, int P, u64* s, int CH, bool in_smem) {
+  if (in_smem) {
+    for (int k = 2; k <= P; k <<= 1) bitonic_steps(g, P, k, k >> 1, 1, 0);
+    return;
+  }
+  const int nchunk = P / CH;
+  for (int c = 0; c < nchunk; ++c) {
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[(int64_t)c * CH + i];
+    __syncthreads();
+    for (int k = 2; k <= CH; k <<= 1) bitonic_steps(s, CH, k, k >> 1, 1, (int64_t)c * CH);
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) g[(int64_t)c * CH + i] = s[i];
+    __syncthreads();
+  }
+  for (int k = CH << 1; k <= P; k <<= 1) {
+    bitonic_steps(g, P, k, k >> 1, CH, 0);
+    for (int c = 0; c < nchunk; ++c) {
+      for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[(int64_t)c * CH + i];
+      __syncthreads();
+      bitonic_steps(s, CH, k, CH >> 1, 1, (int64_t)c * CH);
+      for (int i = threadIdx.x; i < CH; i += blockDim.x) g[(int64_t)c * CH + i] = s[i];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, int64_t sy,
+              int num_pts, int min_pts, int cap_pts, int n_fixed,
+              const int32_t* __restrict__ counts, const int32_t* __restrict__ cand_count,
+              const u64* __restrict__ cand, int64_t cand_cap, u64* __restrict__ sortbuf,
+              int64_t sort_cap, int32_t* __restrict__ status, int32_t* __restrict__ n_out,
+              int64_t* __restrict__ idx_out, float* __restrict__ kps_out,
+              float* __restrict__ kpscore_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* s_keys = (u64*)smem_raw;  // kSortSmemKeys
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_bitmap[kFillBitmapWords];
+  __shared__ unsigned s_fill[kFillMax];
+  __shared__ int s_cnt;
+  __shared__ u64 s_prefix;
+  __shared__ int s_above, s_G, s_done;
+
+  const int b = blockIdx.x;
+  const int hi = H - 2, wi = W - 2;
+  const int64_t n_interior = (int64_t)hi * wi;
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  // n: :249-261 of the reference (min over the batch, then the 128 floor)
+  int n;
+  if (n_fixed >= 0) {
+    n = n_fixed;
+  } else {
+    int m = 0x7fffffff;
+    for (int i = 0; i < B; ++i) m = min(m, counts[i]);
+    n = num_pts > 0 ? min(num_pts, m) : m;
+    n = max(n, min_pts);
+  }
+  if (b == 0 && tid == 0) *n_out = n;
+  if (n > cap_pts || (int64_t)n > n_interior) {
+    if (tid == 0) atomicMax(status, n > cap_pts ? 1 : 2);
+    return;
+  }
+  const int C = (int)min((int64_t)cand_count[b], cand_cap);
+  const int n_real = min(n, C);
+  const u64* keys = cand + (int64_t)b * cand_cap;
+
+  // ---- lower bound LB with n_real <= #{key >= LB} = G, G small enough to sort
+  u64 LB = 0;
+  int G = C;
+  if (C > kSortSmemKeys) {
+    if (tid == 0) { s_prefix = 0; s_above = 0; s_done = 0; }
+    int shift = 56;
+    for (int pass = 0; pass < 8; ++pass, shift -= 8) {
+      for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+      __syncthreads();
+      const u64 prefix = s_prefix;
+      for (int i = tid; i < C; i += kSelThreads) {
+        const u64 key = keys[i];
+        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = s_above;
+        int d = 255;
+        for (; d > 0; --d) {
+          if (cum + (int)s_hist[d] >= n_real) break;
+          cum += (int)s_hist[d];
+        }
+        s_prefix = (prefix << 8) | (u64)d;
+        s_above = cum;
+        s_G = cum + (int)s_hist[d];
+        if (s_G <= kSortSmemKeys || pass == 7) s_done = 1;
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+    LB = s_prefix << shift;
+    G = s_G;
+  }
+  const bool in_smem = G <= kSortSmemKeys;
+  int P = 2;
+  while (P < G) P <<= 1;
+  u64* buf = in_smem ? s_keys : sortbuf + (int64_t)b * sort_cap;
+  if (!in_smem && (int64_t)P > sort_cap) {
+    if (tid == 0) atomicMax(status, 3);
+    return;
+  }
+  // ---- gather keys >= LB
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < C; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    u64 key = 0;
+    bool take = false;
+    if (i < C) { key = keys[i]; take = key >= LB; }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) buf[base + __popc(bal & ((1u << lane) - 1u))] = key;
+    }
+  }
+  __syncthreads();
+  for (int i = G + tid; i < P; i += kSelThreads) buf[i] = 0;
+  __syncthreads();
+  bitonic_sort_desc(buf, P, s_keys, kSortSmemKeys, in_smem);
+
+  // ---- filler for rows [n_real, n): lowest-index pixels that are not winners
+  const int f = n - n_real;
+  if (f > 0) {
+    if (f > kFillMax || n > kFillBitmapWords * 32) {
+      if (tid == 0) atomicMax(status, 4);
+      return;
+    }
+    for (int i = tid; i < kFillBitmapWords; i += kSelThreads) s_bitmap[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_real; i += kSelThreads) {
+      const unsigned idx = 0xffffffffu - (unsigned)buf[i];
+      if (idx < (unsigned)n) atomicOr(&s_bitmap[idx >> 5], 1u << (idx & 31));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cnt = 0;
+      for (int wd = 0; wd < (n + 31) / 32 && cnt < f; ++wd) {
+        unsigned free_bits = ~s_bitmap[wd];
+        while (free_bits && cnt < f) {
+          const int bit = __ffs(free_bits) - 1;
+          free_bits &= free_bits - 1;
+          const int p = wd * 32 + bit;
+          if (p < n) s_fill[cnt++] = (unsigned)p;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- centroid, score, outputs (:243-247, :266-267)
+  const float stepx = 2.0f / (float)(W - 1), stepy = 2.0f / (float)(H - 1);
+  const float* img = score + b * sb;
+  for (int i = tid; i < n; i += kSelThreads) {
+    const unsigned idx = i < n_real ? 0xffffffffu - (unsigned)buf[i] : s_fill[i - n_real];
+    const int y0 = idx / wi, x0 = idx - y0 * wi;
+    float sx = 0.f, sy_ = 0.f, sw = 0.f, mx = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float gy = linspace_pm1(y0 + dy, H, stepy);
+      const float* row = img + (int64_t)(y0 + dy) * sy + x0;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float p = __ldg(row + dx);
+        const float gx = linspace_pm1(x0 + dx, W, stepx);
+        sx = __fadd_rn(sx, __fmul_rn(p, gx));
+        sy_ = __fadd_rn(sy_, __fmul_rn(p, gy));
+        sw = __fadd_rn(sw, p);
+        mx = fmaxf(mx, p);
+      }
+    }
+    const float wgt = __fdiv_rn(sw, 9.0f);
+    const int64_t o = (int64_t)b * cap_pts + i;
+    idx_out[o] = (int64_t)idx;
+    kps_out[2 * o + 0] = __fdiv_rn(__fdiv_rn(sx, 9.0f), wgt);
+    kps_out[2 * o + 1] = __fdiv_rn(__fdiv_rn(sy_, 9.0f), wgt);
+    kpscore_out[o] = mx;
+  }
+}
+
+static int check_common(const float* score, int B, int H, int W, int64_t sy) {
+  PF_CHECK_ARG(score != nullptr, "score is NULL");
+  PF_CHECK_ARG(B >= 1, "B must be >= 1 (got %d)", B);
+  PF_CHECK_ARG(H >= 4 && W >= 4, "score map must be at least 4x4 (got %dx%d)", H, W);
+  PF_CHECK_ARG((int64_t)(H - 2) * (W - 2) < 0xffffffffLL, "interior grid too large for 32-bit indices");
+  PF_CHECK_ARG(sy >= W, "row stride %lld smaller than W=%d", (long long)sy, W);
+  return 0;
+}
+
+}  // namespace posfeat
+
+using namespace posfeat;
+
+extern "C" size_t posfeat_detect_workspace_bytes(int B, int H, int W, int cap_pts) {
+  if (B < 1 || H < 4 || W < 4 || cap_pts < 1) return 0;
+  return carve(nullptr, B, H, W, cap_pts).total;
+}
+
+extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, int W, int64_t stride_b,
+                                             int64_t stride_y, int nms_mode, int radius, int thr_mode,
+                                             float thr, int32_t* counts, void* workspace, size_t ws_bytes,
+                                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_common(score, B, H, W, stride_y)) return e;
+  PF_CHECK_ARG(nms_mode == POSFEAT_NMS_NONE || nms_mode == POSFEAT_NMS_HARD, "unsupported nms_mode %d", nms_mode);
+  PF_CHECK_ARG(thr_mode >= POSFEAT_THR_NONE && thr_mode <= POSFEAT_THR_MEAN, "unsupported thr_mode %d", thr_mode);
+  PF_CHECK_ARG(radius >= 0 && radius <= 16, "nms radius %d outside [0,16]", radius);
+  PF_CHECK_ARG(nms_mode == POSFEAT_NMS_NONE || (radius <= H - 3 && radius <= W - 3),
+               "reflect padding needs radius < interior size");
+  PF_CHECK_ARG(counts && workspace, "counts/workspace is NULL");
+  DetectWs w = carve(workspace, B, H, W, 1);
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  const int r = nms_mode == POSFEAT_NMS_HARD ? radius : 0;
+
+  // zero the small header (cand_count, thr_val, red_sum, red_max, status) and counts
+  PF_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char*)w.cand - (char*)workspace), stream));
+  PF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B, stream));
+  const int has_thr = thr_mode != POSFEAT_THR_NONE;
+  if (has_thr) {
+    if (thr_mode == POSFEAT_THR_MAX || thr_mode == POSFEAT_THR_MEAN) {
+      dim3 g(64, B);
+      reduce_interior_kernel<<<g, 256, 0, stream>>>(score, H, W, stride_b, stride_y, w.red_sum, w.red_max);
+      PF_LAUNCH_CHECK("reduce_interior_kernel");
+    }
+    finalize_thr_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, thr_mode, thr, (int64_t)(H - 2) * (W - 2), w.red_sum,
+                                                              w.red_max, w.thr_val);
+    PF_LAUNCH_CHECK("finalize_thr_kernel");
+  }
+  const int pw = kTileW + 2 * r, ph = kTileH + 2 * r;
+  const size_t smem = sizeof(float) * (size_t)ph * (pw | 1);
+  dim3 grid((W - 2 + kTileW - 1) / kTileW, (H - 2 + kTileH - 1) / kTileH, B);
+  nms_candidates_kernel<<<grid, kNmsThreads, smem, stream>>>(score, H, W, stride_b, stride_y, nms_mode, r, has_thr,
+                                                             w.thr_val, counts, w.cand_count, w.cand, w.cand_cap);
+  PF_LAUNCH_CHECK("nms_candidates_kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W, int64_t stride_b, int64_t stride_y,
+                                         int num_pts, int min_pts, int cap_pts, int n_fixed, const int32_t* counts,
+                                         int32_t* n_out, int64_t* idx_out, float* kps_out, float* kpscore_out,
+                                         void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_common(score, B, H, W, stride_y)) return e;
+  PF_CHECK_ARG(cap_pts >= 1 && num_pts >= 0 && min_pts >= 0, "bad num_pts/min_pts/cap_pts");
+  PF_CHECK_ARG(n_fixed <= cap_pts, "n_fixed %d exceeds cap_pts %d", n_fixed, cap_pts);
+  PF_CHECK_ARG(counts && n_out && idx_out && kps_out && kpscore_out && workspace, "NULL output pointer");
+  DetectWs w = carve(workspace, B, H, W, cap_pts);
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  static bool attr_set = false;
+  const size_t smem = sizeof(u64) * kSortSmemKeys;
+  if (!attr_set) {
+    PF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
+                                                   counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,
+                                                   w.status, n_out, idx_out, kps_out, kpscore_out);
+  PF_LAUNCH_CHECK("select_kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_detect_topk_f32(const float* score, int B, int H, int W, int64_t stride_b, int64_t stride_y,
+                                       int nms_mode, int radius, int thr_mode, float thr, int num_pts, int min_pts,
+                                       int cap_pts, int32_t* counts, int32_t* n_out, int64_t* idx_out, float* kps_out,
+                                       float* kpscore_out, void* workspace, size_t ws_bytes, void* stream) {
+  size_t need = posfeat_detect_workspace_bytes(B, H, W, cap_pts);
+  if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", need, ws_bytes);
+  int e = posfeat_detect_candidates_f32(score, B, H, W, stride_b, stride_y, nms_mode, radius, thr_mode, thr, counts,
+                                        workspace, ws_bytes, stream);
+  if (e) return e;
+  return posfeat_detect_select_f32(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, -1, counts, n_out,
+                                   idx_out, kps_out, kpscore_out, workspace, ws_bytes, stream);
+}
+
+// Reads the device status flag of the last select (host sync on `stream`).
+extern "C" int posfeat_detect_status(void* workspace, int B, int H, int W, int cap_pts, void* stream_) {
+  DetectWs w = carve(workspace, B, H, W, cap_pts);
+  int32_t st = 0;
+  PF_CUDA(cudaMemcpyAsync(&st, w.status, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  PF_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  if (st == 0) return POSFEAT_OK;
+  const char* why = st == 1 ? "n exceeds cap_pts" : st == 2 ? "n exceeds the number of interior pixels (topk k out of range)"
+                    : st == 3 ? "sort buffer too small" : "too many filler rows";
+  return set_error(POSFEAT_EINVAL, "detect select failed on device: %s", why);
+}

@@ -1,0 +1,22 @@
+// Declarations shared by the matcher translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace posfeat {
+
+size_t simt_workspace_bytes(int N, int M);
+int mnn_simt(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
+             int32_t* nn21, void* ws, cudaStream_t stream);
+int run_rowbest_simt(const float* X, int NX, int64_t ldx, const float* Y, int NY, int64_t ldy, int D,
+                     int32_t* nn, void* ws, cudaStream_t stream);
+int launch_mutual_compact(const int32_t* nn12, const int32_t* nn21, int N, int M, int64_t* matches,
+                          int32_t* n_matches, cudaStream_t stream);
+
+// tensor-core path (mnn_tc.cu)
+bool tc_supported(int N, int M, int D);
+size_t tc_workspace_bytes(int N, int M);
+int mnn_tc(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
+           int32_t* nn21, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace posfeat

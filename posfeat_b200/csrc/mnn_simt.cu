@@ -1,0 +1,204 @@
+// Subsystem (3), exact path: mutual nearest neighbours without materialising
+// the N x M similarity matrix, CUDA-core kernel with float64 accumulation.
+//
+// Replaces mnn_matcher / mutual_nn_matcher (reference
+// evaluations/hpatches/evaluation.py:27-38, evaluations/aachen/matchers.py:5-13,
+// evaluations/ETH_local_feature/custom_matcher.py:5-13,
+// losses/preprocess_utils.py:795-803):
+//   sim = A @ B.T ; nn12 = argmax_j ; nn21 = argmax_i ; keep i with nn21[nn12[i]] == i.
+// Products of float32 numbers are exact in float64, so the accumulated value is
+// the real dot product to ~1e-16: the argmax is independent of summation order
+// and exact ties (duplicated descriptors) resolve to the first index like
+// torch.max.  This kernel is also the rescoring reference of the tensor-core path.
+#include "common.cuh"
+#include "mnn_common.cuh"
+
+namespace posfeat {
+
+constexpr int kBM = 64, kBN = 64, kBK = 32, kPitch = 66;
+
+// rows of X (64 per CTA) against a slice of the rows of Y; per-row best (value,
+// index) of the slice goes to part_val/part_idx[split][row].
+__global__ void __launch_bounds__(256)
+rowbest_simt_kernel(const float* __restrict__ X, int NX, int64_t ldx, const float* __restrict__ Y, int NY,
+                    int64_t ldy, int D, int cols_per_split, double* __restrict__ part_val,
+                    int32_t* __restrict__ part_idx) {
+  __shared__ __align__(16) double Xs[kBK][kPitch];
+  __shared__ __align__(16) double Ys[kBK][kPitch];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * kBM;
+  const int split = blockIdx.y;
+  const int c_begin = split * cols_per_split;
+  const int c_end = min(NY, c_begin + cols_per_split);
+
+  double bestv[4];
+  int besti[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
+
+  for (int col0 = c_begin; col0 < c_end; col0 += kBN) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < D; k0 += kBK) {
+      // 64 rows x 32 k per operand, coalesced along k
+      for (int e = tid; e < kBM * kBK; e += 256) {
+        const int r = e >> 5, k = e & 31;
+        float xv = 0.f, yv = 0.f;
+        if (k0 + k < D) {
+          if (row0 + r < NX) xv = __ldg(X + (int64_t)(row0 + r) * ldx + k0 + k);
+          if (col0 + r < c_end) yv = __ldg(Y + (int64_t)(col0 + r) * ldy + k0 + k);
+        }
+        Xs[k][r] = (double)xv;
+        Ys[k][r] = (double)yv;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < kBK; ++k) {
+        const double2 x01 = *reinterpret_cast<const double2*>(&Xs[k][ty * 4]);
+        const double2 x23 = *reinterpret_cast<const double2*>(&Xs[k][ty * 4 + 2]);
+        const double2 y01 = *reinterpret_cast<const double2*>(&Ys[k][tx * 4]);
+        const double2 y23 = *reinterpret_cast<const double2*>(&Ys[k][tx * 4 + 2]);
+        const double xs[4] = {x01.x, x01.y, x23.x, x23.y};
+        const double ys[4] = {y01.x, y01.y, y23.x, y23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(xs[i], ys[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = col0 + tx * 4 + j;
+        if (c < c_end && acc[i][j] > bestv[i]) { bestv[i] = acc[i][j]; besti[i] = c; }
+      }
+  }
+  // reduce over the 16 threads (tx) that share a row group: half-warp butterflies
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bestv[i], o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+      if (ov > bestv[i] || (ov == bestv[i] && oi < besti[i])) { bestv[i] = ov; besti[i] = oi; }
+    }
+    const int r = row0 + ty * 4 + i;
+    if (tx == 0 && r < NX) {
+      part_val[(int64_t)split * NX + r] = bestv[i];
+      part_idx[(int64_t)split * NX + r] = besti[i];
+    }
+  }
+}
+
+__global__ void rowbest_finalize_kernel(const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
+                                        int NX, int splits, int32_t* __restrict__ nn) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= NX) return;
+  double bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = 0; s < splits; ++s) {
+    const double v = part_val[(int64_t)s * NX + r];
+    const int i = part_idx[(int64_t)s * NX + r];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  nn[r] = bi == 0x7fffffff ? 0 : bi;   // all-NaN rows: torch.max also reports an index
+}
+
+// keep rows with nn21[nn12[i]] == i, ordered compaction (ascending i) by one CTA
+__global__ void __launch_bounds__(1024)
+mutual_compact_kernel(const int32_t* __restrict__ nn12, const int32_t* __restrict__ nn21, int N, int M,
+                      int64_t* __restrict__ matches, int32_t* __restrict__ n_matches) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < N; i0 += 1024) {
+    const int i = i0 + tid;
+    bool keep = false;
+    int j = 0;
+    if (i < N) {
+      j = nn12[i];
+      keep = j >= 0 && j < M && nn21[j] == i;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+      const int v = s_warp[lane];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      s_warp[lane] = inc - v;  // exclusive prefix over warps
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    if (keep) {
+      const int pos = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+      matches[2 * (int64_t)pos] = i;
+      matches[2 * (int64_t)pos + 1] = j;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+    __syncthreads();
+  }
+  if (tid == 0) *n_matches = s_base;
+}
+
+int launch_mutual_compact(const int32_t* nn12, const int32_t* nn21, int N, int M, int64_t* matches,
+                          int32_t* n_matches, cudaStream_t stream) {
+  mutual_compact_kernel<<<1, 1024, 0, stream>>>(nn12, nn21, N, M, matches, n_matches);
+  PF_LAUNCH_CHECK("mutual_compact_kernel");
+  return POSFEAT_OK;
+}
+
+static int choose_splits(int NX, int NY) {
+  const int row_blocks = (NX + kBM - 1) / kBM;
+  const int col_tiles = (NY + kBN - 1) / kBN;
+  int want = (2 * sm_count() + row_blocks - 1) / row_blocks;
+  if (want < 1) want = 1;
+  if (want > col_tiles) want = col_tiles;
+  if (want > 64) want = 64;
+  return want;
+}
+
+size_t simt_workspace_bytes(int N, int M) {
+  // partial (value, index) per split and row, both directions (splits <= 64)
+  const size_t per = sizeof(double) + sizeof(int32_t);
+  return align_up((size_t)64 * N * per, 256) + align_up((size_t)64 * M * per, 256) + 512;
+}
+
+int run_rowbest_simt(const float* X, int NX, int64_t ldx, const float* Y, int NY, int64_t ldy, int D,
+                     int32_t* nn, void* ws, cudaStream_t stream) {
+  const int splits = choose_splits(NX, NY);
+  const int col_tiles = (NY + kBN - 1) / kBN;
+  const int cols_per_split = ((col_tiles + splits - 1) / splits) * kBN;
+  const int used = (NY + cols_per_split - 1) / cols_per_split;
+  double* pv = (double*)ws;
+  int32_t* pi = (int32_t*)((char*)ws + align_up(sizeof(double) * (size_t)64 * NX, 256));
+  dim3 grid((NX + kBM - 1) / kBM, used);
+  rowbest_simt_kernel<<<grid, 256, 0, stream>>>(X, NX, ldx, Y, NY, ldy, D, cols_per_split, pv, pi);
+  PF_LAUNCH_CHECK("rowbest_simt_kernel");
+  rowbest_finalize_kernel<<<(NX + 255) / 256, 256, 0, stream>>>(pv, pi, NX, used, nn);
+  PF_LAUNCH_CHECK("rowbest_finalize_kernel");
+  return POSFEAT_OK;
+}
+
+int mnn_simt(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
+             int32_t* nn21, void* ws, cudaStream_t stream) {
+  char* w = (char*)ws;
+  const size_t per = sizeof(double) + sizeof(int32_t);
+  if (int e = run_rowbest_simt(A, N, lda, Bm, M, ldb, D, nn12, w, stream)) return e;
+  w += align_up((size_t)64 * N * per, 256) + 256;
+  return run_rowbest_simt(Bm, M, ldb, A, N, lda, D, nn21, w, stream);
+}
+
+}  // namespace posfeat

@@ -1,0 +1,193 @@
+// Subsystem (2): bilinear descriptor sampling fused with L2 normalisation.
+//
+// Replaces sample_feat_by_coord, reference losses/preprocess_utils.py:40-53:
+//   F.grid_sample(x, coord_n[:, :, None], bilinear, padding 'zeros',
+//                 align_corners=False)  ->  F.normalize(dim=C)  -> [B, n, C].
+// One warp per keypoint.  The descriptor map is addressed through element
+// strides, so NCHW (the reference layout) and NHWC (channels_last backbones)
+// use the same entry point; with unit channel stride the four taps are read
+// as 128-bit vectors (4 x 512 B per keypoint at D=128).  Gather-bound: the
+// algorithmic traffic is n*(4*D*4 + D*4 + 8) bytes.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace posfeat {
+
+struct Taps {
+  int x0, y0;
+  float w00, w01, w10, w11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1), zero when outside
+  bool in00, in01, in10, in11;
+};
+
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w) {
+  // grid_sampler_unnormalize (align_corners=False): ((g + 1) * size - 1) / 2
+  // (explicit _rn ops: no FMA contraction, same roundings as ATen's CUDA sampler)
+  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 0.5f);
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 0.5f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  Taps t;
+  // clamp before the int conversion so absurd coordinates cannot overflow
+  t.x0 = (int)fminf(fmaxf(fx, -2.f), (float)w);
+  t.y0 = (int)fminf(fmaxf(fy, -2.f), (float)h);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+  const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const bool xin0 = t.x0 >= 0 && t.x0 < w, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < w;
+  const bool yin0 = t.y0 >= 0 && t.y0 < h, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < h;
+  t.in00 = xin0 && yin0; t.in01 = xin1 && yin0; t.in10 = xin0 && yin1; t.in11 = xin1 && yin1;
+  t.w00 = __fmul_rn(wy0, wx0); t.w01 = __fmul_rn(wy0, wx1);
+  t.w10 = __fmul_rn(wy1, wx0); t.w11 = __fmul_rn(wy1, wx1);
+  return t;
+}
+
+// generic strides: lane handles channels lane, lane+32, ...
+template <int CPL>  // channels per lane (D <= 32*CPL)
+__global__ void __launch_bounds__(256)
+sample_strided_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc,
+                      int64_t sy, int64_t sx, const float* __restrict__ coord, int n,
+                      const int32_t* __restrict__ n_valid, int do_norm, float* __restrict__ out,
+                      __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nv = n_valid ? min(*n_valid, n) : n;
+  if (p >= nv) return;
+  const float2 g = *reinterpret_cast<const float2*>(coord + ((int64_t)b * n + p) * 2);
+  const Taps t = make_taps(g.x, g.y, h, w);
+  const float* base = fmap + b * sb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+  float v[CPL];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    if (c < D) {
+      const float* pc = base + (int64_t)c * sc;
+      if (t.in00) a00 = __ldg(pc);
+      if (t.in01) a01 = __ldg(pc + sx);
+      if (t.in10) a10 = __ldg(pc + sy);
+      if (t.in11) a11 = __ldg(pc + sy + sx);
+    }
+    v[j] = a00 * t.w00 + a01 * t.w01 + a10 * t.w10 + a11 * t.w11;
+    ss += v[j] * v[j];
+  }
+  float inv = 1.f;
+  if (do_norm) {
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  float* o = out + ((int64_t)b * n + p) * D;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    if (c < D) {
+      const float r = do_norm ? v[j] * inv : v[j];
+      o[c] = r;
+      if (out_bf16) out_bf16[((int64_t)b * n + p) * D + c] = __float2bfloat16_rn(r);
+    }
+  }
+}
+
+// unit channel stride (NHWC), D % 4 == 0, 16-byte aligned pixels: float4 taps
+template <int VPL>  // float4 per lane (D <= 128*VPL)
+__global__ void __launch_bounds__(256)
+sample_nhwc_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sy,
+                   int64_t sx, const float* __restrict__ coord, int n,
+                   const int32_t* __restrict__ n_valid, int do_norm, float* __restrict__ out,
+                   __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nv = n_valid ? min(*n_valid, n) : n;
+  if (p >= nv) return;
+  const float2 g = *reinterpret_cast<const float2*>(coord + ((int64_t)b * n + p) * 2);
+  const Taps t = make_taps(g.x, g.y, h, w);
+  const float* base = fmap + b * sb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+  float4 v[VPL];
+  float ss = 0.f;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    float4 a00 = z, a01 = z, a10 = z, a11 = z;
+    if (c < D) {
+      const float* pc = base + c;
+      if (t.in00) a00 = __ldg(reinterpret_cast<const float4*>(pc));
+      if (t.in01) a01 = __ldg(reinterpret_cast<const float4*>(pc + sx));
+      if (t.in10) a10 = __ldg(reinterpret_cast<const float4*>(pc + sy));
+      if (t.in11) a11 = __ldg(reinterpret_cast<const float4*>(pc + sy + sx));
+    }
+    float4 r;
+    r.x = a00.x * t.w00 + a01.x * t.w01 + a10.x * t.w10 + a11.x * t.w11;
+    r.y = a00.y * t.w00 + a01.y * t.w01 + a10.y * t.w10 + a11.y * t.w11;
+    r.z = a00.z * t.w00 + a01.z * t.w01 + a10.z * t.w10 + a11.z * t.w11;
+    r.w = a00.w * t.w00 + a01.w * t.w01 + a10.w * t.w10 + a11.w * t.w11;
+    v[j] = r;
+    ss += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+  }
+  float inv = 1.f;
+  if (do_norm) {
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  float* o = out + ((int64_t)b * n + p) * D;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < D) {
+      float4 r = v[j];
+      if (do_norm) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+      *reinterpret_cast<float4*>(o + c) = r;
+      if (out_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&lo);
+        pk.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(out_bf16 + ((int64_t)b * n + p) * D + c) = pk;
+      }
+    }
+  }
+}
+
+}  // namespace posfeat
+
+using namespace posfeat;
+
+extern "C" int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc,
+                                         int64_t sy, int64_t sx, const float* coord_n, int n,
+                                         const int32_t* n_valid, int do_norm, float* out, void* out_bf16,
+                                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(fmap && coord_n && out, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && D >= 1 && h >= 1 && w >= 1 && n >= 0, "bad shape B=%d D=%d h=%d w=%d n=%d", B, D, h, w, n);
+  PF_CHECK_ARG(D <= 512, "D=%d > 512 not supported", D);
+  PF_CHECK_ARG(B <= 65535, "B=%d exceeds the grid limit 65535", B);
+  if (n == 0) return POSFEAT_OK;
+  const int warps = 8;
+  dim3 grid((n + warps - 1) / warps, B), block(32 * warps);
+  __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
+  const bool vec = sc == 1 && D % 4 == 0 && sx % 4 == 0 && sy % 4 == 0 && sb % 4 == 0 &&
+                   ((uintptr_t)fmap % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                   (!ob || (uintptr_t)ob % 8 == 0);
+  if (vec) {
+    if (D <= 128)
+      sample_nhwc_kernel<1><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else if (D <= 256)
+      sample_nhwc_kernel<2><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else
+      sample_nhwc_kernel<4><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+  } else {
+    if (D <= 32)
+      sample_strided_kernel<1><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else if (D <= 64)
+      sample_strided_kernel<2><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else if (D <= 128)
+      sample_strided_kernel<4><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else if (D <= 256)
+      sample_strided_kernel<8><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+    else
+      sample_strided_kernel<16><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+  }
+  PF_LAUNCH_CHECK("sample kernel");
+  return POSFEAT_OK;
+}

@@ -1,0 +1,49 @@
+"""Comparison helpers shared by the oracle tests and the GPU parity tests."""
+import numpy as np
+
+
+def check_detect(ref_key, ref_idx, ref_kps, ref_score, ref_counts, kps, sc, idx, counts):
+    """(kps, sc, idx, counts) against a reference run on the same map.
+
+    ref_key[b] is the flattened selection key (nms_mask*score) the reference
+    feeds to topk.  Keypoint indices must match exactly where the selected
+    score is unique, as sets inside equal-score groups above the cut-off, and
+    the score sequence must be identical (torch.topk leaves tie order open;
+    key == 0 entries are filler that topk picks arbitrarily).
+    """
+    assert kps.shape == ref_kps.shape, (kps.shape, ref_kps.shape)
+    np.testing.assert_array_equal(np.asarray(counts, dtype=np.int64), np.asarray(ref_counts, dtype=np.int64))
+    sc = sc.reshape(sc.shape[0], -1)
+    ref_score = ref_score.reshape(ref_score.shape[0], -1)
+    for b in range(ref_idx.shape[0]):
+        rv = ref_key[b][ref_idx[b]]
+        ov = ref_key[b][idx[b]]
+        np.testing.assert_array_equal(rv, ov)
+        assert len(set(idx[b].tolist())) == idx.shape[1]
+        real = rv > 0
+        above = real & (rv > rv[-1])
+        assert set(ref_idx[b][above].tolist()) == set(idx[b][above].tolist())
+        vals, cnt = np.unique(rv, return_counts=True)
+        uniq = np.isin(rv, vals[cnt == 1]) & real
+        np.testing.assert_array_equal(ref_idx[b][uniq], idx[b][uniq])
+        o_r = np.argsort(ref_idx[b][above], kind="stable")
+        o_o = np.argsort(idx[b][above], kind="stable")
+        np.testing.assert_allclose(kps[b][above][o_o], ref_kps[b][above][o_r], rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(sc[b][above][o_o], ref_score[b][above][o_r])
+        for v in vals[cnt > 1]:
+            if v > 0:
+                assert np.all(np.diff(idx[b][rv == v]) > 0), "tie policy: index ascending"
+
+
+def check_mnn_near_tie(a, b, got, want, tol=1e-6):
+    """Match lists must be identical; if they differ, every disagreeing row or
+    column must be a genuine near tie of the exact (float64) similarity."""
+    if got.shape == want.shape and np.array_equal(got, want):
+        return
+    sim = a.astype(np.float64) @ b.astype(np.float64).T
+    gs, ws = {tuple(x) for x in got.tolist()}, {tuple(x) for x in want.tolist()}
+    for (i, j) in gs ^ ws:
+        top_r = np.sort(sim[i])[-2:]
+        top_c = np.sort(sim[:, j])[-2:]
+        assert (top_r[1] - top_r[0] < tol) or (top_c[1] - top_c[0] < tol), \
+            f"pair {(i, j)} differs without a near tie: row gap {top_r[1]-top_r[0]}, col gap {top_c[1]-top_c[0]}"

@@ -35,3 +35,5 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,0 +1,137 @@
+"""GPU parity: descriptor sampling + L2 norm, and mutual-NN matching."""
+import numpy as np
+import pytest
+import torch
+
+from _checks import check_mnn_near_tie
+from oracle import posfeat_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-5, atol=1e-6)   # north_star: descriptors within 1e-5 relative at fp32
+
+
+def test_sample_golden(golden):
+    import posfeat_b200 as P
+    g = golden("sample")
+    x = torch.from_numpy(g["x"]).cuda()
+    c = torch.from_numpy(g["coord"]).cuda()
+    np.testing.assert_allclose(P.sample_feat_by_coord(x, c, False).cpu().numpy(), g["raw"], **TOL)
+    np.testing.assert_allclose(P.sample_feat_by_coord(x, c, True).cpu().numpy(), g["normed"], **TOL)
+    x128 = torch.from_numpy(g["x128"]).cuda()
+    c128 = torch.from_numpy(g["coord128"]).cuda()
+    np.testing.assert_allclose(P.sample_feat_by_coord(x128, c128, True).cpu().numpy(), g["normed128"], **TOL)
+    # channels_last (NHWC) input takes the vectorised kernel and must agree
+    xcl = x128.contiguous(memory_format=torch.channels_last)
+    np.testing.assert_allclose(P.sample_feat_by_coord(xcl, c128, True).cpu().numpy(), g["normed128"], **TOL)
+
+
+@pytest.mark.parametrize("b,c,h,w,n", [(1, 128, 224, 300, 8192), (2, 128, 120, 160, 4096), (1, 64, 33, 47, 1000),
+                                       (1, 20, 9, 11, 77), (1, 256, 16, 16, 300)])
+def test_sample_vs_oracle(b, c, h, w, n):
+    import posfeat_b200 as P
+    g = torch.Generator().manual_seed(c * 1000 + n)
+    x = torch.randn(b, c, h, w, generator=g)
+    coord = torch.rand(b, n, 2, generator=g) * 2.04 - 1.02
+    want = O.sample_feat_by_coord(x.numpy(), coord.numpy(), True)
+    got = P.sample_feat_by_coord(x.cuda(), coord.cuda(), True)
+    np.testing.assert_allclose(got.cpu().numpy(), want, **TOL)
+    got_cl = P.sample_feat_by_coord(x.cuda().contiguous(memory_format=torch.channels_last), coord.cuda(), True)
+    np.testing.assert_allclose(got_cl.cpu().numpy(), want, **TOL)
+    raw = P.sample_feat_by_coord(x.cuda(), coord.cuda(), False).cpu().numpy()
+    np.testing.assert_allclose(raw, O.sample_feat_by_coord(x.numpy(), coord.numpy(), False), **TOL)
+    nrm = np.linalg.norm(got.cpu().numpy(), axis=-1)
+    assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
+
+
+def test_sample_empty_and_bf16():
+    import posfeat_b200 as P
+    x = torch.randn(1, 128, 8, 8, device="cuda")
+    assert P.sample_feat_by_coord(x, torch.zeros(1, 0, 2, device="cuda"), True).shape == (1, 0, 128)
+    c = torch.rand(1, 50, 2, device="cuda") * 2 - 1
+    f, fb = P.sample_l2norm(x, c, True, want_bf16=True)
+    assert torch.equal(fb, f.to(torch.bfloat16))
+
+
+ALGOS = [1, 2]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_mnn_golden(golden, algo):
+    import posfeat_b200 as P
+    g = golden("mnn")
+    a, b = torch.from_numpy(g["a"]).cuda(), torch.from_numpy(g["b"]).cuda()
+    m = P.mnn_matcher(a, b, algo=algo)
+    assert m.dtype == np.int64 and m.ndim == 2 and m.shape[1] == 2
+    check_mnn_near_tie(g["a"], g["b"], m, g["mnn"])
+    ad, bd = torch.from_numpy(g["ad"]).cuda(), torch.from_numpy(g["bd"]).cuda()
+    np.testing.assert_array_equal(P.mnn_matcher(ad, bd, algo=algo), g["mnn_dup"])   # first-index tie rule
+    np.testing.assert_array_equal(P.mnn_matcher(bd, ad, algo=algo), g["mnn_dup_t"])
+    from posfeat_b200.matchers import mutual_nn_matcher
+    check_mnn_near_tie(g["a"], g["b"], mutual_nn_matcher(a, b), g["mutual_nn"])
+
+
+def unit_desc(n, d, seed, base=None, noise=0.5):
+    g = torch.Generator().manual_seed(seed)
+    if base is None:
+        x = torch.randn(n, d, generator=g)
+    else:
+        perm = torch.randperm(base.shape[0], generator=g)[:n]
+        x = base[perm] + noise * torch.randn(n, d, generator=g)
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("N,M,D", [(1500, 1300, 128), (1024, 1024, 128), (4096, 4096, 128), (777, 2049, 128),
+                                   (1, 5, 128), (130, 1, 128), (300, 200, 64), (257, 129, 100)])
+def test_mnn_vs_oracle(algo, N, M, D):
+    import posfeat_b200 as P
+    if algo == 2 and D != 128:
+        with pytest.raises(Exception):
+            P.mnn_matcher(torch.zeros(N, D, device="cuda"), torch.zeros(M, D, device="cuda"), algo=2)
+        return
+    a = unit_desc(N, D, 1)
+    b = unit_desc(M, D, 2, base=a if M <= N else None)
+    want, nn12, nn21 = O.mnn_matcher(a.numpy(), b.numpy(), exact=True, return_nn=True)
+    matches, nm, g12, g21 = P.mnn_match(a.cuda(), b.cuda(), algo=algo)
+    got = matches[:int(nm.item())].cpu().numpy()
+    check_mnn_near_tie(a.numpy(), b.numpy(), got, want)
+    # the exact (float64) argmax is reproduced index for index
+    assert (g12.cpu().numpy() != nn12).sum() <= 1 and (g21.cpu().numpy() != nn21).sum() <= 1
+    assert np.all(np.diff(got[:, 0]) > 0)
+
+
+def test_mnn_8k_properties():
+    """BASELINE size (8192 x 8192 x 128): result is a partial permutation,
+    consistent with nn12/nn21, and symmetric under swapping the operands."""
+    import posfeat_b200 as P
+    a = unit_desc(8192, 128, 11).cuda()
+    b = unit_desc(8192, 128, 12, base=a.cpu()).cuda()
+    m, nm, nn12, nn21 = P.mnn_match(a, b)
+    k = int(nm.item())
+    m = m[:k].cpu().numpy()
+    assert k > 2000
+    assert len(np.unique(m[:, 0])) == k and len(np.unique(m[:, 1])) == k
+    n12, n21 = nn12.cpu().numpy(), nn21.cpu().numpy()
+    assert np.array_equal(n12[m[:, 0]], m[:, 1]) and np.array_equal(n21[m[:, 1]], m[:, 0])
+    mt = P.mnn_matcher(b, a)
+    assert {tuple(x) for x in m.tolist()} == {(j, i) for i, j in mt.tolist()}
+    # both algorithms agree
+    m1 = P.mnn_matcher(a, b, algo=1)
+    np.testing.assert_array_equal(m1, m)
+
+
+def test_mnn_host_entry_and_errors():
+    import posfeat_b200 as P
+    a, b = unit_desc(600, 128, 3), unit_desc(500, 128, 4)
+    want = O.mnn_matcher(a.numpy(), b.numpy(), exact=True)
+    check_mnn_near_tie(a.numpy(), b.numpy(), P.mnn_matcher(a, b), want)      # CPU tensors -> host entry point
+    with pytest.raises(IndexError):
+        P.mnn_matcher(torch.zeros(0, 128, device="cuda"), torch.zeros(4, 128, device="cuda"))
+    with pytest.raises(ValueError):
+        P.mnn_matcher(torch.zeros(3, 128, device="cuda"), torch.zeros(4, 64, device="cuda"))
+    # strided rows (a view into a wider matrix)
+    v = torch.nn.functional.normalize(torch.randn(300, 128, device="cuda"), dim=1)
+    wide = torch.zeros(300, 256, device="cuda")
+    wide[:, :128] = v
+    assert wide[:, :128].stride(0) == 256
+    np.testing.assert_array_equal(P.mnn_matcher(wide[:, :128], v), P.mnn_matcher(v, v))

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import posfeat_oracle as O
+from _checks import check_detect
 
 DETECT_CASES = ["r1_abs", "r3_abs", "r2_max", "r1_mean", "r1_nothr", "nonms_abs",
                 "ties_r1", "ties_r2", "few", "const", "odd_r1", "odd_r5"]
@@ -14,39 +15,8 @@ def _cfg(g, name):
 
 
 def check_detect_against(g, name, kps, sc, idx, counts):
-    """Shared checker: (kps, sc, idx, counts) vs the reference fixture.
-
-    Keypoint indices must match exactly where the reference's scores are
-    distinct and as sets inside equal-score groups (torch.topk leaves that
-    order open); entries whose key is 0 are filler chosen arbitrarily by topk.
-    """
-    rkey, ridx = g[name + "/key"], g[name + "/idx"]
-    assert kps.shape == g[name + "/kps"].shape
-    np.testing.assert_array_equal(np.asarray(counts, dtype=np.float64),
-                                  g[name + "/count"].astype(np.float64))
-    for b in range(ridx.shape[0]):
-        rv = rkey[b][ridx[b]]
-        ov = rkey[b][idx[b]]
-        np.testing.assert_array_equal(rv, ov)           # same score sequence
-        real = rv > 0
-        above = real & (rv > rv[-1])        # the cut-off group may be split differently
-        assert set(ridx[b][above]) == set(idx[b][above])
-        assert len(set(idx[b].tolist())) == idx.shape[1]
-        # exact position match wherever the score is unique in the list
-        vals, cnt = np.unique(rv, return_counts=True)
-        uniq = np.isin(rv, vals[cnt == 1]) & real
-        np.testing.assert_array_equal(ridx[b][uniq], idx[b][uniq])
-        # centroid / score of each selected pixel: compare through the index
-        order_r = np.argsort(ridx[b][above], kind="stable")
-        order_o = np.argsort(idx[b][above], kind="stable")
-        np.testing.assert_allclose(kps[b][above][order_o], g[name + "/kps"][b][above][order_r],
-                                   rtol=1e-5, atol=2e-6)
-        np.testing.assert_array_equal(sc[b][above][order_o], g[name + "/score"][b][above][order_r])
-        # our tie policy: index ascending inside an equal-score group
-        for v in vals[cnt > 1]:
-            if v > 0:
-                grp = idx[b][rv == v]
-                assert np.all(np.diff(grp) > 0)
+    check_detect(g[name + "/key"], g[name + "/idx"], g[name + "/kps"], g[name + "/score"],
+                 g[name + "/count"], kps, sc, idx, counts)
 
 
 @pytest.mark.parametrize("name", DETECT_CASES)
