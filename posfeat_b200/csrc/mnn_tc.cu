@@ -1,10 +1,566 @@
-// placeholder until the tcgen05 kernel lands
+// Subsystem (3), tensor-core path: mutual nearest neighbours on tcgen05 (sm_100a).
+//
+// Replaces sim = A @ B.T; max(dim=1); max(dim=0) of the reference matchers
+// (evaluations/hpatches/evaluation.py:27-38, losses/preprocess_utils.py:795-803)
+// without ever writing the N x M similarity matrix.
+//
+// Per direction (rows of X against all rows of Y; run for (A,B) and (B,A)):
+//   * operands are rounded once to bf16 (prep kernel, also row norms);
+//   * a persistent, warp-specialised kernel walks work units (256 rows of X,
+//     a range of 128-row Y tiles): warp 0 feeds shared memory with TMA
+//     (SWIZZLE_128B boxes), warp 1 issues tcgen05.mma (M=128, N=128, K=16, bf16,
+//     fp32 accumulators in TMEM, two accumulator stages = all 512 columns),
+//     warps 4..11 drain TMEM with tcgen05.ld and keep, per row, the running
+//     approximate maximum and the list of 16-column chunks whose maximum is
+//     within delta of it;
+//   * delta = 2*eps with eps = 2^-7 |x||y| bounding the bf16 rounding error of one
+//     similarity, so the true argmax is always inside a recorded chunk;
+//   * a rescoring kernel recomputes the surviving chunks exactly (float32
+//     operands, float64 accumulation -- the same value the exact SIMT kernel
+//     uses) and takes the argmax with the first-index tie rule.
+// Rows whose record list overflows are rescanned exactly, so the result never
+// depends on the approximation.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "mnn_common.cuh"
+
 namespace posfeat {
-bool tc_supported(int, int, int) { return false; }
-size_t tc_workspace_bytes(int, int) { return 0; }
-int mnn_tc(const float*, int, int64_t, const float*, int, int64_t, int, int32_t*, int32_t*, void*, size_t, cudaStream_t) {
-  return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher not built");
+
+constexpr int kD = 128;
+constexpr int kXRows = 256;   // rows of X per work unit (two M=128 MMA tiles)
+constexpr int kYRows = 128;   // rows of Y per tile (MMA N)
+constexpr int kStages = 4;    // Y ring depth
+constexpr int kSubBytes = 128 * 64 * 2;  // one [128 rows x 64 K] bf16 swizzled sub-tile
+constexpr int kRecCap = 16;
+constexpr int kMaxSplits = 16;
+constexpr int kTcThreads = 384;
+constexpr float kDeltaScale = 0.016f;  // 2 * (2^-7 + slack) : see header comment
+
+constexpr int kSmemX = 0;
+constexpr int kSmemY = 4 * kSubBytes;
+constexpr int kSmemBar = kSmemY + kStages * 2 * kSubBytes;
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kSmemAlloc = kSmemTotal + 1024;
+
+struct DirParams {
+  const float* xnorm;          // [NXpad] row norms of X (float32 data)
+  const unsigned* ymax_bits;   // max row norm of Y (float bits)
+  float* rowmax;               // [splits][NXpad]
+  int* reccnt;                 // [splits][NXpad]
+  uint2* rec;                  // [splits][NXpad][kRecCap] (chunk max bits, first column)
+  int NX, NY, NXpad;
+  int splits, tiles_per_split, y_tiles;
+};
+struct TcParams {
+  DirParams d[2];
+  int units0, units_total;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("posfeat mnn_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kYRows >> 3) << 17) | ((128u >> 4) << 24);
+
+struct UnitInfo {
+  int dir, rb, sp, t0, t1;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int u) {
+  UnitInfo q;
+  q.dir = u >= p.units0 ? 1 : 0;
+  const int v = q.dir ? u - p.units0 : u;
+  const DirParams& d = p.d[q.dir];
+  q.rb = v / d.splits;
+  q.sp = v - q.rb * d.splits;
+  q.t0 = q.sp * d.tiles_per_split;
+  q.t1 = min(d.y_tiles, q.t0 + d.tiles_per_split);
+  return q;
+}
+
+// one 16-column chunk of the accumulator row owned by this thread
+__device__ __forceinline__ void process_chunk(const uint32_t* v, int col0, int NY, float delta, float& run, int& cnt,
+                                              uint2* __restrict__ myrec) {
+  if (col0 >= NY) return;  // warp uniform
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (col0 + 16 > NY) {  // ragged last chunk: padding rows of Y are zeros, mask them
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j >= NY) f[j] = -INFINITY;
+  }
+  const float m0 = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3]));
+  const float m1 = fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7]));
+  const float m2 = fmaxf(fmaxf(f[8], f[9]), fmaxf(f[10], f[11]));
+  const float m3 = fmaxf(fmaxf(f[12], f[13]), fmaxf(f[14], f[15]));
+  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  run = fmaxf(run, m);
+  if (m >= run - delta) {
+    if (cnt < kRecCap) myrec[cnt] = make_uint2(__float_as_uint(m), (unsigned)col0);
+    ++cnt;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = sbase + kSmemBar;
+  const uint32_t bar_x_full = bar0, bar_x_empty = bar0 + 8;
+  const uint32_t bar_y_full = bar0 + 16, bar_y_empty = bar_y_full + 8 * kStages;
+  const uint32_t bar_acc_full = bar_y_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t tmem_slot = bar_acc_empty + 16;
+  unsigned char* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemBar + 16 + 16 * kStages + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_x_full, 1);
+    mbar_init(bar_x_empty, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_y_full + 8 * s, 1);
+      mbar_init(bar_y_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, 8);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int ys = 0, yph = 0, it = 0;
+    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++it) {
+      const UnitInfo q = decode_unit(p, u);
+      const CUtensorMap* xmap = q.dir ? &mapB : &mapA;
+      const CUtensorMap* ymap = q.dir ? &mapA : &mapB;
+      mbar_wait(bar_x_empty, (it & 1) ^ 1);
+      mbar_expect_tx(bar_x_full, 4 * kSubBytes);
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh)
+          tma_load_2d(sbase + kSmemX + (m * 2 + kh) * kSubBytes, xmap, kh * 64, q.rb * kXRows + m * 128, bar_x_full);
+      for (int t = q.t0; t < q.t1; ++t) {
+        mbar_wait(bar_y_empty + 8 * ys, yph ^ 1);
+        mbar_expect_tx(bar_y_full + 8 * ys, 2 * kSubBytes);
+        tma_load_2d(sbase + kSmemY + (ys * 2 + 0) * kSubBytes, ymap, 0, t * kYRows, bar_y_full + 8 * ys);
+        tma_load_2d(sbase + kSmemY + (ys * 2 + 1) * kSubBytes, ymap, 64, t * kYRows, bar_y_full + 8 * ys);
+        if (++ys == kStages) { ys = 0; yph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer (single thread) =====
+    int ys = 0, yph = 0, as = 0, aph = 0, it = 0;
+    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++it) {
+      const UnitInfo q = decode_unit(p, u);
+      mbar_wait(bar_x_full, it & 1);
+      for (int t = q.t0; t < q.t1; ++t) {
+        mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);
+        mbar_wait(bar_y_full + 8 * ys, yph);
+        tc_fence_after();
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + m * 128);
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const uint64_t ad = make_sw128_desc(sbase + kSmemX + (m * 2 + kh) * kSubBytes);
+            const uint64_t bd = make_sw128_desc(sbase + kSmemY + (ys * 2 + kh) * kSubBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc, (kh | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(bar_y_empty + 8 * ys);     // smem stage may be refilled once these MMAs retire
+        tc_commit(bar_acc_full + 8 * as);    // accumulator ready for the epilogue
+        if (t == q.t1 - 1) tc_commit(bar_x_empty);
+        if (++ys == kStages) { ys = 0; yph ^= 1; }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> running max + candidate chunks =====
+    const int wg = (warp - 4) >> 2, quarter = warp & 3;
+    const int row_in_block = wg * 128 + quarter * 32 + lane;
+    int as = 0, aph = 0;
+    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+      const UnitInfo q = decode_unit(p, u);
+      const DirParams& d = p.d[q.dir];
+      const int row = q.rb * kXRows + row_in_block;
+      const float delta = kDeltaScale * d.xnorm[row] * __uint_as_float(*d.ymax_bits);
+      const size_t slot = (size_t)q.sp * d.NXpad + row;
+      uint2* myrec = d.rec + slot * kRecCap;
+      float run = -INFINITY;
+      int cnt = 0;
+      for (int t = q.t0; t < q.t1; ++t) {
+        mbar_wait(bar_acc_full + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + wg * 128) + ((uint32_t)(quarter * 32) << 16);
+        const int c0 = t * kYRows;
+        uint32_t va[32], vb[32];
+        tc_ld32(taddr, va);
+        tc_wait_ld();
+        tc_ld32(taddr + 32, vb);
+        process_chunk(va, c0, d.NY, delta, run, cnt, myrec);
+        process_chunk(va + 16, c0 + 16, d.NY, delta, run, cnt, myrec);
+        tc_wait_ld();
+        tc_ld32(taddr + 64, va);
+        process_chunk(vb, c0 + 32, d.NY, delta, run, cnt, myrec);
+        process_chunk(vb + 16, c0 + 48, d.NY, delta, run, cnt, myrec);
+        tc_wait_ld();
+        tc_ld32(taddr + 96, vb);
+        process_chunk(va, c0 + 64, d.NY, delta, run, cnt, myrec);
+        process_chunk(va + 16, c0 + 80, d.NY, delta, run, cnt, myrec);
+        tc_wait_ld();
+        process_chunk(vb, c0 + 96, d.NY, delta, run, cnt, myrec);
+        process_chunk(vb + 16, c0 + 112, d.NY, delta, run, cnt, myrec);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      d.rowmax[slot] = run;
+      d.reccnt[slot] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ prep
+// float32 rows -> bf16 [rows_pad, 128] (zero padded), row norms, max norm
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ X, int NX, int64_t ldx, int NXpad, __nv_bfloat16* __restrict__ Xb,
+               float* __restrict__ xnorm, unsigned* __restrict__ max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= NXpad) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < NX) {
+    const float* src = X + (int64_t)row * ldx + lane * 4;
+    v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+  }
+  float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss) * 1.0000005f;  // never under-estimate the norm
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<unsigned*>(&lo);
+  pk.y = *reinterpret_cast<unsigned*>(&hi);
+  *reinterpret_cast<uint2*>(Xb + (int64_t)row * kD + lane * 4) = pk;
+  if (lane == 0) {
+    xnorm[row] = nrm;
+    if (row < NX) atomicMax(max_bits, __float_as_uint(nrm));
+  }
+}
+
+// ------------------------------------------------------------------ rescoring
+// One warp per row of X: exact (float64) similarity of the candidate chunks.
+__global__ void __launch_bounds__(256)
+tc_rescore_kernel(const DirParams d, const float* __restrict__ X, int64_t ldx, const float* __restrict__ Y,
+                  int64_t ldy, int32_t* __restrict__ nn) {
+  __shared__ float xs[8][kD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + w;
+  if (row >= d.NX) return;
+  {
+    const float* src = X + (int64_t)row * ldx + lane * 4;
+    xs[w][lane * 4 + 0] = __ldg(src);
+    xs[w][lane * 4 + 1] = __ldg(src + 1);
+    xs[w][lane * 4 + 2] = __ldg(src + 2);
+    xs[w][lane * 4 + 3] = __ldg(src + 3);
+  }
+  __syncwarp();
+  float F = -INFINITY;
+  for (int s = 0; s < d.splits; ++s) F = fmaxf(F, d.rowmax[(size_t)s * d.NXpad + row]);
+  const float thr = F - kDeltaScale * d.xnorm[row] * __uint_as_float(*d.ymax_bits);
+
+  double bestv = -INFINITY;
+  int besti = 0x7fffffff;
+  const int c = lane & 15, half = lane >> 4;
+  auto rescore = [&](int col0) {
+    const int col = col0 + c;
+    double acc = 0.0;
+    if (col < d.NY) {
+      const float* yr = Y + (int64_t)col * ldy + half * 64;
+      const float* xr = &xs[w][half * 64];
+#pragma unroll 4
+      for (int k = 0; k < 64; k += 4) {
+        acc = fma((double)xr[k], (double)__ldg(yr + k), acc);
+        acc = fma((double)xr[k + 1], (double)__ldg(yr + k + 1), acc);
+        acc = fma((double)xr[k + 2], (double)__ldg(yr + k + 2), acc);
+        acc = fma((double)xr[k + 3], (double)__ldg(yr + k + 3), acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    double v = col < d.NY ? acc : -INFINITY;
+    int i = col < d.NY ? col : 0x7fffffff;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+    if (v > bestv || (v == bestv && i < besti)) { bestv = v; besti = i; }
+  };
+
+  for (int s = 0; s < d.splits; ++s) {
+    const size_t slot = (size_t)s * d.NXpad + row;
+    const int cnt = d.reccnt[slot];
+    if (cnt > kRecCap) {
+      // record list overflowed: exact scan of this split's whole column range
+      const int cb = s * d.tiles_per_split * kYRows;
+      const int ce = min(d.NY, (s + 1) * d.tiles_per_split * kYRows);
+      for (int col0 = cb; col0 < ce; col0 += 16) rescore(col0);
+    } else {
+      const uint2* r = d.rec + slot * kRecCap;
+      for (int k = 0; k < cnt; ++k) {
+        const uint2 e = r[k];
+        if (__uint_as_float(e.x) >= thr) rescore((int)e.y);
+      }
+    }
+  }
+  if (lane == 0) nn[row] = besti == 0x7fffffff ? 0 : besti;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, void* base, int rows_pad) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(POSFEAT_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)kD, (cuuint64_t)rows_pad};
+  cuuint64_t gstride[1] = {(cuuint64_t)kD * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(POSFEAT_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return POSFEAT_OK;
+}
+
+static inline int pad_rows(int n) { return (n + kXRows - 1) / kXRows * kXRows; }
+
+struct TcWs {
+  __nv_bfloat16 *Ab, *Bb;
+  float *anorm, *bnorm;
+  unsigned* maxn;  // [2]: max norm of A rows, of B rows
+  float* rowmax[2];
+  int* reccnt[2];
+  uint2* rec[2];
+  size_t total;
+};
+
+static TcWs carve_tc(void* base, int N, int M) {
+  TcWs w;
+  const int Np = pad_rows(N), Mp = pad_rows(M);
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  w.Ab = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * (size_t)Np * kD);
+  w.Bb = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * (size_t)Mp * kD);
+  w.anorm = (float*)take(sizeof(float) * Np);
+  w.bnorm = (float*)take(sizeof(float) * Mp);
+  w.maxn = (unsigned*)take(sizeof(unsigned) * 2);
+  const int rows[2] = {Np, Mp};
+  for (int d = 0; d < 2; ++d) {
+    w.rowmax[d] = (float*)take(sizeof(float) * (size_t)kMaxSplits * rows[d]);
+    w.reccnt[d] = (int*)take(sizeof(int) * (size_t)kMaxSplits * rows[d]);
+    w.rec[d] = (uint2*)take(sizeof(uint2) * (size_t)kMaxSplits * rows[d] * kRecCap);
+  }
+  w.total = off;
+  return w;
+}
+
+bool tc_supported(int N, int M, int D) { return D == kD && N >= 1 && M >= 1; }
+size_t tc_workspace_bytes(int N, int M) { return carve_tc(nullptr, N, M).total; }
+
+// choose the number of column splits so the persistent grid runs full waves
+static void choose_splits(int rb0, int yt0, int rb1, int yt1, int G, int* s0, int* s1) {
+  double best = -1.0;
+  *s0 = *s1 = 1;
+  for (int S = 1; S <= kMaxSplits; ++S) {
+    auto used = [&](int yt) {
+      const int tps = (yt + S - 1) / S;
+      return (yt + tps - 1) / tps;
+    };
+    const int u0 = used(yt0), u1 = used(yt1);
+    const long total = (long)rb0 * u0 + (long)rb1 * u1;
+    const long waves = (total + G - 1) / G;
+    // cost model: every unit reloads its X block (2 tile-times), waves are quantised
+    const double tiles = (double)rb0 * yt0 + (double)rb1 * yt1;
+    const double per_wave = tiles / total + 0.7;
+    const double time = waves * per_wave;
+    const double score = 1.0 / time;
+    if (score > best * 1.02) { best = score; *s0 = u0; *s1 = u1; }
+  }
+}
+
+int mnn_tc(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
+           int32_t* nn21, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (D != kD) return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
+  TcWs w = carve_tc(ws, N, M);
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  if (((uintptr_t)ws & 1023) != 0) return set_error(POSFEAT_EINVAL, "mnn workspace must be 1024-byte aligned");
+  const int Np = pad_rows(N), Mp = pad_rows(M);
+
+  PF_CUDA(cudaMemsetAsync(w.maxn, 0, sizeof(unsigned) * 2, stream));
+  tc_prep_kernel<<<(Np + 7) / 8, 256, 0, stream>>>(A, N, lda, Np, w.Ab, w.anorm, w.maxn);
+  PF_LAUNCH_CHECK("tc_prep_kernel(A)");
+  tc_prep_kernel<<<(Mp + 7) / 8, 256, 0, stream>>>(Bm, M, ldb, Mp, w.Bb, w.bnorm, w.maxn + 1);
+  PF_LAUNCH_CHECK("tc_prep_kernel(B)");
+
+  CUtensorMap mapA, mapB;
+  if (int e = make_map(&mapA, w.Ab, Np)) return e;
+  if (int e = make_map(&mapB, w.Bb, Mp)) return e;
+
+  TcParams p;
+  const int G = sm_count();
+  const int rb0 = Np / kXRows, rb1 = Mp / kXRows;
+  const int yt0 = (M + kYRows - 1) / kYRows, yt1 = (N + kYRows - 1) / kYRows;
+  int s0, s1;
+  choose_splits(rb0, yt0, rb1, yt1, G, &s0, &s1);
+  auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int yt, int S) {
+    d.xnorm = dir ? w.bnorm : w.anorm;
+    d.ymax_bits = dir ? w.maxn : w.maxn + 1;
+    d.rowmax = w.rowmax[dir];
+    d.reccnt = w.reccnt[dir];
+    d.rec = w.rec[dir];
+    d.NX = NX; d.NY = NY; d.NXpad = NXpad;
+    d.y_tiles = yt;
+    d.tiles_per_split = (yt + S - 1) / S;
+    d.splits = (yt + d.tiles_per_split - 1) / d.tiles_per_split;
+  };
+  fill(p.d[0], 0, N, M, Np, yt0, s0);
+  fill(p.d[1], 1, M, N, Mp, yt1, s1);
+  p.units0 = rb0 * p.d[0].splits;
+  p.units_total = p.units0 + rb1 * p.d[1].splits;
+
+  PF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+  const int grid = p.units_total < G ? p.units_total : G;
+  mnn_tc_kernel<<<grid, kTcThreads, kSmemAlloc, stream>>>(mapA, mapB, p);
+  PF_LAUNCH_CHECK("mnn_tc_kernel");
+
+  tc_rescore_kernel<<<(N + 7) / 8, 256, 0, stream>>>(p.d[0], A, lda, Bm, ldb, nn12);
+  PF_LAUNCH_CHECK("tc_rescore_kernel(A->B)");
+  tc_rescore_kernel<<<(M + 7) / 8, 256, 0, stream>>>(p.d[1], Bm, ldb, A, lda, nn21);
+  PF_LAUNCH_CHECK("tc_rescore_kernel(B->A)");
+  return POSFEAT_OK;
+}
+
 }  // namespace posfeat

@@ -47,3 +47,20 @@ def check_mnn_near_tie(a, b, got, want, tol=1e-6):
         top_c = np.sort(sim[:, j])[-2:]
         assert (top_r[1] - top_r[0] < tol) or (top_c[1] - top_c[0] < tol), \
             f"pair {(i, j)} differs without a near tie: row gap {top_r[1]-top_r[0]}, col gap {top_c[1]-top_c[0]}"
+
+
+def assert_close_vec(got, want, rel=1e-5, axis=-1):
+    """|got - want| <= rel * (largest |component| of the reference vector).
+
+    This is the "within 1e-5 relative at fp32" bar of the north star read
+    vector-wise: a bilinear blend of O(1) values carries an absolute error of
+    a few ulps of the sampling coordinate regardless of how close to zero an
+    individual component lands, so a per-element relative test is meaningless.
+    """
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = np.max(np.abs(want), axis=axis, keepdims=True)
+    err = np.abs(got - want)
+    bad = err > rel * scale + 1e-12
+    assert not bad.any(), f"{bad.sum()} elements off; worst err/scale = {np.max(err / np.maximum(scale, 1e-30)):.3e}"

@@ -3,11 +3,11 @@ import numpy as np
 import pytest
 import torch
 
-from _checks import check_mnn_near_tie
+from _checks import assert_close_vec, check_mnn_near_tie
 from oracle import posfeat_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = dict(rtol=1e-5, atol=1e-6)   # north_star: descriptors within 1e-5 relative at fp32
+REL = 1e-5   # north_star: descriptors within 1e-5 relative at fp32 (vector-wise, see _checks)
 
 
 def test_sample_golden(golden):
@@ -15,14 +15,14 @@ def test_sample_golden(golden):
     g = golden("sample")
     x = torch.from_numpy(g["x"]).cuda()
     c = torch.from_numpy(g["coord"]).cuda()
-    np.testing.assert_allclose(P.sample_feat_by_coord(x, c, False).cpu().numpy(), g["raw"], **TOL)
-    np.testing.assert_allclose(P.sample_feat_by_coord(x, c, True).cpu().numpy(), g["normed"], **TOL)
+    assert_close_vec(P.sample_feat_by_coord(x, c, False).cpu().numpy(), g["raw"], REL)
+    assert_close_vec(P.sample_feat_by_coord(x, c, True).cpu().numpy(), g["normed"], REL)
     x128 = torch.from_numpy(g["x128"]).cuda()
     c128 = torch.from_numpy(g["coord128"]).cuda()
-    np.testing.assert_allclose(P.sample_feat_by_coord(x128, c128, True).cpu().numpy(), g["normed128"], **TOL)
+    assert_close_vec(P.sample_feat_by_coord(x128, c128, True).cpu().numpy(), g["normed128"], REL)
     # channels_last (NHWC) input takes the vectorised kernel and must agree
     xcl = x128.contiguous(memory_format=torch.channels_last)
-    np.testing.assert_allclose(P.sample_feat_by_coord(xcl, c128, True).cpu().numpy(), g["normed128"], **TOL)
+    assert_close_vec(P.sample_feat_by_coord(xcl, c128, True).cpu().numpy(), g["normed128"], REL)
 
 
 @pytest.mark.parametrize("b,c,h,w,n", [(1, 128, 224, 300, 8192), (2, 128, 120, 160, 4096), (1, 64, 33, 47, 1000),
@@ -34,11 +34,11 @@ def test_sample_vs_oracle(b, c, h, w, n):
     coord = torch.rand(b, n, 2, generator=g) * 2.04 - 1.02
     want = O.sample_feat_by_coord(x.numpy(), coord.numpy(), True)
     got = P.sample_feat_by_coord(x.cuda(), coord.cuda(), True)
-    np.testing.assert_allclose(got.cpu().numpy(), want, **TOL)
+    assert_close_vec(got.cpu().numpy(), want, REL)
     got_cl = P.sample_feat_by_coord(x.cuda().contiguous(memory_format=torch.channels_last), coord.cuda(), True)
-    np.testing.assert_allclose(got_cl.cpu().numpy(), want, **TOL)
+    assert_close_vec(got_cl.cpu().numpy(), want, REL)
     raw = P.sample_feat_by_coord(x.cuda(), coord.cuda(), False).cpu().numpy()
-    np.testing.assert_allclose(raw, O.sample_feat_by_coord(x.numpy(), coord.numpy(), False), **TOL)
+    assert_close_vec(raw, O.sample_feat_by_coord(x.numpy(), coord.numpy(), False), REL)
     nrm = np.linalg.norm(got.cpu().numpy(), axis=-1)
     assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
 
