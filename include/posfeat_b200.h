@@ -49,6 +49,16 @@ int posfeat_last_error(char* buf, int n);
 /* Number of SMs of the current device (grid sizing for callers), <0 on error. */
 int posfeat_device_sm_count(void);
 
+/* Accounting used by bench.py: kernels launched by this process so far, and
+ * optional CUDA-event timing of the individual kernels (events are recorded on
+ * the launching stream around each launch while enabled; read() synchronises
+ * on them, returns the summed duration and launch count, and resets the slot). */
+int64_t posfeat_launch_count(void);
+int posfeat_profile_enable(int on);
+int posfeat_profile_slot_count(void);
+const char* posfeat_profile_slot_name(int slot);
+int posfeat_profile_read(int slot, double* total_ms, int32_t* launches);
+
 /* ---- (1) score-map keypoint selection -------------------------------------
  * Replaces generate_kpts_single(..., stable=True), losses/preprocess_utils.py:215-267
  * (nms :449-464, threshold :232-240, centroid/score :243-247, count clamp
@@ -131,6 +141,17 @@ size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo);
 int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb,
                     int D, int algo, int32_t* nn12, int32_t* nn21, int64_t* matches,
                     int32_t* n_matches, void* workspace, size_t ws_bytes, void* stream);
+
+/* Batched over P independent pairs of equal shape (the pair pipeline's call):
+ * pair p reads A + p*stride_a and Bm + p*stride_b (strides in elements) and
+ * writes nn12[p*N..], nn21[p*M..], matches[p*N*2..], n_matches[p].  One launch
+ * chain serves all pairs, so launch and prologue costs are paid once. */
+size_t posfeat_mnn_batched_workspace_bytes(int P, int N, int M, int D, int algo);
+int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, int64_t lda,
+                            const float* Bm, int64_t stride_b, int M, int64_t ldb,
+                            int D, int P, int algo, int32_t* nn12, int32_t* nn21,
+                            int64_t* matches, int32_t* n_matches,
+                            void* workspace, size_t ws_bytes, void* stream);
 
 /* Same, operands and results in HOST memory (pageable or pinned): copies in,
  * runs, copies back and synchronises `stream`.  This is the call a reader of

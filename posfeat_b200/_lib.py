@@ -23,6 +23,11 @@ SIGNATURES = {
     "posfeat_version": (_i, []),
     "posfeat_last_error": (_i, [C.c_char_p, _i]),
     "posfeat_device_sm_count": (_i, []),
+    "posfeat_launch_count": (_i64, []),
+    "posfeat_profile_enable": (_i, [_i]),
+    "posfeat_profile_slot_count": (_i, []),
+    "posfeat_profile_slot_name": (C.c_char_p, [_i]),
+    "posfeat_profile_read": (_i, [_i, C.POINTER(C.c_double), c_i32p]),
     "posfeat_detect_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_detect_candidates_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "posfeat_detect_select_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
@@ -34,6 +39,9 @@ SIGNATURES = {
                                        _vp, _vp]),
     "posfeat_mnn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "posfeat_mnn_batched_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "posfeat_mnn_batched_f32": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                     _sz, _vp]),
     "posfeat_mnn_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_host_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
@@ -83,3 +91,23 @@ class PosfeatError(RuntimeError):
 def check(status: int):
     if status != 0:
         raise PosfeatError(f"posfeat_b200 error {status}: {last_error()}")
+
+
+def profile_enable(on: bool):
+    load().posfeat_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """{kernel name: (total_ms, launches)} since the last read (synchronises)."""
+    lib = load()
+    out = {}
+    for slot in range(lib.posfeat_profile_slot_count()):
+        ms, n = C.c_double(0), C.c_int32(0)
+        check(lib.posfeat_profile_read(slot, C.byref(ms), C.byref(n)))
+        if n.value:
+            out[lib.posfeat_profile_slot_name(slot).decode()] = (ms.value, n.value)
+    return out
+
+
+def launch_count() -> int:
+    return int(load().posfeat_launch_count())

@@ -3,6 +3,10 @@
 // tcgen05 tensor-core kernel.
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "mnn_common.cuh"
 
@@ -16,6 +20,37 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfPair { cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof[PROF_COUNT];
+static cudaEvent_t g_prof_open[PROF_COUNT];
+static const char* kProfNames[PROF_COUNT] = {"nms_candidates", "select_topk", "sample_l2norm", "mnn_prep", "mnn_tc",
+                                             "mnn_rescore", "mnn_simt", "mnn_compact", "corr_fwd", "corr_bwd",
+                                             "window_fwd", "window_bwd"};
+
+void prof_begin(int slot, cudaStream_t s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  g_prof_open[slot] = e;
+}
+void prof_end(int slot, cudaStream_t s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_open[slot]) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  g_prof[slot].push_back({g_prof_open[slot], e});
+  g_prof_open[slot] = nullptr;
 }
 
 int sm_count() {
@@ -72,6 +107,35 @@ extern "C" int posfeat_last_error(char* buf, int n) {
   return POSFEAT_OK;
 }
 
+extern "C" int64_t posfeat_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int posfeat_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return POSFEAT_OK;
+}
+extern "C" int posfeat_profile_slot_count(void) { return PROF_COUNT; }
+extern "C" const char* posfeat_profile_slot_name(int slot) {
+  return (slot >= 0 && slot < PROF_COUNT) ? kProfNames[slot] : "";
+}
+extern "C" int posfeat_profile_read(int slot, double* total_ms, int32_t* launches) {
+  PF_CHECK_ARG(slot >= 0 && slot < PROF_COUNT && total_ms && launches, "bad profile slot %d", slot);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0;
+  int n = 0;
+  for (ProfPair& pr : g_prof[slot]) {
+    float t = 0.f;
+    if (cudaEventSynchronize(pr.b) == cudaSuccess && cudaEventElapsedTime(&t, pr.a, pr.b) == cudaSuccess) {
+      ms += t;
+      ++n;
+    }
+    cudaEventDestroy(pr.a);
+    cudaEventDestroy(pr.b);
+  }
+  g_prof[slot].clear();
+  *total_ms = ms;
+  *launches = n;
+  return POSFEAT_OK;
+}
+
 extern "C" int posfeat_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -84,38 +148,52 @@ static int resolve_algo(int N, int M, int D, int algo) {
   return algo;
 }
 
-extern "C" size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo) {
-  if (N < 1 || M < 1 || D < 1) return 0;
+extern "C" size_t posfeat_mnn_batched_workspace_bytes(int P, int N, int M, int D, int algo) {
+  if (P < 1 || N < 1 || M < 1 || D < 1) return 0;
   size_t need = simt_workspace_bytes(N, M);
   const int a = resolve_algo(N, M, D, algo);
   if (a == POSFEAT_MNN_TC && tc_supported(N, M, D)) {
-    const size_t t = tc_workspace_bytes(N, M);
+    const size_t t = tc_workspace_bytes(P, N, M);
     if (t > need) need = t;
   }
   return need;
 }
 
-extern "C" int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D,
-                               int algo, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches,
-                               void* workspace, size_t ws_bytes, void* stream_) {
+extern "C" size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo) {
+  return posfeat_mnn_batched_workspace_bytes(1, N, M, D, algo);
+}
+
+extern "C" int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, int64_t lda, const float* Bm,
+                                       int64_t stride_b, int M, int64_t ldb, int D, int P, int algo, int32_t* nn12,
+                                       int32_t* nn21, int64_t* matches, int32_t* n_matches, void* workspace,
+                                       size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PF_CHECK_ARG(A && Bm && nn12 && nn21 && matches && n_matches && workspace, "NULL pointer");
+  PF_CHECK_ARG(P >= 1 && P <= 65535, "pairs=%d outside [1, 65535]", P);
   PF_CHECK_ARG(N >= 1 && M >= 1 && D >= 1, "empty operand (N=%d M=%d D=%d): the reference's torch.max raises on an empty reduction too", N, M, D);
   PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
   PF_CHECK_ARG(algo >= POSFEAT_MNN_AUTO && algo <= POSFEAT_MNN_TC, "unknown algo %d", algo);
   const int a = resolve_algo(N, M, D, algo);
-  const size_t need = posfeat_mnn_workspace_bytes(N, M, D, a);
+  const size_t need = posfeat_mnn_batched_workspace_bytes(P, N, M, D, a);
   if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "mnn workspace: need %zu bytes, got %zu", need, ws_bytes);
-  int e;
   if (a == POSFEAT_MNN_TC) {
     if (!tc_supported(N, M, D))
       return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
-    e = mnn_tc(A, N, lda, Bm, M, ldb, D, nn12, nn21, workspace, ws_bytes, stream);
+    if (int e = mnn_tc(A, stride_a, N, lda, Bm, stride_b, M, ldb, D, P, nn12, nn21, workspace, ws_bytes, stream)) return e;
   } else {
-    e = mnn_simt(A, N, lda, Bm, M, ldb, D, nn12, nn21, workspace, stream);
+    for (int p = 0; p < P; ++p)
+      if (int e = mnn_simt(A + p * stride_a, N, lda, Bm + p * stride_b, M, ldb, D, nn12 + (size_t)p * N,
+                           nn21 + (size_t)p * M, workspace, stream))
+        return e;
   }
-  if (e) return e;
-  return launch_mutual_compact(nn12, nn21, N, M, matches, n_matches, stream);
+  return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);
+}
+
+extern "C" int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D,
+                               int algo, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  return posfeat_mnn_batched_f32(A, 0, N, lda, Bm, 0, M, ldb, D, 1, algo, nn12, nn21, matches, n_matches, workspace,
+                                 ws_bytes, stream);
 }
 
 extern "C" size_t posfeat_mnn_host_scratch_bytes(int N, int M, int D, int algo) {

@@ -27,6 +27,7 @@ int set_error(int code, const char* fmt, ...);
 
 #define PF_LAUNCH_CHECK(name)                                                     \
   do {                                                                            \
+    ::posfeat::count_launch();                                                    \
     cudaError_t e__ = cudaGetLastError();                                         \
     if (e__ != cudaSuccess)                                                       \
       return ::posfeat::set_error(POSFEAT_ECUDA, "launch of %s failed: %s", name, \
@@ -58,5 +59,19 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 int sm_count();
+
+// launch accounting and optional per-kernel CUDA-event timing (api.cu)
+void count_launch();
+enum ProfSlot {
+  PROF_NMS = 0, PROF_SELECT, PROF_SAMPLE, PROF_MNN_PREP, PROF_MNN_TC, PROF_MNN_RESCORE, PROF_MNN_SIMT,
+  PROF_MNN_COMPACT, PROF_CORR_FWD, PROF_CORR_BWD, PROF_WIN_FWD, PROF_WIN_BWD, PROF_COUNT
+};
+void prof_begin(int slot, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+struct ProfScope {
+  int slot; cudaStream_t s;
+  ProfScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_) { prof_begin(slot, s); }
+  ~ProfScope() { prof_end(slot, s); }
+};
 
 }  // namespace posfeat

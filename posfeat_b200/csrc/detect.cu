@@ -462,6 +462,7 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
   const int pw = kTileW + 2 * r, ph = kTileH + 2 * r;
   const size_t smem = sizeof(float) * (size_t)ph * (pw | 1);
   dim3 grid((W - 2 + kTileW - 1) / kTileW, (H - 2 + kTileH - 1) / kTileH, B);
+  ProfScope prof(PROF_NMS, stream);
   nms_candidates_kernel<<<grid, kNmsThreads, smem, stream>>>(score, H, W, stride_b, stride_y, nms_mode, r, has_thr,
                                                              w.thr_val, counts, w.cand_count, w.cand, w.cand_cap);
   PF_LAUNCH_CHECK("nms_candidates_kernel");
@@ -485,6 +486,7 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
     PF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  ProfScope prof(PROF_SELECT, stream);
   select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
                                                    counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,
                                                    w.status, n_out, idx_out, kps_out, kpscore_out);

@@ -109,55 +109,78 @@ __global__ void rowbest_finalize_kernel(const double* __restrict__ part_val, con
   nn[r] = bi == 0x7fffffff ? 0 : bi;   // all-NaN rows: torch.max also reports an index
 }
 
-// keep rows with nn21[nn12[i]] == i, ordered compaction (ascending i) by one CTA
+// keep rows with nn21[nn12[i]] == i, ordered compaction (ascending i); one CTA per
+// pair, kItems consecutive rows per thread so all loads of a pass are in flight together
+constexpr int kItems = 8;
 __global__ void __launch_bounds__(1024)
-mutual_compact_kernel(const int32_t* __restrict__ nn12, const int32_t* __restrict__ nn21, int N, int M,
-                      int64_t* __restrict__ matches, int32_t* __restrict__ n_matches) {
+mutual_compact_kernel(const int32_t* __restrict__ nn12_, const int32_t* __restrict__ nn21_, int N, int M,
+                      int64_t* __restrict__ matches_, int32_t* __restrict__ n_matches) {
   __shared__ int s_warp[32];
   __shared__ int s_base, s_total;
+  const int pair = blockIdx.x;
+  const int32_t* nn12 = nn12_ + (size_t)pair * N;
+  const int32_t* nn21 = nn21_ + (size_t)pair * M;
+  int64_t* matches = matches_ + (size_t)pair * N * 2;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < N; i0 += 1024) {
-    const int i = i0 + tid;
-    bool keep = false;
-    int j = 0;
-    if (i < N) {
-      j = nn12[i];
-      keep = j >= 0 && j < M && nn21[j] == i;
+  for (int i0 = 0; i0 < N; i0 += 1024 * kItems) {
+    const int first = i0 + tid * kItems;
+    int j[kItems], back[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) j[k] = (first + k < N) ? nn12[first + k] : -1;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) back[k] = (j[k] >= 0 && j[k] < M) ? nn21[j[k]] : -1;
+    unsigned keep = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) keep |= (back[k] == first + k && first + k < N) ? (1u << k) : 0u;
+    const int mine = __popc(keep);
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[wid] = __popc(bal);
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
       const int v = s_warp[lane];
-      int inc = v;
+      int winc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
       }
-      s_warp[lane] = inc - v;  // exclusive prefix over warps
-      if (lane == 31) s_total = inc;
+      s_warp[lane] = winc - v;  // exclusive prefix over warps
+      if (lane == 31) s_total = winc;
     }
     __syncthreads();
-    if (keep) {
-      const int pos = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
-      matches[2 * (int64_t)pos] = i;
-      matches[2 * (int64_t)pos + 1] = j;
-    }
+    int pos = s_base + s_warp[wid] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (keep & (1u << k)) {
+        matches[2 * (int64_t)pos] = first + k;
+        matches[2 * (int64_t)pos + 1] = j[k];
+        ++pos;
+      }
     __syncthreads();
     if (tid == 0) s_base += s_total;
     __syncthreads();
   }
-  if (tid == 0) *n_matches = s_base;
+  if (tid == 0) n_matches[pair] = s_base;
+}
+
+int launch_mutual_compact_batched(const int32_t* nn12, const int32_t* nn21, int P, int N, int M, int64_t* matches,
+                                  int32_t* n_matches, cudaStream_t stream) {
+  ProfScope prof(PROF_MNN_COMPACT, stream);
+  mutual_compact_kernel<<<P, 1024, 0, stream>>>(nn12, nn21, N, M, matches, n_matches);
+  PF_LAUNCH_CHECK("mutual_compact_kernel");
+  return POSFEAT_OK;
 }
 
 int launch_mutual_compact(const int32_t* nn12, const int32_t* nn21, int N, int M, int64_t* matches,
                           int32_t* n_matches, cudaStream_t stream) {
-  mutual_compact_kernel<<<1, 1024, 0, stream>>>(nn12, nn21, N, M, matches, n_matches);
-  PF_LAUNCH_CHECK("mutual_compact_kernel");
-  return POSFEAT_OK;
+  return launch_mutual_compact_batched(nn12, nn21, 1, N, M, matches, n_matches, stream);
 }
 
 static int choose_splits(int NX, int NY) {
@@ -185,6 +208,7 @@ int run_rowbest_simt(const float* X, int NX, int64_t ldx, const float* Y, int NY
   double* pv = (double*)ws;
   int32_t* pi = (int32_t*)((char*)ws + align_up(sizeof(double) * (size_t)64 * NX, 256));
   dim3 grid((NX + kBM - 1) / kBM, used);
+  ProfScope prof(PROF_MNN_SIMT, stream);
   rowbest_simt_kernel<<<grid, 256, 0, stream>>>(X, NX, ldx, Y, NY, ldy, D, cols_per_split, pv, pi);
   PF_LAUNCH_CHECK("rowbest_simt_kernel");
   rowbest_finalize_kernel<<<(NX + 255) / 256, 256, 0, stream>>>(pv, pi, NX, used, nn);

@@ -5,23 +5,29 @@
 // without ever writing the N x M similarity matrix.
 //
 // Per direction (rows of X against all rows of Y; run for (A,B) and (B,A)):
-//   * operands are rounded once to bf16 (prep kernel, also row norms);
+//   * operands are rounded once to bf16 (prep kernel; it also records |x|, the
+//     norm of the rounding error |x~ - x| per row, and their maxima);
 //   * a persistent, warp-specialised kernel walks work units (256 rows of X,
 //     a range of 128-row Y tiles): warp 0 feeds shared memory with TMA
 //     (SWIZZLE_128B boxes), warp 1 issues tcgen05.mma (M=128, N=128, K=16, bf16,
 //     fp32 accumulators in TMEM, two accumulator stages = all 512 columns),
-//     warps 4..11 drain TMEM with tcgen05.ld and keep, per row, the running
-//     approximate maximum and the list of 16-column chunks whose maximum is
-//     within delta of it;
-//   * delta = 2*eps with eps = 2^-7 |x||y| bounding the bf16 rounding error of one
-//     similarity, so the true argmax is always inside a recorded chunk;
-//   * a rescoring kernel recomputes the surviving chunks exactly (float32
-//     operands, float64 accumulation -- the same value the exact SIMT kernel
-//     uses) and takes the argmax with the first-index tie rule.
-// Rows whose record list overflows are rescanned exactly, so the result never
-// depends on the approximation.
+//     warps 4..19 drain TMEM with tcgen05.ld and reduce every 8 consecutive
+//     columns of a row to their maximum, stored as fp16 in a chunk-maximum
+//     table [rows][M/8] (1/16 of the bytes of the similarity matrix, which is
+//     itself never written);
+//   * the rescoring kernel takes the table row of each x, finds the chunks whose
+//     maximum is within delta of the row maximum, where
+//     delta_i = 2 (|e_xi| max|y~| + |x_i| max|e_y|) + slack bounds twice the error
+//     of an approximate similarity (Cauchy-Schwarz on x~.y~ - x.y plus the fp16
+//     rounding of the table), so the true argmax always lies in such a chunk;
+//     it re-evaluates those chunks in float32, then every column within the
+//     float32 error band exactly (float64 accumulation -- the value the exact
+//     SIMT kernel uses) and takes the argmax, first index on ties.
+// The result therefore never depends on the approximation.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "mnn_common.cuh"
@@ -29,34 +35,65 @@
 namespace posfeat {
 
 constexpr int kD = 128;
-constexpr int kXRows = 256;   // rows of X per work unit (two M=128 MMA tiles)
-constexpr int kYRows = 128;   // rows of Y per tile (MMA N)
-constexpr int kStages = 4;    // Y ring depth
+constexpr int kXRows = 256;   // rows of X per work unit: one cta_group::2 MMA tile, 128 rows per CTA of the pair
+constexpr int kYRows = 256;   // rows of Y per tile (MMA N); each CTA of the pair stages 128 of them
+constexpr int kStages = 5;    // Y ring depth (per CTA: 5 x 32 KB)
 constexpr int kSubBytes = 128 * 64 * 2;  // one [128 rows x 64 K] bf16 swizzled sub-tile
-constexpr int kRecCap = 16;
-constexpr int kMaxSplits = 16;
-constexpr int kTcThreads = 384;
-constexpr float kDeltaScale = 0.016f;  // 2 * (2^-7 + slack) : see header comment
+constexpr int kChunk = 8;     // candidate granularity (columns)
+constexpr int kMaxSplits = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kTcThreads = (4 + kEpiWarps) * 32;
+constexpr float kAccSlack = 3.0e-5f;   // fp32 accumulation error of the tensor core, relative to |x||y|
+constexpr float kEps32 = 1.0e-5f;      // float32 dot-product error bound (>= 128 * 2^-24), relative to |x||y|
+constexpr float kHalfSlack = 9.8e-4f;  // 2 * 2^-11: fp16 rounding of two table entries of magnitude <= 1
 
-constexpr int kSmemX = 0;
-constexpr int kSmemY = 4 * kSubBytes;
+constexpr int kSmemX = 0;                      // 2 buffers x 2 K-halves
+constexpr int kSmemY = 4 * kSubBytes;          // kStages x 2 K-halves
 constexpr int kSmemBar = kSmemY + kStages * 2 * kSubBytes;
 constexpr int kSmemTotal = kSmemBar + 256;
 constexpr int kSmemAlloc = kSmemTotal + 1024;
 
-struct DirParams {
-  const float* xnorm;          // [NXpad] row norms of X (float32 data)
-  const unsigned* ymax_bits;   // max row norm of Y (float bits)
-  float* rowmax;               // [splits][NXpad]
-  int* reccnt;                 // [splits][NXpad]
-  uint2* rec;                  // [splits][NXpad][kRecCap] (chunk max bits, first column)
-  int NX, NY, NXpad;
+// per-matrix scalars produced by the prep kernel (float bits, combined with atomicMax)
+struct MatStats {
+  unsigned max_norm;      // max_j |y_j|
+  unsigned max_norm_bf;   // max_j |y~_j|
+  unsigned max_err;       // max_j |y~_j - y_j|
+  unsigned pad;
+};
+
+struct DirParams {            // all arrays are batched over pairs: index = pair * stride + ...
+  const float* xnorm;          // [pairs][NXpad] |x_i|
+  const float* xerr;           // [pairs][NXpad] |x~_i - x_i|
+  const MatStats* xstats;      // [pairs][2] -> element pair*2 + which (set up per direction)
+  const MatStats* ystats;
+  __half* table;               // [pairs][NXpad][pitch] chunk maxima, scaled by 1/(max|x| max|y|)
+  int pitch;                   // y_tiles * 32 chunks per row
+  int NX, NY, NXpad, NYpad;
   int splits, tiles_per_split, y_tiles;
+  int row_blocks;              // NXpad / 256
 };
 struct TcParams {
   DirParams d[2];
-  int units0, units_total;
+  int pairs;
+  int units0, units_pair;      // units of direction 0 / of both directions, per pair
+  int units_total;             // pairs * units_pair
+  int debug;   // POSFEAT_TC_DEBUG bits (bring-up only)
 };
+
+// 1 / (max|x| max|y|): keeps every table entry inside [-1, 1]
+__device__ __forceinline__ float table_scale(const DirParams& d, int pair) {
+  const float m = __uint_as_float(d.xstats[2 * pair].max_norm) * __uint_as_float(d.ystats[2 * pair].max_norm);
+  return m > 0.f ? 1.f / m : 0.f;
+}
+
+__device__ __forceinline__ float row_delta(const DirParams& d, int pair, int row) {
+  const MatStats& ys = d.ystats[2 * pair];
+  const float yb = __uint_as_float(ys.max_norm_bf), ye = __uint_as_float(ys.max_err);
+  const float yn = __uint_as_float(ys.max_norm);
+  const size_t r = (size_t)pair * d.NXpad + row;
+  const float xn = d.xnorm[r];
+  return 2.f * (d.xerr[r] * yb + xn * ye + kAccSlack * xn * yn);
+}
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,6 +164,43 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs load into their own shared memory; the bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all prior MMAs retire) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -137,16 +211,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;              // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kYRows >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=256 (CTA pair), N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kYRows >> 3) << 17) | ((256u >> 4) << 24);
 
 struct UnitInfo {
-  int dir, rb, sp, t0, t1;
+  int pair, dir, rb, sp, t0, t1;
 };
 __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int u) {
   UnitInfo q;
-  q.dir = u >= p.units0 ? 1 : 0;
-  const int v = q.dir ? u - p.units0 : u;
+  q.pair = u / p.units_pair;
+  int v = u - q.pair * p.units_pair;
+  q.dir = v >= p.units0 ? 1 : 0;
+  if (q.dir) v -= p.units0;
   const DirParams& d = p.d[q.dir];
   q.rb = v / d.splits;
   q.sp = v - q.rb * d.splits;
@@ -155,269 +231,395 @@ __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int u) {
   return q;
 }
 
-// one 16-column chunk of the accumulator row owned by this thread
-__device__ __forceinline__ void process_chunk(const uint32_t* v, int col0, int NY, float delta, float& run, int& cnt,
-                                              uint2* __restrict__ myrec) {
-  if (col0 >= NY) return;  // warp uniform
-  float f[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-  if (col0 + 16 > NY) {  // ragged last chunk: padding rows of Y are zeros, mask them
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (col0 + j >= NY) f[j] = -INFINITY;
-  }
-  const float m0 = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3]));
-  const float m1 = fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7]));
-  const float m2 = fmaxf(fmaxf(f[8], f[9]), fmaxf(f[10], f[11]));
-  const float m3 = fmaxf(fmaxf(f[12], f[13]), fmaxf(f[14], f[15]));
-  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  run = fmaxf(run, m);
-  if (m >= run - delta) {
-    if (cnt < kRecCap) myrec[cnt] = make_uint2(__float_as_uint(m), (unsigned)col0);
-    ++cnt;
-  }
+__device__ __forceinline__ float max8(const float* f) {
+  return fmaxf(fmaxf(fmaxf(f[0], f[1]), f[2]), fmaxf(fmaxf(fmaxf(f[3], f[4]), f[5]), fmaxf(f[6], f[7])));
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// 32 accumulator columns of the row owned by this thread -> four scaled chunk
+// maxima packed as 2 x half2
+template <bool kRagged>
+__device__ __forceinline__ uint2 reduce32(const uint32_t (&v)[32], int col0, int NY, float scale) {
+  float m[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = __uint_as_float(v[c * 8 + j]);
+      if (kRagged && col0 + c * 8 + j >= NY) f[j] = -INFINITY;   // zero padding rows of Y
+    }
+    m[c] = max8(f) * scale;
+  }
+  const __half2 lo = __floats2half2_rn(m[0], m[1]), hi = __floats2half2_rn(m[2], m[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<const unsigned*>(&lo);
+  r.y = *reinterpret_cast<const unsigned*>(&hi);
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = sbase + kSmemBar;
-  const uint32_t bar_x_full = bar0, bar_x_empty = bar0 + 8;
-  const uint32_t bar_y_full = bar0 + 16, bar_y_empty = bar_y_full + 8 * kStages;
-  const uint32_t bar_acc_full = bar_y_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t bar_x_full = bar0, bar_x_empty = bar0 + 16;                       // [2] each
+  const uint32_t bar_y_full = bar0 + 32, bar_y_empty = bar_y_full + 8 * kStages;   // [kStages] each
+  const uint32_t bar_acc_full = bar_y_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;  // [2] each
   const uint32_t tmem_slot = bar_acc_empty + 16;
   unsigned char* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemBar + 16 + 16 * kStages + 32);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemBar + 32 + 16 * kStages + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader (issues the MMAs), 1 = peer
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_x_full, 1);
-    mbar_init(bar_x_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_x_full + 8 * b, 1);
+      mbar_init(bar_x_empty + 8 * b, 1);
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, 2 * kEpiWarps);  // one arrival per epilogue warp of BOTH CTAs (leader's copy is used)
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_y_full + 8 * s, 1);
       mbar_init(bar_y_empty + 8 * s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_acc_full + 8 * a, 1);
-      mbar_init(bar_acc_empty + 8 * a, 8);  // one arrival per epilogue warp
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) {   // same warp in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();      // barriers of both CTAs initialised, TMEM allocated, before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs: own half of X and of every Y tile) =====
     int ys = 0, yph = 0, it = 0;
-    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++it) {
+    for (int u = cluster_id; u < p.units_total; u += n_clusters, ++it) {
       const UnitInfo q = decode_unit(p, u);
       const CUtensorMap* xmap = q.dir ? &mapB : &mapA;
       const CUtensorMap* ymap = q.dir ? &mapA : &mapB;
-      mbar_wait(bar_x_empty, (it & 1) ^ 1);
-      mbar_expect_tx(bar_x_full, 4 * kSubBytes);
+      const int xb = it & 1;
+      mbar_wait(bar_x_empty + 8 * xb, ((it >> 1) & 1) ^ 1);
+      if (rank == 0) mbar_expect_tx(bar_x_full + 8 * xb, 2 * 2 * kSubBytes);
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh)
-          tma_load_2d(sbase + kSmemX + (m * 2 + kh) * kSubBytes, xmap, kh * 64, q.rb * kXRows + m * 128, bar_x_full);
+      for (int kh = 0; kh < 2; ++kh)
+        tma_load_2d_pair(sbase + kSmemX + (xb * 2 + kh) * kSubBytes, xmap, kh * 64,
+                         q.pair * p.d[q.dir].NXpad + q.rb * kXRows + (int)rank * 128, bar_x_full + 8 * xb);
       for (int t = q.t0; t < q.t1; ++t) {
         mbar_wait(bar_y_empty + 8 * ys, yph ^ 1);
-        mbar_expect_tx(bar_y_full + 8 * ys, 2 * kSubBytes);
-        tma_load_2d(sbase + kSmemY + (ys * 2 + 0) * kSubBytes, ymap, 0, t * kYRows, bar_y_full + 8 * ys);
-        tma_load_2d(sbase + kSmemY + (ys * 2 + 1) * kSubBytes, ymap, 64, t * kYRows, bar_y_full + 8 * ys);
+        if (p.debug & 8) {   // bring-up: no Y traffic, MMA runs on stale shared memory
+          if (rank == 0) mbar_arrive(bar_y_full + 8 * ys);
+        } else {
+          if (rank == 0) mbar_expect_tx(bar_y_full + 8 * ys, 2 * 2 * kSubBytes);
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh)
+            tma_load_2d_pair(sbase + kSmemY + (ys * 2 + kh) * kSubBytes, ymap, kh * 64,
+                             q.pair * p.d[q.dir].NYpad + t * kYRows + (int)rank * 128, bar_y_full + 8 * ys);
+        }
         if (++ys == kStages) { ys = 0; yph ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer (single thread) =====
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===== MMA issuer (one thread of the leader CTA drives both tensor cores) =====
     int ys = 0, yph = 0, as = 0, aph = 0, it = 0;
-    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x, ++it) {
+    for (int u = cluster_id; u < p.units_total; u += n_clusters, ++it) {
       const UnitInfo q = decode_unit(p, u);
-      mbar_wait(bar_x_full, it & 1);
+      const int xb = it & 1;
+      mbar_wait(bar_x_full + 8 * xb, (it >> 1) & 1);
       for (int t = q.t0; t < q.t1; ++t) {
-        mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);
+        if (!(p.debug & 16)) mbar_wait(bar_acc_empty + 8 * as, aph ^ 1);   // bit 16 (bring-up): ignore the epilogue
         mbar_wait(bar_y_full + 8 * ys, yph);
         tc_fence_after();
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256 + m * 128);
+        if (!(p.debug & 4)) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh) {
-            const uint64_t ad = make_sw128_desc(sbase + kSmemX + (m * 2 + kh) * kSubBytes);
+            const uint64_t ad = make_sw128_desc(sbase + kSmemX + (xb * 2 + kh) * kSubBytes);
             const uint64_t bd = make_sw128_desc(sbase + kSmemY + (ys * 2 + kh) * kSubBytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc, (kh | k) ? 1u : 0u);
+              tc_mma_bf16_pair(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdesc, (kh | k) ? 1u : 0u);
           }
         }
-        tc_commit(bar_y_empty + 8 * ys);     // smem stage may be refilled once these MMAs retire
-        tc_commit(bar_acc_full + 8 * as);    // accumulator ready for the epilogue
-        if (t == q.t1 - 1) tc_commit(bar_x_empty);
+        tc_commit_pair(bar_y_empty + 8 * ys);     // both producers may refill this stage once the MMAs retire
+        tc_commit_pair(bar_acc_full + 8 * as);    // accumulators ready in both CTAs
+        if (t == q.t1 - 1) tc_commit_pair(bar_x_empty + 8 * xb);
         if (++ys == kStages) { ys = 0; yph ^= 1; }
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> running max + candidate chunks =====
-    const int wg = (warp - 4) >> 2, quarter = warp & 3;
-    const int row_in_block = wg * 128 + quarter * 32 + lane;
+    // ===== epilogue (both CTAs): TMEM -> registers -> per-chunk maxima -> fp16 table =====
+    // warp -> (TMEM lane quarter, 64-column quarter of every 256-column Y tile)
+    const int quarter = warp & 3, j = (warp - 4) >> 2;
+    const int row_in_block = (int)rank * 128 + quarter * 32 + lane;
     int as = 0, aph = 0;
-    for (int u = blockIdx.x; u < p.units_total; u += gridDim.x) {
+    for (int u = cluster_id; u < p.units_total; u += n_clusters) {
       const UnitInfo q = decode_unit(p, u);
       const DirParams& d = p.d[q.dir];
       const int row = q.rb * kXRows + row_in_block;
-      const float delta = kDeltaScale * d.xnorm[row] * __uint_as_float(*d.ymax_bits);
-      const size_t slot = (size_t)q.sp * d.NXpad + row;
-      uint2* myrec = d.rec + slot * kRecCap;
-      float run = -INFINITY;
-      int cnt = 0;
+      const float scale = table_scale(d, q.pair);
+      __half* trow = d.table + ((size_t)q.pair * d.NXpad + row) * d.pitch + j * 8;
       for (int t = q.t0; t < q.t1; ++t) {
         mbar_wait(bar_acc_full + 8 * as, aph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + wg * 128) + ((uint32_t)(quarter * 32) << 16);
-        const int c0 = t * kYRows;
+        const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + j * 64) + ((uint32_t)(quarter * 32) << 16);
+        const int c0 = t * kYRows + j * 64;
         uint32_t va[32], vb[32];
-        tc_ld32(taddr, va);
-        tc_wait_ld();
-        tc_ld32(taddr + 32, vb);
-        process_chunk(va, c0, d.NY, delta, run, cnt, myrec);
-        process_chunk(va + 16, c0 + 16, d.NY, delta, run, cnt, myrec);
-        tc_wait_ld();
-        tc_ld32(taddr + 64, va);
-        process_chunk(vb, c0 + 32, d.NY, delta, run, cnt, myrec);
-        process_chunk(vb + 16, c0 + 48, d.NY, delta, run, cnt, myrec);
-        tc_wait_ld();
-        tc_ld32(taddr + 96, vb);
-        process_chunk(va, c0 + 64, d.NY, delta, run, cnt, myrec);
-        process_chunk(va + 16, c0 + 80, d.NY, delta, run, cnt, myrec);
-        tc_wait_ld();
-        process_chunk(vb, c0 + 96, d.NY, delta, run, cnt, myrec);
-        process_chunk(vb + 16, c0 + 112, d.NY, delta, run, cnt, myrec);
+        if (!(p.debug & 2)) {
+          tc_ld32(taddr, va);
+          tc_ld32(taddr + 32, vb);
+          tc_wait_ld();
+        }
+        // this thread's accumulator slice is in registers: release the TMEM stage (leader's barrier)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+        if (lane == 0) mbar_arrive_remote(bar_acc_empty + 8 * as, 0);
         if (++as == 2) { as = 0; aph ^= 1; }
+        if (p.debug & 3) {
+          if ((p.debug & 1) && !(p.debug & 2) && (va[0] ^ vb[31]) == 0x12345678u) trow[0] = __float2half(1.f);
+          continue;
+        }
+        uint2 lo, hi;
+        if (c0 + 64 <= d.NY) {
+          lo = reduce32<false>(va, c0, d.NY, scale);
+          hi = reduce32<false>(vb, c0 + 32, d.NY, scale);
+        } else {
+          lo = reduce32<true>(va, c0, d.NY, scale);
+          hi = reduce32<true>(vb, c0 + 32, d.NY, scale);
+        }
+        *reinterpret_cast<uint4*>(trow + t * 32) = make_uint4(lo.x, lo.y, hi.x, hi.y);
       }
-      d.rowmax[slot] = run;
-      d.reccnt[slot] = cnt;
     }
   }
 
+  // no CTA may exit (or free TMEM) while its peer can still signal it
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
 // ------------------------------------------------------------------ prep
-// float32 rows -> bf16 [rows_pad, 128] (zero padded), row norms, max norm
+// float32 rows -> bf16 [pairs][rows_pad][128] (zero padded) for both matrices of
+// every pair in one launch; per row |x| and |x~ - x|; per matrix the maxima.
+struct PrepArgs {
+  const float* A; int64_t lda, strideA; int N, Np;
+  const float* B; int64_t ldb, strideB; int M, Mp;
+  __nv_bfloat16 *Ab, *Bb;
+  float *anorm, *aerr, *bnorm, *berr;
+  MatStats* stats;   // [pairs][2]
+  int pairs;
+};
+
+constexpr int kPrepRowsPerWarp = 8;
 __global__ void __launch_bounds__(256)
-tc_prep_kernel(const float* __restrict__ X, int NX, int64_t ldx, int NXpad, __nv_bfloat16* __restrict__ Xb,
-               float* __restrict__ xnorm, unsigned* __restrict__ max_bits) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= NXpad) return;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < NX) {
-    const float* src = X + (int64_t)row * ldx + lane * 4;
-    v.x = __ldg(src); v.y = __ldg(src + 1); v.z = __ldg(src + 2); v.w = __ldg(src + 3);
+tc_prep_kernel(const PrepArgs a) {
+  // a block = 64 consecutive rows of one matrix of one pair (row counts are multiples of 256)
+  __shared__ float s_max[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows_pair = a.Np + a.Mp;
+  const long long g0 = (long long)blockIdx.x * 64;
+  const int pair = (int)(g0 / rows_pair);
+  int row0 = (int)(g0 - (long long)pair * rows_pair);
+  const bool second = row0 >= a.Np;
+  if (second) row0 -= a.Np;
+  const float* X = second ? a.B + pair * a.strideB : a.A + pair * a.strideA;
+  const int NX = second ? a.M : a.N, NXp = second ? a.Mp : a.Np;
+  const int64_t ldx = second ? a.ldb : a.lda;
+  __nv_bfloat16* Xb = second ? a.Bb : a.Ab;
+  float* xnorm = second ? a.bnorm : a.anorm;
+  float* xerr = second ? a.berr : a.aerr;
+  float m_n = 0.f, m_b = 0.f, m_e = 0.f;
+  float4 v[kPrepRowsPerWarp];
+#pragma unroll
+  for (int k = 0; k < kPrepRowsPerWarp; ++k) {
+    const int row = row0 + warp * kPrepRowsPerWarp + k;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < NX) {
+      const float* src = X + (int64_t)row * ldx + lane * 4;
+      v[k].x = __ldg(src); v[k].y = __ldg(src + 1); v[k].z = __ldg(src + 2); v[k].w = __ldg(src + 3);
+    }
   }
-  float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  ss = warp_sum(ss);
-  const float nrm = sqrtf(ss) * 1.0000005f;  // never under-estimate the norm
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<unsigned*>(&lo);
-  pk.y = *reinterpret_cast<unsigned*>(&hi);
-  *reinterpret_cast<uint2*>(Xb + (int64_t)row * kD + lane * 4) = pk;
-  if (lane == 0) {
-    xnorm[row] = nrm;
-    if (row < NX) atomicMax(max_bits, __float_as_uint(nrm));
+#pragma unroll
+  for (int k = 0; k < kPrepRowsPerWarp; ++k) {
+    const int row = row0 + warp * kPrepRowsPerWarp + k;
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[k].x, v[k].y), hi = __floats2bfloat162_rn(v[k].z, v[k].w);
+    const float2 rl = __bfloat1622float2(lo), rh = __bfloat1622float2(hi);
+    float ss = v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    float sb = rl.x * rl.x + rl.y * rl.y + rh.x * rh.x + rh.y * rh.y;
+    const float ex = rl.x - v[k].x, ey = rl.y - v[k].y, ez = rh.x - v[k].z, ew = rh.y - v[k].w;
+    float se = ex * ex + ey * ey + ez * ez + ew * ew;
+    ss = warp_sum(ss); sb = warp_sum(sb); se = warp_sum(se);
+    const float up = 1.000001f;   // never under-estimate a norm (float32 rounding of the sums)
+    const float nrm = sqrtf(ss) * up, nrb = sqrtf(sb) * up, nre = sqrtf(se) * up;
+    uint2 pk;
+    pk.x = *reinterpret_cast<const unsigned*>(&lo);
+    pk.y = *reinterpret_cast<const unsigned*>(&hi);
+    const size_t r = (size_t)pair * NXp + row;
+    *reinterpret_cast<uint2*>(Xb + r * kD + lane * 4) = pk;
+    if (lane == 0) { xnorm[r] = nrm; xerr[r] = nre; }
+    m_n = fmaxf(m_n, nrm); m_b = fmaxf(m_b, nrb); m_e = fmaxf(m_e, nre);   // zero rows contribute 0
+  }
+  if (lane == 0) { s_max[0][warp] = m_n; s_max[1][warp] = m_b; s_max[2][warp] = m_e; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, s_max[threadIdx.x][k]);
+    unsigned* dst = &a.stats[2 * pair + (second ? 1 : 0)].max_norm + threadIdx.x;   // max_norm, max_norm_bf, max_err
+    if (__float_as_uint(m) > *(volatile unsigned*)dst) atomicMax(dst, __float_as_uint(m));
   }
 }
 
 // ------------------------------------------------------------------ rescoring
-// One warp per row of X: exact (float64) similarity of the candidate chunks.
+// One warp per row, both directions in one launch.  The row of the chunk-maximum
+// table gives the approximate row maximum F and the candidate chunks (>= F -
+// delta).  Candidates are evaluated in float32 (error <= kEps32 |x||y|); every
+// column within twice that band of the running float32 maximum is evaluated
+// exactly (float32 operands, float64 accumulation); the argmax of the exact
+// values wins, first index on ties.
+struct RescoreArgs {
+  DirParams d;
+  const float* X; int64_t ldx, strideX;   // pair stride in elements
+  const float* Y; int64_t ldy, strideY;
+  int32_t* nn;                            // [pairs][NX]
+};
+
 __global__ void __launch_bounds__(256)
-tc_rescore_kernel(const DirParams d, const float* __restrict__ X, int64_t ldx, const float* __restrict__ Y,
-                  int64_t ldy, int32_t* __restrict__ nn) {
-  __shared__ float xs[8][kD];
+tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
+  __shared__ __align__(16) float xs[8][kD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + w;
-  if (row >= d.NX) return;
+  const int rows_pair = a0.d.NX + a1.d.NX;
+  const long long g = (long long)blockIdx.x * 8 + w;
+  const int pair = (int)(g / rows_pair);
+  if (pair >= pairs) return;
+  int row = (int)(g - (long long)pair * rows_pair);
+  const bool second = row >= a0.d.NX;
+  if (second) row -= a0.d.NX;
+  const RescoreArgs& a = second ? a1 : a0;
+  const DirParams& d = a.d;
+  const float* __restrict__ Y = a.Y + pair * a.strideY;
+  const int64_t ldy = a.ldy;
   {
-    const float* src = X + (int64_t)row * ldx + lane * 4;
+    const float* src = a.X + pair * a.strideX + (int64_t)row * a.ldx + lane * 4;
     xs[w][lane * 4 + 0] = __ldg(src);
     xs[w][lane * 4 + 1] = __ldg(src + 1);
     xs[w][lane * 4 + 2] = __ldg(src + 2);
     xs[w][lane * 4 + 3] = __ldg(src + 3);
   }
+  // ---- pass 1 over the table row: F = max (pitch is a multiple of 16 halves; 8 per uint4)
+  const uint4* trow = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row) * d.pitch);
+  const int nvec = d.pitch >> 3;
+  __half2 hm = __float2half2_rn(-65504.f);
+  for (int i = lane; i < nvec; i += 32) {
+    const uint4 u = trow[i];
+    hm = __hmax2(hm, __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&u.x), *reinterpret_cast<const __half2*>(&u.y)),
+                             __hmax2(*reinterpret_cast<const __half2*>(&u.z), *reinterpret_cast<const __half2*>(&u.w))));
+  }
+  const float F = warp_max(fmaxf(__low2float(hm), __high2float(hm)));
+  const float xn = d.xnorm[(size_t)pair * d.NXpad + row], ymax = __uint_as_float(d.ystats[2 * pair].max_norm);
+  const float thr = F - (row_delta(d, pair, row) * table_scale(d, pair) + kHalfSlack);
+  const float band = 2.f * kEps32 * xn * ymax;
+  const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
   __syncwarp();
-  float F = -INFINITY;
-  for (int s = 0; s < d.splits; ++s) F = fmaxf(F, d.rowmax[(size_t)s * d.NXpad + row]);
-  const float thr = F - kDeltaScale * d.xnorm[row] * __uint_as_float(*d.ymax_bits);
 
-  double bestv = -INFINITY;
+  float m32 = -INFINITY;       // running float32 maximum over everything seen
+  double bestv = -INFINITY;    // exact best
   int besti = 0x7fffffff;
-  const int c = lane & 15, half = lane >> 4;
-  auto rescore = [&](int col0) {
-    const int col = col0 + c;
-    double acc = 0.0;
-    if (col < d.NY) {
-      const float* yr = Y + (int64_t)col * ldy + half * 64;
-      const float* xr = &xs[w][half * 64];
-#pragma unroll 4
-      for (int k = 0; k < 64; k += 4) {
-        acc = fma((double)xr[k], (double)__ldg(yr + k), acc);
-        acc = fma((double)xr[k + 1], (double)__ldg(yr + k + 1), acc);
-        acc = fma((double)xr[k + 2], (double)__ldg(yr + k + 2), acc);
-        acc = fma((double)xr[k + 3], (double)__ldg(yr + k + 3), acc);
-      }
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-    double v = col < d.NY ? acc : -INFINITY;
-    int i = col < d.NY ? col : 0x7fffffff;
+  const int c = lane & 7, kq = lane >> 3;   // column within the chunk, quarter of K
+  const float4* x4 = reinterpret_cast<const float4*>(&xs[w][0]);
+
+  auto exact_col = [&](int col) {   // whole warp: exact <x, y_col>
+    const float* yr = Y + (int64_t)col * ldy + lane * 4;
+    const float4 xv = x4[lane];
+    double acc = (double)xv.x * (double)__ldg(yr);
+    acc = fma((double)xv.y, (double)__ldg(yr + 1), acc);
+    acc = fma((double)xv.z, (double)__ldg(yr + 2), acc);
+    acc = fma((double)xv.w, (double)__ldg(yr + 3), acc);
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-    if (v > bestv || (v == bestv && i < besti)) { bestv = v; besti = i; }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (acc > bestv || (acc == bestv && col < besti)) { bestv = acc; besti = col; }
   };
 
-  for (int s = 0; s < d.splits; ++s) {
-    const size_t slot = (size_t)s * d.NXpad + row;
-    const int cnt = d.reccnt[slot];
-    if (cnt > kRecCap) {
-      // record list overflowed: exact scan of this split's whole column range
-      const int cb = s * d.tiles_per_split * kYRows;
-      const int ce = min(d.NY, (s + 1) * d.tiles_per_split * kYRows);
-      for (int col0 = cb; col0 < ce; col0 += 16) rescore(col0);
-    } else {
-      const uint2* r = d.rec + slot * kRecCap;
-      for (int k = 0; k < cnt; ++k) {
-        const uint2 e = r[k];
-        if (__uint_as_float(e.x) >= thr) rescore((int)e.y);
+  auto rescore = [&](int col0) {
+    const int col = col0 + c;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    if (col < d.NY) {
+      const float* yr = Y + (int64_t)col * ldy + kq * 32;
+      if (vec_ok) {
+        const float4* y4 = reinterpret_cast<const float4*>(yr);
+        float4 yv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) yv[q] = __ldg(y4 + q);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 xv = x4[kq * 8 + q];
+          q0 = fmaf(xv.x, yv[q].x, q0); q1 = fmaf(xv.y, yv[q].y, q1);
+          q2 = fmaf(xv.z, yv[q].z, q2); q3 = fmaf(xv.w, yv[q].w, q3);
+        }
+      } else {
+        for (int k = 0; k < 32; k += 4) {
+          q0 = fmaf(xs[w][kq * 32 + k], __ldg(yr + k), q0);
+          q1 = fmaf(xs[w][kq * 32 + k + 1], __ldg(yr + k + 1), q1);
+          q2 = fmaf(xs[w][kq * 32 + k + 2], __ldg(yr + k + 2), q2);
+          q3 = fmaf(xs[w][kq * 32 + k + 3], __ldg(yr + k + 3), q3);
+        }
+      }
+    }
+    float s32 = (q0 + q1) + (q2 + q3);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 16);
+    if (col >= d.NY) s32 = -INFINITY;
+    float cm = s32;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    m32 = fmaxf(m32, cm);
+    unsigned need = __ballot_sync(0xffffffffu, kq == 0 && s32 >= m32 - band);
+    while (need) {
+      const int l = __ffs(need) - 1;
+      need &= need - 1;
+      exact_col(col0 + l);
+    }
+  };
+
+  // ---- pass 2: candidate chunks (the table row is re-read: it is L1/L2 resident)
+  for (int i0 = 0; i0 < nvec; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned mask = 0;
+    if (i < nvec) {
+      const uint4 u = trow[i];
+      const unsigned wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[k]));
+        if (f.x >= thr) mask |= 1u << (2 * k);
+        if (f.y >= thr) mask |= 2u << (2 * k);
+      }
+    }
+    unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+    while (any) {
+      const int l = __ffs(any) - 1;
+      any &= any - 1;
+      unsigned mk = __shfl_sync(0xffffffffu, mask, l);
+      while (mk) {
+        const int k = __ffs(mk) - 1;
+        mk &= mk - 1;
+        rescore(((i0 + l) * 8 + k) * kChunk);
       }
     }
   }
-  if (lane == 0) nn[row] = besti == 0x7fffffff ? 0 : besti;
+  if (lane == 0) a.nn[(size_t)pair * d.NX + row] = besti == 0x7fffffff ? 0 : besti;
 }
 
 // ------------------------------------------------------------------ host side
@@ -454,17 +656,16 @@ static inline int pad_rows(int n) { return (n + kXRows - 1) / kXRows * kXRows; }
 
 struct TcWs {
   __nv_bfloat16 *Ab, *Bb;
-  float *anorm, *bnorm;
-  unsigned* maxn;  // [2]: max norm of A rows, of B rows
-  float* rowmax[2];
-  int* reccnt[2];
-  uint2* rec[2];
+  float *anorm, *aerr, *bnorm, *berr;
+  MatStats* stats;  // [pairs][2]: A, B
+  __half* table[2];
+  int pitch[2];
   size_t total;
 };
 
-static TcWs carve_tc(void* base, int N, int M) {
+static TcWs carve_tc(void* base, int P, int N, int M) {
   TcWs w;
-  const int Np = pad_rows(N), Mp = pad_rows(M);
+  const size_t Np = pad_rows(N), Mp = pad_rows(M);
   size_t off = 0;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -472,26 +673,27 @@ static TcWs carve_tc(void* base, int N, int M) {
     off += align_up(bytes, 1024);
     return r;
   };
-  w.Ab = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * (size_t)Np * kD);
-  w.Bb = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * (size_t)Mp * kD);
-  w.anorm = (float*)take(sizeof(float) * Np);
-  w.bnorm = (float*)take(sizeof(float) * Mp);
-  w.maxn = (unsigned*)take(sizeof(unsigned) * 2);
-  const int rows[2] = {Np, Mp};
-  for (int d = 0; d < 2; ++d) {
-    w.rowmax[d] = (float*)take(sizeof(float) * (size_t)kMaxSplits * rows[d]);
-    w.reccnt[d] = (int*)take(sizeof(int) * (size_t)kMaxSplits * rows[d]);
-    w.rec[d] = (uint2*)take(sizeof(uint2) * (size_t)kMaxSplits * rows[d] * kRecCap);
-  }
+  w.Ab = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * P * Np * kD);
+  w.Bb = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * P * Mp * kD);
+  w.anorm = (float*)take(sizeof(float) * P * Np);
+  w.aerr = (float*)take(sizeof(float) * P * Np);
+  w.bnorm = (float*)take(sizeof(float) * P * Mp);
+  w.berr = (float*)take(sizeof(float) * P * Mp);
+  w.stats = (MatStats*)take(sizeof(MatStats) * 2 * P);
+  // chunk-maximum tables: rows of X times (tiles of Y) * 32 chunks, fp16
+  w.pitch[0] = ((M + kYRows - 1) / kYRows) * (kYRows / kChunk);
+  w.pitch[1] = ((N + kYRows - 1) / kYRows) * (kYRows / kChunk);
+  w.table[0] = (__half*)take(sizeof(__half) * P * Np * w.pitch[0]);
+  w.table[1] = (__half*)take(sizeof(__half) * P * Mp * w.pitch[1]);
   w.total = off;
   return w;
 }
 
 bool tc_supported(int N, int M, int D) { return D == kD && N >= 1 && M >= 1; }
-size_t tc_workspace_bytes(int N, int M) { return carve_tc(nullptr, N, M).total; }
+size_t tc_workspace_bytes(int P, int N, int M) { return carve_tc(nullptr, P, N, M).total; }
 
 // choose the number of column splits so the persistent grid runs full waves
-static void choose_splits(int rb0, int yt0, int rb1, int yt1, int G, int* s0, int* s1) {
+static void choose_splits(int P, int rb0, int yt0, int rb1, int yt1, int G, int* s0, int* s1) {
   double best = -1.0;
   *s0 = *s1 = 1;
   for (int S = 1; S <= kMaxSplits; ++S) {
@@ -500,66 +702,81 @@ static void choose_splits(int rb0, int yt0, int rb1, int yt1, int G, int* s0, in
       return (yt + tps - 1) / tps;
     };
     const int u0 = used(yt0), u1 = used(yt1);
-    const long total = (long)rb0 * u0 + (long)rb1 * u1;
+    const long total = (long)P * ((long)rb0 * u0 + (long)rb1 * u1);
     const long waves = (total + G - 1) / G;
-    // cost model: every unit reloads its X block (2 tile-times), waves are quantised
-    const double tiles = (double)rb0 * yt0 + (double)rb1 * yt1;
-    const double per_wave = tiles / total + 0.7;
-    const double time = waves * per_wave;
-    const double score = 1.0 / time;
+    // cost model: waves are quantised; every unit pays a small cost for its (double buffered) X block
+    const double tiles = (double)P * ((double)rb0 * yt0 + (double)rb1 * yt1);
+    const double per_wave = tiles / total + 0.4;
+    const double score = 1.0 / (waves * per_wave);
     if (score > best * 1.02) { best = score; *s0 = u0; *s1 = u1; }
   }
 }
 
-int mnn_tc(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
-           int32_t* nn21, void* ws, size_t ws_bytes, cudaStream_t stream) {
+int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm, int64_t strideB, int M, int64_t ldb,
+           int D, int P, int32_t* nn12, int32_t* nn21, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (D != kD) return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
-  TcWs w = carve_tc(ws, N, M);
+  TcWs w = carve_tc(ws, P, N, M);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
-  if (((uintptr_t)ws & 1023) != 0) return set_error(POSFEAT_EINVAL, "mnn workspace must be 1024-byte aligned");
+  if (((uintptr_t)ws & 255) != 0) return set_error(POSFEAT_EINVAL, "mnn workspace must be 256-byte aligned");
   const int Np = pad_rows(N), Mp = pad_rows(M);
+  if ((long long)P * Np >= (1ll << 31) || (long long)P * Mp >= (1ll << 31))
+    return set_error(POSFEAT_EINVAL, "batched matcher: pairs * rows exceeds 2^31");
 
-  PF_CUDA(cudaMemsetAsync(w.maxn, 0, sizeof(unsigned) * 2, stream));
-  tc_prep_kernel<<<(Np + 7) / 8, 256, 0, stream>>>(A, N, lda, Np, w.Ab, w.anorm, w.maxn);
-  PF_LAUNCH_CHECK("tc_prep_kernel(A)");
-  tc_prep_kernel<<<(Mp + 7) / 8, 256, 0, stream>>>(Bm, M, ldb, Mp, w.Bb, w.bnorm, w.maxn + 1);
-  PF_LAUNCH_CHECK("tc_prep_kernel(B)");
+  PF_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(MatStats) * 2 * P, stream));
+  PrepArgs pa{A, lda, strideA, N, Np, Bm, ldb, strideB, M, Mp, w.Ab, w.Bb, w.anorm, w.aerr, w.bnorm, w.berr, w.stats, P};
+  const long long prep_warps = (long long)P * (Np + Mp);
+  prof_begin(PROF_MNN_PREP, stream);
+  tc_prep_kernel<<<(unsigned)(prep_warps / 64), 256, 0, stream>>>(pa);
+  prof_end(PROF_MNN_PREP, stream);
+  PF_LAUNCH_CHECK("tc_prep_kernel");
 
   CUtensorMap mapA, mapB;
-  if (int e = make_map(&mapA, w.Ab, Np)) return e;
-  if (int e = make_map(&mapB, w.Bb, Mp)) return e;
+  if (int e = make_map(&mapA, w.Ab, P * Np)) return e;
+  if (int e = make_map(&mapB, w.Bb, P * Mp)) return e;
 
   TcParams p;
-  const int G = sm_count();
+  const int G = sm_count() / 2;   // persistent CTA pairs
   const int rb0 = Np / kXRows, rb1 = Mp / kXRows;
   const int yt0 = (M + kYRows - 1) / kYRows, yt1 = (N + kYRows - 1) / kYRows;
   int s0, s1;
-  choose_splits(rb0, yt0, rb1, yt1, G, &s0, &s1);
-  auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int yt, int S) {
+  choose_splits(P, rb0, yt0, rb1, yt1, G, &s0, &s1);
+  auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int NYpad, int yt, int S) {
     d.xnorm = dir ? w.bnorm : w.anorm;
-    d.ymax_bits = dir ? w.maxn : w.maxn + 1;
-    d.rowmax = w.rowmax[dir];
-    d.reccnt = w.reccnt[dir];
-    d.rec = w.rec[dir];
-    d.NX = NX; d.NY = NY; d.NXpad = NXpad;
+    d.xerr = dir ? w.berr : w.aerr;
+    d.xstats = w.stats + (dir ? 1 : 0);
+    d.ystats = w.stats + (dir ? 0 : 1);
+    d.table = w.table[dir];
+    d.pitch = w.pitch[dir];
+    d.NX = NX; d.NY = NY; d.NXpad = NXpad; d.NYpad = NYpad;
     d.y_tiles = yt;
     d.tiles_per_split = (yt + S - 1) / S;
     d.splits = (yt + d.tiles_per_split - 1) / d.tiles_per_split;
+    d.row_blocks = NXpad / kXRows;
   };
-  fill(p.d[0], 0, N, M, Np, yt0, s0);
-  fill(p.d[1], 1, M, N, Mp, yt1, s1);
+  fill(p.d[0], 0, N, M, Np, Mp, yt0, s0);
+  fill(p.d[1], 1, M, N, Mp, Np, yt1, s1);
+  p.pairs = P;
   p.units0 = rb0 * p.d[0].splits;
-  p.units_total = p.units0 + rb1 * p.d[1].splits;
+  p.units_pair = p.units0 + rb1 * p.d[1].splits;
+  p.units_total = P * p.units_pair;
+  {
+    const char* dbg = getenv("POSFEAT_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
 
   PF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
-  const int grid = p.units_total < G ? p.units_total : G;
+  const int grid = 2 * (p.units_total < G ? p.units_total : G);
+  prof_begin(PROF_MNN_TC, stream);
   mnn_tc_kernel<<<grid, kTcThreads, kSmemAlloc, stream>>>(mapA, mapB, p);
+  prof_end(PROF_MNN_TC, stream);
   PF_LAUNCH_CHECK("mnn_tc_kernel");
 
-  tc_rescore_kernel<<<(N + 7) / 8, 256, 0, stream>>>(p.d[0], A, lda, Bm, ldb, nn12);
-  PF_LAUNCH_CHECK("tc_rescore_kernel(A->B)");
-  tc_rescore_kernel<<<(M + 7) / 8, 256, 0, stream>>>(p.d[1], Bm, ldb, A, lda, nn21);
-  PF_LAUNCH_CHECK("tc_rescore_kernel(B->A)");
+  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12}, r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21};
+  const long long resc_warps = (long long)P * (N + M);
+  prof_begin(PROF_MNN_RESCORE, stream);
+  tc_rescore_kernel<<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
+  prof_end(PROF_MNN_RESCORE, stream);
+  PF_LAUNCH_CHECK("tc_rescore_kernel");
   return POSFEAT_OK;
 }
 

@@ -166,6 +166,7 @@ extern "C" int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h,
   const int warps = 8;
   dim3 grid((n + warps - 1) / warps, B), block(32 * warps);
   __nv_bfloat16* ob = (__nv_bfloat16*)out_bf16;
+  ProfScope prof(PROF_SAMPLE, stream);
   const bool vec = sc == 1 && D % 4 == 0 && sx % 4 == 0 && sy % 4 == 0 && sb % 4 == 0 &&
                    ((uintptr_t)fmap % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                    (!ob || (uintptr_t)ob % 8 == 0);

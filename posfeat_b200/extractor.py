@@ -1,0 +1,106 @@
+"""Drop-in for the boundary functions of the reference's managers/extractor.py:
+``process`` (:318-355) and ``save_desc`` (:254-316), backed by the B200 kernels.
+
+The reference's Extractor shell (config/yaml/logging/dataloader) stays host
+Python and is out of scope; ``FeatureExtractor`` below only carries the state
+``process`` and ``save_desc`` read (config keys are the reference's).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import preprocess_utils as pu
+
+
+def process(inputs, outputs, config, detector=None, sift_kp=False, remove_pad=False):
+    """managers/extractor.py:318-355.  inputs: {'im1', 'name1', ['im1_ori','pad1','coord1','scale']},
+    outputs: {'local_map' [1,D,H/4,W/4], 'local_point' [1,1,H,W]}.
+    Returns {'kpt': ndarray (n,2) float32 pixel xy, 'desc': Tensor [1,n,D], 'kp_score': Tensor [1,n,1]}."""
+    detector = detector or pu.generate_kpts_single
+    desc_f = outputs["local_map"]
+    name = inputs["name1"][0]
+    if remove_pad:
+        b, c, h, w = inputs["im1_ori"].shape
+        pad = inputs["pad1"]
+        desc_f = desc_f[:, :, :-(pad[3] // 4), :-(pad[0] // 4)]
+        outputs["local_point"] = outputs["local_point"][:, :, :-(pad[3] // 4), :-(pad[0] // 4)]
+    else:
+        b, c, h, w = inputs["im1"].shape
+    if sift_kp:
+        coords = inputs["coord1"]
+        coord_n = pu.normalize_coords(coords, h, w)
+        kp_score = torch.ones_like(coord_n)[:, :, :1]
+    else:
+        cfg = config["detector_config"]
+        if config.get("data") == "Aachen_Day_Night" and name.split("/")[0] == "query":
+            cfg = config["detector_config_query"]
+        coord_n, kp_score = detector(outputs["local_point"], **cfg)
+        coords = pu.denormalize_coords(coord_n, h, w)
+    feat_f = pu.sample_feat_by_coord(desc_f, coord_n, config["loss_distance"] == "cos")
+    kpt = coords.cpu().numpy().squeeze(0)
+    if "scale" in inputs:
+        kpt = kpt * inputs["scale"].cpu().numpy()
+    return {"kpt": kpt, "desc": feat_f, "kp_score": kp_score}
+
+
+def save_desc(inputs, processed, desc_root, postfix, save_npz=True, save_h5=False, image_size=None):
+    """managers/extractor.py:254-316.  Writes ``<desc_root>/<name1>.<postfix>`` with
+    np.savez(keypoints (n,2) f32, scores (n,1) f32, descriptors (n,D) f32) -- a
+    file object is passed, so no '.npz' suffix is appended, exactly like the
+    reference.  The h5 layout follows SURVEY.md section 3.4 (the reference's own
+    h5 branch references undefined names); it needs h5py."""
+    kpt = processed["kpt"]
+    name = inputs["name1"][0]
+    save_path = os.path.join(desc_root, name)
+    os.makedirs(os.path.dirname(save_path), exist_ok=True)
+    desc = processed["desc"].squeeze(0).detach().cpu().numpy()
+    scores = processed["kp_score"].squeeze(0).detach().cpu().numpy()
+    message = "\nkpts: {}".format(kpt.shape[0])
+    if save_npz:
+        with open(save_path + ".{}".format(postfix), "wb") as f:
+            np.savez(f, keypoints=kpt, scores=scores, descriptors=desc)
+    if save_h5:
+        try:
+            import h5py
+        except ImportError as e:   # the authoring image has no h5py
+            raise RuntimeError("save_h5=True needs h5py, which is not installed") from e
+        h5_root = desc_root.rstrip("/") + "h5"
+        stem = name.split(".")[0]
+        seq, key = os.path.dirname(stem), os.path.basename(stem)
+        os.makedirs(os.path.join(h5_root, seq), exist_ok=True)
+        for fname, data in (("keypoints.h5", kpt), ("descriptors.h5", desc), ("scores.h5", scores),
+                            ("scales.h5", np.ones_like(scores))):
+            with h5py.File(os.path.join(h5_root, seq, fname), "a") as fh:
+                fh[key] = data
+        with h5py.File(os.path.join(h5_root, "feat.h5"), "a") as fh:
+            grp = fh.create_group(name)
+            grp.create_dataset("keypoints", data=kpt)
+            grp.create_dataset("scores", data=scores)
+            grp.create_dataset("descriptors", data=desc)
+            if image_size is not None:
+                grp.create_dataset("image_size", data=np.asarray(image_size))
+    return message
+
+
+class FeatureExtractor:
+    """Minimal carrier of the state Extractor.process/save_desc use (config keys
+    as in configs/extract_hpatches.yaml)."""
+
+    def __init__(self, config: dict, desc_root: str = None):
+        self.config = config
+        self.sift_kp = bool(config.get("use_sift", False))
+        self.detector = getattr(pu, config.get("detector", "generate_kpts_single"))
+        self.desc_root = desc_root
+        self.save_npz = config.get("save_npz", True)
+        self.save_h5 = config.get("save_h5", False)
+
+    def process(self, inputs, outputs, remove_pad=False):
+        return process(inputs, outputs, self.config, self.detector, self.sift_kp, remove_pad)
+
+    def save_desc(self, inputs, outputs, processed):
+        h, w = inputs["im1"].shape[2:]
+        return save_desc(inputs, processed, self.desc_root, self.config["postfix"], self.save_npz,
+                         self.save_h5, image_size=(w, h))

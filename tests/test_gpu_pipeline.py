@@ -1,0 +1,122 @@
+"""GPU parity: the fused pair pipeline, the batched matcher entry and the
+Extractor.process / save_desc boundary, against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _checks import assert_close_vec, check_mnn_near_tie
+from oracle import posfeat_oracle as O
+
+pytestmark = pytest.mark.gpu
+CFG = dict(nms_radius=1, num_pts=700, thr=0.9, thr_mod="abs", use_nms=True, stable=True)
+
+
+def small_pairs(P, seed=3, H=160, W=208, D=128):
+    g = torch.Generator().manual_seed(seed)
+    score = torch.nn.functional.softplus(torch.randn(2 * P, 1, H, W, generator=g))
+    fmap = torch.randn(2 * P, D, H // 4, W // 4, generator=g)
+    fmap[1::2] = fmap[0::2] + 0.4 * torch.randn(P, D, H // 4, W // 4, generator=g)
+    score[1::2] = score[0::2]
+    return score, fmap
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_pair_pipeline_vs_oracle(algo):
+    from posfeat_b200.pairs import PairPipeline
+    P = 3
+    score, fmap = small_pairs(P)
+    pipe = PairPipeline(CFG, mnn_algo=algo)
+    feats, matches, nm = pipe.run(score.cuda(), fmap.cuda())
+    cfg = {k: v for k, v in CFG.items() if k != "stable"}
+    okps, osc, oidx, _ = O.generate_kpts_single(score.numpy(), return_idx=True, **cfg)
+    np.testing.assert_array_equal(feats["idx"].cpu().numpy(), oidx)          # keypoint indices bit exact
+    np.testing.assert_allclose(feats["kps_n"].cpu().numpy(), okps, rtol=1e-5, atol=2e-6)
+    odesc = O.sample_feat_by_coord(fmap.numpy(), okps, True)
+    assert_close_vec(feats["desc"].cpu().numpy(), odesc, 1e-5)
+    np.testing.assert_allclose(feats["kpt"].cpu().numpy(), O.denormalize_coords(okps, 160, 208), rtol=1e-6, atol=1e-4)
+    for i in range(P):
+        want = O.mnn_matcher(odesc[2 * i], odesc[2 * i + 1], exact=True)
+        got = matches[i, :int(nm[i])].cpu().numpy()
+        check_mnn_near_tie(odesc[2 * i], odesc[2 * i + 1], got, want)
+        assert len(got) > 100
+
+
+def test_pipeline_host_entry_matches_device_entry():
+    from posfeat_b200.pairs import PairPipeline
+    score, fmap = small_pairs(2, seed=9)
+    pipe = PairPipeline(CFG)
+    feats, matches, nm = pipe.run(score.cuda(), fmap.cuda())
+    kpt_h, m_h, nm_h = pipe.run_host(score.pin_memory(), fmap.pin_memory())
+    assert kpt_h.device.type == "cpu"
+    assert torch.equal(kpt_h, feats["kpt"].cpu()) and torch.equal(nm_h, nm.cpu())
+    for i in range(2):
+        assert torch.equal(m_h[i, :int(nm_h[i])], matches[i, :int(nm[i])].cpu())
+
+
+def test_batched_matcher_equals_single_calls():
+    import posfeat_b200 as Pb
+    from posfeat_b200 import _lib
+    from posfeat_b200._runtime import check, lib, stream_ptr, workspace
+    L = lib()
+    g = torch.Generator().manual_seed(5)
+    P, N, M, D = 3, 700, 900, 128
+    A = torch.nn.functional.normalize(torch.randn(P, N, D, generator=g), dim=-1).cuda()
+    B = torch.nn.functional.normalize(torch.randn(P, M, D, generator=g), dim=-1).cuda()
+    for algo in (1, 2):
+        nn12 = torch.empty((P, N), dtype=torch.int32, device="cuda")
+        nn21 = torch.empty((P, M), dtype=torch.int32, device="cuda")
+        matches = torch.empty((P, N, 2), dtype=torch.int64, device="cuda")
+        nm = torch.empty(P, dtype=torch.int32, device="cuda")
+        ws = workspace("mnn", L.posfeat_mnn_batched_workspace_bytes(P, N, M, D, algo), A.device)
+        check(L.posfeat_mnn_batched_f32(A.data_ptr(), A.stride(0), N, A.stride(1), B.data_ptr(), B.stride(0), M,
+                                        B.stride(1), D, P, algo, nn12.data_ptr(), nn21.data_ptr(),
+                                        matches.data_ptr(), nm.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        stream_ptr(A.device)))
+        for i in range(P):
+            m1, n1, a12, a21 = Pb.mnn_match(A[i], B[i], algo=algo)
+            assert int(n1) == int(nm[i])
+            assert torch.equal(m1[:int(n1)], matches[i, :int(nm[i])])
+            assert torch.equal(a12, nn12[i]) and torch.equal(a21, nn21[i])
+            want = O.mnn_matcher(A[i].cpu().numpy(), B[i].cpu().numpy(), exact=True)
+            check_mnn_near_tie(A[i].cpu().numpy(), B[i].cpu().numpy(), m1[:int(n1)].cpu().numpy(), want)
+
+
+def test_extractor_process_and_npz(tmp_path):
+    """managers/extractor.py:318-355 + :254-271: dict contract and .npz layout."""
+    from posfeat_b200.extractor import FeatureExtractor
+    g = torch.Generator().manual_seed(21)
+    H, W = 96, 128
+    outputs = {"local_point": torch.nn.functional.softplus(torch.randn(1, 1, H, W, generator=g)).cuda(),
+               "local_map": torch.randn(1, 128, H // 4, W // 4, generator=g).cuda()}
+    inputs = {"im1": torch.zeros(1, 3, H, W), "name1": ["v_seq/1.ppm"]}
+    config = {"detector": "generate_kpts_single", "loss_distance": "cos", "postfix": "PoSFeat_test",
+              "detector_config": dict(num_pts=300, stable=True, use_nms=True, nms_radius=1, thr=0.9, thr_mod="abs")}
+    ex = FeatureExtractor(config, desc_root=str(tmp_path / "desc"))
+    pr = ex.process(inputs, outputs)
+    assert pr["kpt"].shape == (300, 2) and pr["kpt"].dtype == np.float32
+    assert tuple(pr["desc"].shape) == (1, 300, 128) and tuple(pr["kp_score"].shape) == (1, 300, 1)
+    okps, osc = O.generate_kpts_single(outputs["local_point"].cpu().numpy(), nms_radius=1, num_pts=300, thr=0.9,
+                                       thr_mod="abs")
+    np.testing.assert_allclose(pr["kpt"], O.denormalize_coords(okps, H, W)[0], rtol=1e-6, atol=1e-4)
+    ex.save_desc(inputs, outputs, pr)
+    path = os.path.join(str(tmp_path / "desc"), "v_seq", "1.ppm.PoSFeat_test")
+    assert os.path.exists(path)                                  # no '.npz' suffix, like the reference
+    z = np.load(path)
+    assert set(z.files) == {"keypoints", "scores", "descriptors"}
+    assert z["keypoints"].shape == (300, 2) and z["scores"].shape == (300, 1) and z["descriptors"].shape == (300, 128)
+    # the evaluation reader's path: np.load -> mnn_matcher on the descriptors
+    import posfeat_b200 as Pb
+    m = Pb.mnn_matcher(torch.from_numpy(z["descriptors"]), torch.from_numpy(z["descriptors"]))
+    np.testing.assert_array_equal(m, np.stack([np.arange(300)] * 2, -1))
+
+
+def test_install_patches_reference_style_module():
+    import types
+    import posfeat_b200 as Pb
+    fake = types.SimpleNamespace(generate_kpts_single=None, sample_feat_by_coord=None, mnn_matcher=None)
+    Pb.install(fake)
+    det = getattr(fake, "generate_kpts_single")                 # managers/extractor.py:87 style dispatch
+    k, s = det(torch.rand(1, 1, 40, 48).cuda() + 0.1, nms_radius=1, num_pts=140)
+    assert tuple(k.shape) == (1, 140, 2) and tuple(s.shape) == (1, 140, 1)
