@@ -121,6 +121,14 @@ int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h, int w,
                               const float* coord_n, int n, const int32_t* n_valid,
                               int do_norm, float* out, void* out_bf16, void* stream);
 
+/* Backward of the gather (training path, losses/preprocess.py:56-57): accumulates
+ * w_tap * g_out [B,n,D] into g_fmap (same strides as fmap, zero-initialised by
+ * the caller; float atomics).  The L2 normalisation is differentiated on the
+ * host side (plain tensor ops). */
+int posfeat_sample_bwd_f32(const float* g_out, int B, int D, int h, int w,
+                           int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                           const float* coord_n, int n, float* g_fmap, void* stream);
+
 /* ---- (3) mutual nearest neighbour matching ---------------------------------
  * Replaces mnn_matcher / mutual_nn_matcher: evaluations/hpatches/evaluation.py:27-38,
  * evaluations/aachen/matchers.py:5-13, evaluations/ETH_local_feature/custom_matcher.py:5-13,
@@ -171,8 +179,9 @@ int posfeat_mnn_host_f32(const float* A_host, int N, const float* B_host, int M,
  *   q [B,n,D], k [B,m,D] (row strides D), v [B or 1, m, C] value table
  *   (C <= 4: e.g. x, y, x^2, y^2); out [B,n,C] = sum_j softmax_j(scale*q.k_j) v_j;
  *   lse [B,n] = log-sum-exp of the scaled logits (saved for backward).
- * Backward: given g_out [B,n,C] produces g_q [B,n,D] and g_k [B,m,D]
- * (g_k is accumulated with atomics into a zero-initialised buffer).
+ * Backward: given g_out [B,n,C] produces g_q [B,n,D] and/or g_k [B,m,D] (either
+ * may be NULL); the logits are recomputed from (q, k, lse); no atomics.
+ * D <= 128, C <= 4.
  */
 int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, int v_batched,
                                 int B, int n, int m, int D, int C, float scale,
@@ -182,26 +191,30 @@ int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, 
                                 const float* out, const float* lse, const float* g_out,
                                 float* g_q, float* g_k, void* stream);
 
-/* Window variant: get_expected_correspondence_within_window,
- * losses/preprocess_utils.py:721-758.  fmap [B,D,h,w] with element strides
- * (sb,sc,sy,sx); q [B,n,D]; centre [B,n,2] normalised; offsets [m,2] (the
- * gen_grid(-ws,ws,...) table).  The [B,n,m,D] gathered tensor is never
- * materialised.  Outputs: exp_xy [B,n,2], std [B,n] (sum_xy sqrt(clamp(var,
- * 1e-10))), prob [B,n,m] (optional, may be NULL), lse [B,n].
- * Backward gets g_exp [B,n,2], g_std [B,n] and produces g_q [B,n,D] and
- * g_fmap (same strides as fmap, zero-initialised by the caller, atomics).
+/* Window / line variant.  mode 0: get_expected_correspondence_within_window,
+ * losses/preprocess_utils.py:721-758 -- positions = centre [B,n,2] + offsets [m,2]
+ * (the gen_grid(-ws,ws,...) table), grid_sample padding 'zeros'.  mode 1: the
+ * sampling half of epipolar_line_search, :668-675 -- centre holds two endpoints
+ * [B,n,4] = (x1,y1,x2,y2), positions = e1 + (e2-e1)*linspace(0,1,m), padding
+ * 'border'.  fmap [B,D,h,w] with element strides (sb,sc,sy,sx); q [B,n,D].  The
+ * [B,n,m,D] gathered tensor is never materialised.  Outputs: exp_xy [B,n,2] =
+ * sum_p prob_p pos_p, std [B,n] = sum_xy sqrt(clamp(var, 1e-10)), prob [B,n,m]
+ * (may be NULL), lse [B,n].
+ * Backward (mode 0): given g_exp [B,n,2] and g_std [B,n] produces g_q [B,n,D]
+ * and accumulates into g_fmap (same strides as fmap, zero-initialised by the
+ * caller, float atomics -- as ATen's grid_sampler backward does).
  */
 int posfeat_window_expect_fwd_f32(const float* fmap, int B, int D, int h, int w,
                                   int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                                   const float* q, const float* centre, int n,
-                                  const float* offsets, int m,
+                                  const float* offsets, int m, int mode,
                                   float* exp_xy, float* std_out, float* prob, float* lse,
                                   void* stream);
 int posfeat_window_expect_bwd_f32(const float* fmap, int B, int D, int h, int w,
                                   int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                                   const float* q, const float* centre, int n,
                                   const float* offsets, int m,
-                                  const float* exp_xy, const float* lse,
+                                  const float* exp_xy, const float* prob,
                                   const float* g_exp, const float* g_std,
                                   float* g_q, float* g_fmap, void* stream);
 

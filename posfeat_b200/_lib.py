@@ -37,6 +37,7 @@ SIGNATURES = {
     "posfeat_detect_status": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "posfeat_sample_l2norm_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _i, _vp,
                                        _vp, _vp]),
+    "posfeat_sample_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "posfeat_mnn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_mnn_batched_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
@@ -47,7 +48,7 @@ SIGNATURES = {
     "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "posfeat_corr_expect_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                          _vp]),
-    "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i,
+    "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i, _i,
                                            _vp, _vp, _vp, _vp, _vp]),
     "posfeat_window_expect_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

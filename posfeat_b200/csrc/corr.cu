@@ -1,23 +1,568 @@
-// Subsystem (4): training-side correlation + softmax expectation (placeholder:
-// entry points exist so the ABI is complete; kernels land next).
+// Subsystem (4): training-side correlation + softmax expectation for sm_100a.
+//
+// Dense variant (get_expected_correspondence_locs, reference
+// losses/preprocess_utils.py:55-82, and the grid<->grid stage of
+// Preprocess_Line2Window.forward, losses/preprocess.py:59-81):
+//     out[b,i,:] = sum_j softmax_j(scale * <q_i, k_j>) * v[j,:]
+// computed flash-style: 64x64 logit tiles in registers, online softmax, the
+// [B,n,m] probability tensor is never written.  The backward pass recomputes
+// the logits from (q, k, lse) and needs no atomics (one kernel owns rows of q,
+// one owns rows of k).
+//
+// Window / line variant (get_expected_correspondence_within_window,
+// losses/preprocess_utils.py:721-758; the sampling half of epipolar_line_search,
+// :662-675): per query, m sampling positions (centre + offset table, or a line
+// between two endpoints) are bilinearly gathered on the fly from the feature
+// map, dotted with the query and soft-maxed; the [B,n,m,D] gathered tensor of
+// the reference (943 MB at B=8, n=1200) is never materialised.
 #include "common.cuh"
+
+namespace posfeat {
+
+constexpr int kCT = 64;          // logit tile edge
+constexpr int kCDmax = 128;      // descriptor length supported by the dense kernels
+constexpr int kCmax = 4;         // value-table width
+
+// ---------------------------------------------------------------------------
+// dense forward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+corr_expect_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                       int v_batched, int n, int m, int D, int C, float scale, float* __restrict__ out,
+                       float* __restrict__ lse) {
+  __shared__ __align__(16) float Qs[32][kCT + 4];   // [kk][row]
+  __shared__ __align__(16) float Ks[32][kCT + 4];
+  __shared__ float Vs[kCT][kCmax];
+  const int b = blockIdx.y, row0 = blockIdx.x * kCT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* qb = q + (size_t)b * n * D;
+  const float* kb = k + (size_t)b * m * D;
+  const float* vb = v + (v_batched ? (size_t)b * m * C : 0);
+
+  float mrun[4], lpart[4], acc[4][kCmax];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mrun[i] = -INFINITY; lpart[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCmax; ++c) acc[i][c] = 0.f;
+  }
+  for (int col0 = 0; col0 < m; col0 += kCT) {
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += 32) {
+      for (int e = tid; e < kCT * 32; e += 256) {
+        const int r = e >> 5, kk = e & 31;
+        float qv = 0.f, kv = 0.f;
+        if (k0 + kk < D) {
+          if (row0 + r < n) qv = __ldg(qb + (size_t)(row0 + r) * D + k0 + kk);
+          if (col0 + r < m) kv = __ldg(kb + (size_t)(col0 + r) * D + k0 + kk);
+        }
+        Qs[kk][r] = qv;
+        Ks[kk][r] = kv;
+      }
+      if (k0 == 0) {
+        for (int e = tid; e < kCT * kCmax; e += 256) {
+          const int r = e / kCmax, c = e - r * kCmax;
+          Vs[r][c] = (c < C && col0 + r < m) ? __ldg(vb + (size_t)(col0 + r) * C + c) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
+        const float4 bq = *reinterpret_cast<const float4*>(&Ks[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+      }
+      __syncthreads();
+    }
+    // online softmax update (rows are shared by the 16 threads with the same ty)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (col0 + tx * 4 + j < m) ? s[i][j] * scale : -INFINITY;
+        tmax = fmaxf(tmax, s[i][j]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      const float mnew = fmaxf(mrun[i], tmax);
+      const float corr = (mrun[i] == -INFINITY) ? 0.f : expf(mrun[i] - mnew);
+      lpart[i] *= corr;
+#pragma unroll
+      for (int c = 0; c < kCmax; ++c) acc[i][c] *= corr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = (s[i][j] == -INFINITY) ? 0.f : expf(s[i][j] - mnew);
+        lpart[i] += p;
+#pragma unroll
+        for (int c = 0; c < kCmax; ++c) acc[i][c] = fmaf(p, Vs[tx * 4 + j][c], acc[i][c]);
+      }
+      mrun[i] = mnew;
+    }
+    __syncthreads();   // Vs is rewritten by the next tile
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      lpart[i] += __shfl_xor_sync(0xffffffffu, lpart[i], o);
+#pragma unroll
+      for (int c = 0; c < kCmax; ++c) acc[i][c] += __shfl_xor_sync(0xffffffffu, acc[i][c], o);
+    }
+    const int r = row0 + ty * 4 + i;
+    if (tx == 0 && r < n) {
+      const float inv = 1.f / lpart[i];
+      for (int c = 0; c < C; ++c) out[((size_t)b * n + r) * C + c] = acc[i][c] * inv;
+      lse[(size_t)b * n + r] = mrun[i] + logf(lpart[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dense backward: rows of X are owned by the CTA, Y is swept in 64-row tiles.
+//   kXisQ = true : X = q, Y = k, result g_q      kXisQ = false : X = k, Y = q, result g_k
+//   W(x,y) = exp(scale*<x,y> - lse[qi]) * (<g[qi], v[ki]> - <g[qi], out[qi]>)
+//   gX[x,:] = scale * sum_y W(x,y) * Y[y,:]
+// ---------------------------------------------------------------------------
+template <bool kXisQ>
+__global__ void __launch_bounds__(256)
+corr_expect_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                       int v_batched, int n, int m, int D, int C, float scale, const float* __restrict__ out,
+                       const float* __restrict__ lse, const float* __restrict__ g_out, float* __restrict__ gX) {
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;                        // [kCDmax][kCT+4]  (k-major)
+  float* Ys = Xs + kCDmax * (kCT + 4);     // [kCT][kCDmax+4]  (row-major: second GEMM reads rows)
+  float* Ws = Ys + kCT * (kCDmax + 4);     // [kCT x][kCT+1 y]
+  float* Yt = Ws + kCT * (kCT + 1);        // [32][kCT+4] k-major chunk of Y for the first GEMM
+  __shared__ float s_lse[kCT], s_go[kCT], s_g[kCT][kCmax], s_v[kCT][kCmax];
+
+  const int b = blockIdx.y, x0 = blockIdx.x * kCT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int nX = kXisQ ? n : m, nY = kXisQ ? m : n;
+  const float* Xg = (kXisQ ? q + (size_t)b * n * D : k + (size_t)b * m * D);
+  const float* Yg = (kXisQ ? k + (size_t)b * m * D : q + (size_t)b * n * D);
+  const float* vb = v + (v_batched ? (size_t)b * m * C : 0);
+  const float* ob = out + (size_t)b * n * C;
+  const float* gb = g_out + (size_t)b * n * C;
+  const float* lb = lse + (size_t)b * n;
+
+  // X tile, k-major, zero padded to kCDmax
+  for (int e = tid; e < kCT * kCDmax; e += 256) {
+    const int r = e / kCDmax, kk = e - r * kCDmax;
+    Xs[kk * (kCT + 4) + r] = (kk < D && x0 + r < nX) ? __ldg(Xg + (size_t)(x0 + r) * D + kk) : 0.f;
+  }
+  // per-row side data of the owner side
+  auto load_side = [&](int base, int count_q_side, bool is_q_side) {
+    if (tid < kCT) {
+      const int r = base + tid;
+      if (is_q_side) {
+        float go = 0.f;
+        for (int c = 0; c < kCmax; ++c) {
+          const float g = (c < C && r < n) ? __ldg(gb + (size_t)r * C + c) : 0.f;
+          const float o = (c < C && r < n) ? __ldg(ob + (size_t)r * C + c) : 0.f;
+          s_g[tid][c] = g;
+          go = fmaf(g, o, go);
+        }
+        s_go[tid] = go;
+        s_lse[tid] = r < n ? __ldg(lb + r) : INFINITY;      // exp(. - inf) = 0 for padding rows
+      } else {
+        for (int c = 0; c < kCmax; ++c) s_v[tid][c] = (c < C && r < m) ? __ldg(vb + (size_t)r * C + c) : 0.f;
+      }
+    }
+    (void)count_q_side;
+  };
+  load_side(x0, 0, kXisQ);
+
+  float acc[4][8];   // rows ty*4.., cols tx*8..  of gX tile [64][128]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int y0 = 0; y0 < nY; y0 += kCT) {
+    __syncthreads();
+    // Y tile row-major (for W*Y) ...
+    for (int e = tid; e < kCT * kCDmax; e += 256) {
+      const int r = e / kCDmax, kk = e - r * kCDmax;
+      Ys[r * (kCDmax + 4) + kk] = (kk < D && y0 + r < nY) ? __ldg(Yg + (size_t)(y0 + r) * D + kk) : 0.f;
+    }
+    load_side(y0, 0, !kXisQ);
+    __syncthreads();
+    // first GEMM: S = X * Y^T (64x64), Y re-staged k-major in 32-wide chunks
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += 32) {
+      for (int e = tid; e < kCT * 32; e += 256) {
+        const int r = e >> 5, kk = e & 31;
+        Yt[kk * (kCT + 4) + r] = Ys[r * (kCDmax + 4) + k0 + kk];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&Xs[(k0 + kk) * (kCT + 4) + ty * 4]);
+        const float4 bq = *reinterpret_cast<const float4*>(&Yt[kk * (kCT + 4) + tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+      }
+      __syncthreads();
+    }
+    // W tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xr = ty * 4 + i, yr = tx * 4 + j;
+        const int qi = kXisQ ? xr : yr, ki = kXisQ ? yr : xr;
+        float gv = 0.f;
+#pragma unroll
+        for (int c = 0; c < kCmax; ++c) gv = fmaf(s_g[qi][c], s_v[ki][c], gv);
+        const bool valid = (x0 + xr < nX) && (y0 + yr < nY);
+        const float p = valid ? expf(s[i][j] * scale - s_lse[qi]) : 0.f;
+        Ws[xr * (kCT + 1) + yr] = p * (gv - s_go[qi]);
+      }
+    __syncthreads();
+    // second GEMM: acc[64 x 128] += W[64 x 64] * Y[64 x 128]
+#pragma unroll 4
+    for (int yy = 0; yy < kCT; ++yy) {
+      const float4 y0v = *reinterpret_cast<const float4*>(&Ys[yy * (kCDmax + 4) + tx * 8]);
+      const float4 y1v = *reinterpret_cast<const float4*>(&Ys[yy * (kCDmax + 4) + tx * 8 + 4]);
+      const float yv[8] = {y0v.x, y0v.y, y0v.z, y0v.w, y1v.x, y1v.y, y1v.z, y1v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float wv = Ws[(ty * 4 + i) * (kCT + 1) + yy];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv, yv[j], acc[i][j]);
+      }
+    }
+  }
+  float* gXb = gX + (size_t)b * nX * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = x0 + ty * 4 + i;
+    if (r < nX)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j;
+        if (c < D) gXb[(size_t)r * D + c] = acc[i][j] * scale;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// window / line gather variant
+// ---------------------------------------------------------------------------
+struct TapSet {
+  int x0, y0;
+  float w00, w01, w10, w11;
+  bool in00, in01, in10, in11;
+};
+// align_corners=False unnormalisation; border=1 clamps the sampling coordinate
+__device__ __forceinline__ TapSet taps_of(float gx, float gy, int h, int w, int border) {
+  float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 0.5f);
+  float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 0.5f);
+  if (border) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(w - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(h - 1));
+  }
+  const float fx = floorf(ix), fy = floorf(iy);
+  TapSet t;
+  t.x0 = (int)fminf(fmaxf(fx, -2.f), (float)w);
+  t.y0 = (int)fminf(fmaxf(fy, -2.f), (float)h);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const bool xin0 = t.x0 >= 0 && t.x0 < w, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < w;
+  const bool yin0 = t.y0 >= 0 && t.y0 < h, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < h;
+  t.in00 = xin0 && yin0; t.in01 = xin1 && yin0; t.in10 = xin0 && yin1; t.in11 = xin1 && yin1;
+  t.w00 = wy0 * wx0; t.w01 = wy0 * wx1; t.w10 = wy1 * wx0; t.w11 = wy1 * wx1;
+  return t;
+}
+
+constexpr int kWinThreads = 128;
+constexpr int kWinMaxPts = 1024;
+constexpr int kWinCPL = 4;     // channels per lane: D <= 128
+
+// position p of query (b,i): mode 0 = centre + offsets[p];  mode 1 = e1 + (e2-e1)*linspace(0,1,m)[p]
+__device__ __forceinline__ float2 win_pos(int mode, const float* __restrict__ centre, const float* __restrict__ offsets,
+                                          size_t qi, int p, int m) {
+  if (mode == 0) {
+    const float2 c = *reinterpret_cast<const float2*>(centre + qi * 2);
+    const float2 o = *reinterpret_cast<const float2*>(offsets + (size_t)p * 2);
+    return make_float2(c.x + o.x, c.y + o.y);
+  }
+  const float4 e = *reinterpret_cast<const float4*>(centre + qi * 4);   // (x1, y1, x2, y2)
+  const float step = 1.0f / (float)(m - 1);
+  const float t = (p < m / 2) ? step * (float)p : 1.0f - step * (float)(m - 1 - p);   // torch.linspace(0, 1, m)
+  return make_float2(__fadd_rn(__fmul_rn(e.z - e.x, t), e.x), __fadd_rn(__fmul_rn(e.w - e.y, t), e.y));
+}
+
+__device__ __forceinline__ float gather_dot(const float* __restrict__ fb, const TapSet& t, int D, int64_t sc,
+                                            int64_t sy, int64_t sx, const float (&qv)[kWinCPL], int lane,
+                                            float (&sv)[kWinCPL]) {
+  const float* base = fb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kWinCPL; ++j) {
+    const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    if (c < D) {
+      const float* pc = base + (int64_t)c * sc;
+      if (t.in00) a00 = __ldg(pc);
+      if (t.in01) a01 = __ldg(pc + sx);
+      if (t.in10) a10 = __ldg(pc + sy);
+      if (t.in11) a11 = __ldg(pc + sy + sx);
+    }
+    sv[j] = a00 * t.w00 + a01 * t.w01 + a10 * t.w10 + a11 * t.w11;
+    dot = fmaf(sv[j], qv[j], dot);
+  }
+  return warp_sum(dot);
+}
+
+// one CTA (4 warps) per query
+__global__ void __launch_bounds__(kWinThreads)
+window_expect_fwd_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
+                         int64_t sx, const float* __restrict__ q, const float* __restrict__ centre, int n,
+                         const float* __restrict__ offsets, int m, int mode, float* __restrict__ exp_xy,
+                         float* __restrict__ std_out, float* __restrict__ prob, float* __restrict__ lse_out) {
+  __shared__ float z[kWinMaxPts], px[kWinMaxPts], py[kWinMaxPts];
+  __shared__ float red[8][kWinThreads / 32];
+  const int b = blockIdx.y, i = blockIdx.x;
+  const size_t qi = (size_t)b * n + i;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* fb = fmap + b * sb;
+  float qv[kWinCPL];
+#pragma unroll
+  for (int j = 0; j < kWinCPL; ++j) {
+    const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+    qv[j] = c < D ? __ldg(q + qi * D + c) : 0.f;
+  }
+  for (int p = warp; p < m; p += kWinThreads / 32) {
+    const float2 pos = win_pos(mode, centre, offsets, qi, p, m);
+    const TapSet t = taps_of(pos.x, pos.y, h, w, mode);
+    float sv[kWinCPL];
+    const float d = gather_dot(fb, t, D, sc, sy, sx, qv, lane, sv);
+    if (lane == 0) { z[p] = d; px[p] = pos.x; py[p] = pos.y; }
+  }
+  __syncthreads();
+  // softmax statistics over the m positions (block reduction)
+  float mx = -INFINITY;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) mx = fmaxf(mx, z[p]);
+  mx = warp_max(mx);
+  if (lane == 0) red[0][warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0][0], red[0][1]), fmaxf(red[0][2], red[0][3]));
+  float se = 0.f, sxv = 0.f, syv = 0.f, sxx = 0.f, syy = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) {
+    const float e = expf(z[p] - mx);
+    se += e; sxv = fmaf(e, px[p], sxv); syv = fmaf(e, py[p], syv);
+    sxx = fmaf(e, px[p] * px[p], sxx); syy = fmaf(e, py[p] * py[p], syy);
+  }
+  se = warp_sum(se); sxv = warp_sum(sxv); syv = warp_sum(syv); sxx = warp_sum(sxx); syy = warp_sum(syy);
+  if (lane == 0) { red[1][warp] = se; red[2][warp] = sxv; red[3][warp] = syv; red[4][warp] = sxx; red[5][warp] = syy; }
+  __syncthreads();
+  float tot[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tot[k] = red[1 + k][0] + red[1 + k][1] + red[1 + k][2] + red[1 + k][3];
+  const float inv = 1.f / tot[0];
+  const float ex = tot[1] * inv, ey = tot[2] * inv;
+  if (threadIdx.x == 0) {
+    exp_xy[qi * 2 + 0] = ex;
+    exp_xy[qi * 2 + 1] = ey;
+    const float vx = tot[3] * inv - ex * ex, vy = tot[4] * inv - ey * ey;
+    std_out[qi] = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
+    lse_out[qi] = mx + logf(tot[0]);
+  }
+  if (prob)
+    for (int p = threadIdx.x; p < m; p += kWinThreads) prob[qi * m + p] = expf(z[p] - mx) * inv;
+}
+
+// backward of the window variant (mode 0): g_q and g_fmap from (g_exp, g_std)
+__global__ void __launch_bounds__(kWinThreads)
+window_expect_bwd_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
+                         int64_t sx, const float* __restrict__ q, const float* __restrict__ centre, int n,
+                         const float* __restrict__ offsets, int m, const float* __restrict__ exp_xy,
+                         const float* __restrict__ prob, const float* __restrict__ g_exp,
+                         const float* __restrict__ g_std, float* __restrict__ g_q, float* __restrict__ g_fmap) {
+  __shared__ float dz[kWinMaxPts];
+  __shared__ float red[kWinThreads / 32];
+  __shared__ float gq_part[kWinThreads / 32][128];
+  const int b = blockIdx.y, i = blockIdx.x;
+  const size_t qi = (size_t)b * n + i;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float ex = exp_xy[qi * 2], ey = exp_xy[qi * 2 + 1];
+  const float gex = g_exp[qi * 2], gey = g_exp[qi * 2 + 1], gs = g_std[qi];
+  // variance of the window distribution (for the std gradient)
+  float sxx = 0.f, syy = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) {
+    const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+    const float pr = prob[qi * m + p];
+    sxx = fmaf(pr, pos.x * pos.x, sxx); syy = fmaf(pr, pos.y * pos.y, syy);
+  }
+  sxx = warp_sum(sxx); syy = warp_sum(syy);
+  if (lane == 0) { red[warp] = sxx; }
+  __syncthreads();
+  const float vx = red[0] + red[1] + red[2] + red[3] - ex * ex;
+  __syncthreads();
+  if (lane == 0) { red[warp] = syy; }
+  __syncthreads();
+  const float vy = red[0] + red[1] + red[2] + red[3] - ey * ey;
+  __syncthreads();
+  const float hx = vx > 1e-10f ? gs * 0.5f / sqrtf(vx) : 0.f;   // d std / d var_x (clamp kills the gradient)
+  const float hy = vy > 1e-10f ? gs * 0.5f / sqrtf(vy) : 0.f;
+  // dL/dP_p and its probability-weighted mean
+  float wsum = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) {
+    const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+    const float dP = gex * pos.x + gey * pos.y + hx * (pos.x * pos.x - 2.f * ex * pos.x) +
+                     hy * (pos.y * pos.y - 2.f * ey * pos.y);
+    dz[p] = dP;
+    wsum = fmaf(prob[qi * m + p], dP, wsum);
+  }
+  wsum = warp_sum(wsum);
+  if (lane == 0) red[warp] = wsum;
+  __syncthreads();
+  const float mean = red[0] + red[1] + red[2] + red[3];
+  for (int p = threadIdx.x; p < m; p += kWinThreads) dz[p] = prob[qi * m + p] * (dz[p] - mean);
+  __syncthreads();
+
+  const float* fb = fmap + b * sb;
+  float* gfb = g_fmap + b * sb;
+  float qv[kWinCPL], gq[kWinCPL];
+#pragma unroll
+  for (int j = 0; j < kWinCPL; ++j) {
+    const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+    qv[j] = c < D ? __ldg(q + qi * D + c) : 0.f;
+    gq[j] = 0.f;
+  }
+  for (int p = warp; p < m; p += kWinThreads / 32) {
+    const float d = dz[p];
+    if (d == 0.f) continue;
+    const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+    const TapSet t = taps_of(pos.x, pos.y, h, w, 0);
+    float* base = gfb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+    const float* rbase = fb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+#pragma unroll
+    for (int j = 0; j < kWinCPL; ++j) {
+      const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+      if (c >= D) continue;
+      const int64_t off = (int64_t)c * sc;
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+      const float gd = d * qv[j];
+      if (t.in00) { a00 = __ldg(rbase + off); atomicAdd(base + off, gd * t.w00); }
+      if (t.in01) { a01 = __ldg(rbase + off + sx); atomicAdd(base + off + sx, gd * t.w01); }
+      if (t.in10) { a10 = __ldg(rbase + off + sy); atomicAdd(base + off + sy, gd * t.w10); }
+      if (t.in11) { a11 = __ldg(rbase + off + sy + sx); atomicAdd(base + off + sy + sx, gd * t.w11); }
+      gq[j] = fmaf(d, a00 * t.w00 + a01 * t.w01 + a10 * t.w10 + a11 * t.w11, gq[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kWinCPL; ++j) {
+    const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+    gq_part[warp][c] = gq[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += kWinThreads)
+    g_q[qi * D + c] = gq_part[0][c] + gq_part[1][c] + gq_part[2][c] + gq_part[3][c];
+}
+
+}  // namespace posfeat
+
 using namespace posfeat;
 
-extern "C" int posfeat_corr_expect_fwd_f32(const float*, const float*, const float*, int, int, int, int, int, int,
-                                           float, float*, float*, void*) {
-  return set_error(POSFEAT_EUNSUPPORTED, "corr_expect_fwd not built yet");
+static int check_dense(const void* q, const void* k, const void* v, int B, int n, int m, int D, int C) {
+  PF_CHECK_ARG(q && k && v, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && B <= 65535 && n >= 1 && m >= 1, "bad shape B=%d n=%d m=%d", B, n, m);
+  PF_CHECK_ARG(D >= 1 && D <= kCDmax, "descriptor length %d outside [1, %d]", D, kCDmax);
+  PF_CHECK_ARG(C >= 1 && C <= kCmax, "value width %d outside [1, %d]", C, kCmax);
+  return 0;
 }
-extern "C" int posfeat_corr_expect_bwd_f32(const float*, const float*, const float*, int, int, int, int, int, int,
-                                           float, const float*, const float*, const float*, float*, float*, void*) {
-  return set_error(POSFEAT_EUNSUPPORTED, "corr_expect_bwd not built yet");
+
+extern "C" int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, int v_batched, int B, int n,
+                                           int m, int D, int C, float scale, float* out, float* lse, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_dense(q, k, v, B, n, m, D, C)) return e;
+  PF_CHECK_ARG(out && lse, "NULL output pointer");
+  dim3 grid((n + kCT - 1) / kCT, B);
+  ProfScope prof(PROF_CORR_FWD, stream);
+  corr_expect_fwd_kernel<<<grid, 256, 0, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse);
+  PF_LAUNCH_CHECK("corr_expect_fwd_kernel");
+  return POSFEAT_OK;
 }
-extern "C" int posfeat_window_expect_fwd_f32(const float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t,
-                                             const float*, const float*, int, const float*, int, float*, float*,
-                                             float*, float*, void*) {
-  return set_error(POSFEAT_EUNSUPPORTED, "window_expect_fwd not built yet");
+
+extern "C" int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, int v_batched, int B, int n,
+                                           int m, int D, int C, float scale, const float* out, const float* lse,
+                                           const float* g_out, float* g_q, float* g_k, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_dense(q, k, v, B, n, m, D, C)) return e;
+  PF_CHECK_ARG(out && lse && g_out && (g_q || g_k), "NULL pointer");
+  const size_t smem = sizeof(float) * (kCDmax * (kCT + 4) + kCT * (kCDmax + 4) + kCT * (kCT + 1) + 32 * (kCT + 4));
+  PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(PROF_CORR_BWD, stream);
+  if (g_q) {
+    dim3 grid((n + kCT - 1) / kCT, B);
+    corr_expect_bwd_kernel<true><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, g_q);
+    PF_LAUNCH_CHECK("corr_expect_bwd_kernel<q>");
+  }
+  if (g_k) {
+    dim3 grid((m + kCT - 1) / kCT, B);
+    corr_expect_bwd_kernel<false><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, g_k);
+    PF_LAUNCH_CHECK("corr_expect_bwd_kernel<k>");
+  }
+  return POSFEAT_OK;
 }
-extern "C" int posfeat_window_expect_bwd_f32(const float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t,
-                                             const float*, const float*, int, const float*, int, const float*,
-                                             const float*, const float*, const float*, float*, float*, void*) {
-  return set_error(POSFEAT_EUNSUPPORTED, "window_expect_bwd not built yet");
+
+static int check_window(const void* fmap, int B, int D, int h, int w, const void* q, const void* centre, int n, int m) {
+  PF_CHECK_ARG(fmap && q && centre, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && B <= 65535 && h >= 1 && w >= 1 && n >= 1, "bad shape B=%d h=%d w=%d n=%d", B, h, w, n);
+  PF_CHECK_ARG(D >= 1 && D <= 32 * kWinCPL, "descriptor length %d outside [1, %d]", D, 32 * kWinCPL);
+  PF_CHECK_ARG(m >= 1 && m <= kWinMaxPts, "number of sampling positions %d outside [1, %d]", m, kWinMaxPts);
+  return 0;
+}
+
+extern "C" int posfeat_window_expect_fwd_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc,
+                                             int64_t sy, int64_t sx, const float* q, const float* centre, int n,
+                                             const float* offsets, int m, int mode, float* exp_xy, float* std_out,
+                                             float* prob, float* lse, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_window(fmap, B, D, h, w, q, centre, n, m)) return e;
+  PF_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (window) or 1 (line)");
+  PF_CHECK_ARG(mode == 1 || offsets, "window mode needs an offset table");
+  PF_CHECK_ARG(mode == 0 || m >= 2, "line mode needs at least 2 samples");
+  PF_CHECK_ARG(exp_xy && std_out && lse, "NULL output pointer");
+  PF_CHECK_ARG(sc == 1 ? (D % kWinCPL == 0 || D <= 32 * kWinCPL) : true, "bad D");
+  dim3 grid(n, B);
+  ProfScope prof(PROF_WIN_FWD, stream);
+  window_expect_fwd_kernel<<<grid, kWinThreads, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, q, centre, n, offsets, m, mode,
+                                                              exp_xy, std_out, prob, lse);
+  PF_LAUNCH_CHECK("window_expect_fwd_kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_window_expect_bwd_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc,
+                                             int64_t sy, int64_t sx, const float* q, const float* centre, int n,
+                                             const float* offsets, int m, const float* exp_xy, const float* prob,
+                                             const float* g_exp, const float* g_std, float* g_q, float* g_fmap,
+                                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_window(fmap, B, D, h, w, q, centre, n, m)) return e;
+  PF_CHECK_ARG(offsets && exp_xy && prob && g_exp && g_std && g_q && g_fmap, "NULL pointer");
+  dim3 grid(n, B);
+  ProfScope prof(PROF_WIN_BWD, stream);
+  window_expect_bwd_kernel<<<grid, kWinThreads, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, q, centre, n, offsets, m, exp_xy,
+                                                              prob, g_exp, g_std, g_q, g_fmap);
+  PF_LAUNCH_CHECK("window_expect_bwd_kernel");
+  return POSFEAT_OK;
 }

@@ -24,6 +24,8 @@ constexpr int kSelThreads = 1024;
 constexpr int kSortSmemKeys = 16384;      // 128 KB of 64-bit keys
 constexpr int kFillBitmapWords = 2048;    // filler search covers the first 65536 pixels
 constexpr int kFillMax = 4096;
+constexpr int kDigitBits = 11;   // radix-select digit width (2048-bin shared histogram)
+constexpr int kUnroll = 8;       // independent candidate loads in flight per thread
 
 struct DetectWs {
   int32_t* cand_count;   // [B] positive-score survivors written to cand
@@ -205,6 +207,113 @@ nms_candidates_kernel(const float* __restrict__ score, int H, int W, int64_t sb,
   for (int i = threadIdx.x; i < n; i += kNmsThreads) dst[i] = s_list[i];
 }
 
+// ---- phase 1, fast path: register sliding window, one warp per vertical strip ----
+// For radius R <= 3 (and for use_nms=False, R = 0) a warp owns a strip of
+// 32 - 2R interior columns (R halo lanes on each side) and walks down kStripRows
+// rows.  Every input row is loaded once (coalesced), horizontal window maxima
+// come from warp shuffles, the vertical window lives in registers:
+//   keep(y,x) <=> c >  max over rows above of hmax(row)      (they precede in scan order)
+//              && c >  max of the R pixels to the left       (same row, precede)
+//              && c >= max of the R pixels to the right      (same row, follow)
+//              && c >= max over rows below of hmax(row)      (follow)
+// Kept pixels are pairwise non-adjacent, so a strip yields at most
+// ceil(rows/2)*ceil(cols/2) <= 512 survivors: they are staged in a per-warp
+// shared-memory list and flushed with ONE global atomic per warp.
+constexpr int kStripWarps = 8;
+constexpr int kStripList = 512;
+
+template <int R>
+__global__ void __launch_bounds__(kStripWarps * 32)
+nms_strip_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int64_t sy, int rows_per_strip,
+                 int has_thr, const float* __restrict__ thr_val, int32_t* __restrict__ counts,
+                 int32_t* __restrict__ cand_count, u64* __restrict__ cand, int64_t cand_cap) {
+  __shared__ u64 s_list[kStripWarps][kStripList];
+  constexpr int kUse = 32 - 2 * R;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int b = blockIdx.z;
+  const int hi = H - 2, wi = W - 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x = (blockIdx.x * kStripWarps + warp) * kUse + lane - R;   // interior column of this lane
+  const int y0 = blockIdx.y * rows_per_strip;
+  const int y1 = min(hi, y0 + rows_per_strip);
+  if ((blockIdx.x * kStripWarps + warp) * kUse >= wi) return;          // whole warp outside the map
+  const bool col_loadable = x < wi + R;                                // inside the reflect-padded extent
+  const int xr = reflect_idx(min(x, wi + R - 1), wi);
+  const bool col_eval = lane >= R && lane < 32 - R && x < wi;
+  const float* img = score + b * sb + xr + 1;
+  const float tv = has_thr ? thr_val[b] : 0.f;
+
+  // sliding state: hm[k] = horizontal window max of input row (yy - 2R + k); centre row = index R
+  float hm[2 * R + 1], cv[R + 1], lv[R + 1], rv[R + 1];
+#pragma unroll
+  for (int k = 0; k < 2 * R + 1; ++k) hm[k] = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < R + 1; ++k) { cv[k] = -INFINITY; lv[k] = -INFINITY; rv[k] = -INFINITY; }
+
+  int cnt = 0, n_all = 0;
+  constexpr int kBatch = 8;
+  for (int yb = y0 - R; yb < y1 + R; yb += kBatch) {
+    float in[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int yy = yb + k;
+      float v = -INFINITY;
+      if (col_loadable && yy < hi + R && yy < y1 + R) v = __ldg(img + (int64_t)(reflect_idx(yy, hi) + 1) * sy);
+      in[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int yy = yb + k;              // input row just loaded; the centre row is yy - R
+      const float v = in[k];
+      float L = -INFINITY, Rm = -INFINITY;
+#pragma unroll
+      for (int d = 1; d <= R; ++d) {
+        L = fmaxf(L, __shfl_up_sync(kFull, v, d));
+        Rm = fmaxf(Rm, __shfl_down_sync(kFull, v, d));
+      }
+      // shift the window down by one row
+#pragma unroll
+      for (int q = 0; q < 2 * R; ++q) hm[q] = hm[q + 1];
+      hm[2 * R] = fmaxf(fmaxf(L, Rm), v);
+#pragma unroll
+      for (int q = 0; q < R; ++q) { cv[q] = cv[q + 1]; lv[q] = lv[q + 1]; rv[q] = rv[q + 1]; }
+      cv[R] = v; lv[R] = L; rv[R] = Rm;
+      const int yc = yy - R;
+      const float c = cv[0];
+      bool keep = col_eval && yc >= y0 && yc < y1;
+      if (has_thr) keep = keep && c > tv;
+      if (R > 0) {
+        float above = -INFINITY, below = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < R; ++q) { above = fmaxf(above, hm[q]); below = fmaxf(below, hm[R + 1 + q]); }
+        keep = keep && c > above && c > lv[0] && c >= rv[0] && c >= below;
+      }
+      const unsigned ball = __ballot_sync(kFull, keep);
+      n_all += __popc(ball);
+      const bool emit = keep && c > 0.f;
+      const unsigned bal = __ballot_sync(kFull, emit);
+      if (bal) {
+        if (emit) {
+          const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+          const unsigned idx = (unsigned)yc * (unsigned)wi + (unsigned)x;
+          if (pos < kStripList) s_list[warp][pos] = ((u64)__float_as_uint(c) << 32) | (u64)(0xffffffffu - idx);
+        }
+        cnt += __popc(bal);
+      }
+    }
+  }
+  cnt = min(cnt, kStripList);   // cannot trigger: survivors of a strip are pairwise non-adjacent
+  __syncwarp();
+  int base = 0;
+  if (lane == 0) {
+    if (cnt) base = atomicAdd(cand_count + b, cnt);
+    if (n_all) atomicAdd(counts + b, n_all);
+  }
+  base = __shfl_sync(kFull, base, 0);
+  u64* dst = cand + (int64_t)b * cand_cap + base;
+  for (int i = lane; i < cnt; i += 32) dst[i] = s_list[warp][i];
+}
+
 // ---- phase 2: select + sort + centroid ------------------------------------
 __device__ void bitonic_steps(u64* a, int P, int k, int j_from, int j_to, int64_t gbase) {
   // descending bitonic network steps j = j_from, j_from/2, ..., j_to for stage k
@@ -221,19 +330,54 @@ __device__ void bitonic_steps(u64* a, int P, int k, int j_from, int j_to, int64_
   }
 }
 
-// Sort P (power of two) keys descending.  If `g` is shared memory (P <= CH) the
-// whole network runs there; otherwise steps with stride >= CH run in global
-// memory and the rest chunk by chunk through the shared buffer `s`.
+// Shared-memory bitonic network (descending), 4 independent compare-exchanges
+// per thread in flight.  `s` must point into shared memory.
+__device__ __forceinline__ void bitonic_steps_smem(u64* s, int P, int k, int j_from, int j_to, int64_t gbase) {
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s);
+  const int npairs = P >> 1;
+  for (int j = j_from; j >= j_to; j >>= 1) {
+    for (int base = 0; base < npairs; base += 4 * kSelThreads) {
+      u64 x[4], y[4];
+      unsigned ai[4], al[4];
+      bool act[4], up[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = base + u * kSelThreads + (int)threadIdx.x;
+        act[u] = p < npairs;
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        ai[u] = sbase + 8u * (unsigned)i;
+        al[u] = ai[u] + 8u * (unsigned)j;
+        up[u] = (((int64_t)i + gbase) & k) != 0;
+        if (act[u]) {
+          asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x[u]) : "r"(ai[u]));
+          asm volatile("ld.shared.u64 %0, [%1];" : "=l"(y[u]) : "r"(al[u]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (act[u] && (up[u] ? (x[u] > y[u]) : (x[u] < y[u]))) {
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(ai[u]), "l"(y[u]) : "memory");
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(al[u]), "l"(x[u]) : "memory");
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Sort P (power of two) keys descending.  If the keys live in shared memory (P <=
+// CH) the whole network runs there; otherwise steps with stride >= CH run in
+// global memory and the rest chunk by chunk through the shared buffer `s`.
 __device__ void bitonic_sort_desc(u64* g, int P, u64* s, int CH, bool in_smem) {
   if (in_smem) {
-    for (int k = 2; k <= P; k <<= 1) bitonic_steps(g, P, k, k >> 1, 1, 0);
+    for (int k = 2; k <= P; k <<= 1) bitonic_steps_smem(g, P, k, k >> 1, 1, 0);
     return;
   }
   const int nchunk = P / CH;
   for (int c = 0; c < nchunk; ++c) {
     for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[(int64_t)c * CH + i];
     __syncthreads();
-    for (int k = 2; k <= CH; k <<= 1) bitonic_steps(s, CH, k, k >> 1, 1, (int64_t)c * CH);
+    for (int k = 2; k <= CH; k <<= 1) bitonic_steps_smem(s, CH, k, k >> 1, 1, (int64_t)c * CH);
     for (int i = threadIdx.x; i < CH; i += blockDim.x) g[(int64_t)c * CH + i] = s[i];
     __syncthreads();
   }
@@ -242,7 +386,7 @@ __device__ void bitonic_sort_desc(u64* g, int P, u64* s, int CH, bool in_smem) {
     for (int c = 0; c < nchunk; ++c) {
       for (int i = threadIdx.x; i < CH; i += blockDim.x) s[i] = g[(int64_t)c * CH + i];
       __syncthreads();
-      bitonic_steps(s, CH, k, CH >> 1, 1, (int64_t)c * CH);
+      bitonic_steps_smem(s, CH, k, CH >> 1, 1, (int64_t)c * CH);
       for (int i = threadIdx.x; i < CH; i += blockDim.x) g[(int64_t)c * CH + i] = s[i];
       __syncthreads();
     }
@@ -259,12 +403,13 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
               float* __restrict__ kpscore_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* s_keys = (u64*)smem_raw;  // kSortSmemKeys
-  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_hist[1 << kDigitBits];
   __shared__ unsigned s_bitmap[kFillBitmapWords];
   __shared__ unsigned s_fill[kFillMax];
   __shared__ int s_cnt;
   __shared__ u64 s_prefix;
-  __shared__ int s_above, s_G, s_done;
+  __shared__ int s_above, s_G, s_done, s_shift0;
+  __shared__ u64 s_red[2][kSelThreads / 32];
 
   const int b = blockIdx.x;
   const int hi = H - 2, wi = W - 2;
@@ -294,31 +439,81 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   u64 LB = 0;
   int G = C;
   if (C > kSortSmemKeys) {
-    if (tid == 0) { s_prefix = 0; s_above = 0; s_done = 0; }
-    int shift = 56;
-    for (int pass = 0; pass < 8; ++pass, shift -= 8) {
-      for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+    // common leading bits (scores of one map share sign/exponent bits): start the
+    // radix walk at the first differing bit so the histogram bins actually spread
+    u64 kmin = ~0ull, kmax = 0ull;
+    for (int base = 0; base < C; base += kSelThreads * kUnroll) {
+      u64 k[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = base + u * kSelThreads + tid;
+        k[u] = i < C ? keys[i] : keys[0];
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        kmin = k[u] < kmin ? k[u] : kmin;
+        kmax = k[u] > kmax ? k[u] : kmax;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 a = __shfl_xor_sync(0xffffffffu, kmin, o), bb = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmin = a < kmin ? a : kmin;
+      kmax = bb > kmax ? bb : kmax;
+    }
+    if (lane == 0) { s_red[0][tid >> 5] = kmin; s_red[1][tid >> 5] = kmax; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < kSelThreads / 32; ++k) {
+        kmin = s_red[0][k] < kmin ? s_red[0][k] : kmin;
+        kmax = s_red[1][k] > kmax ? s_red[1][k] : kmax;
+      }
+      const u64 diff = kmin ^ kmax;
+      const int top = diff ? 63 - __clzll((long long)diff) : kDigitBits - 1;      // highest differing bit
+      int sh = top - (kDigitBits - 1);
+      if (sh < 0) sh = 0;
+      s_shift0 = sh;
+      s_prefix = sh + kDigitBits < 64 ? (kmax >> (sh + kDigitBits)) : 0ull;       // shared by every key
+      s_above = 0;
+      s_done = 0;
+    }
+    __syncthreads();
+    int shift = s_shift0, bits = kDigitBits;       // current digit = key bits [shift, shift + bits)
+    for (;;) {
+      for (int i = tid; i < (1 << kDigitBits); i += kSelThreads) s_hist[i] = 0;
       __syncthreads();
       const u64 prefix = s_prefix;
-      for (int i = tid; i < C; i += kSelThreads) {
-        const u64 key = keys[i];
-        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+      const bool top_pass = shift + bits >= 64;
+      const unsigned dmask = (1u << bits) - 1u;
+      for (int base = 0; base < C; base += kSelThreads * kUnroll) {
+        u64 k[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int i = base + u * kSelThreads + tid;
+          k[u] = i < C ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int i = base + u * kSelThreads + tid;
+          if (i < C && (top_pass || (k[u] >> (shift + bits)) == prefix))
+            atomicAdd(&s_hist[(unsigned)(k[u] >> shift) & dmask], 1u);
+        }
       }
       __syncthreads();
       if (tid == 0) {
         int cum = s_above;
-        int d = 255;
+        int d = (int)dmask;
         for (; d > 0; --d) {
           if (cum + (int)s_hist[d] >= n_real) break;
           cum += (int)s_hist[d];
         }
-        s_prefix = (prefix << 8) | (u64)d;
+        s_prefix = (prefix << bits) | (u64)d;
         s_above = cum;
         s_G = cum + (int)s_hist[d];
-        if (s_G <= kSortSmemKeys || pass == 7) s_done = 1;
+        if (s_G <= kSortSmemKeys || shift == 0) s_done = 1;
       }
       __syncthreads();
       if (s_done) break;
+      if (shift >= kDigitBits) { shift -= kDigitBits; } else { bits = shift; shift = 0; }
     }
     LB = s_prefix << shift;
     G = s_G;
@@ -334,17 +529,24 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   // ---- gather keys >= LB
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < C; i0 += kSelThreads) {
-    const int i = i0 + tid;
-    u64 key = 0;
-    bool take = false;
-    if (i < C) { key = keys[i]; take = key >= LB; }
-    const unsigned bal = __ballot_sync(0xffffffffu, take);
-    if (bal) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_cnt, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (take) buf[base + __popc(bal & ((1u << lane) - 1u))] = key;
+  for (int base = 0; base < C; base += kSelThreads * kUnroll) {
+    u64 k[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * kSelThreads + tid;
+      k[u] = i < C ? keys[i] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int i = base + u * kSelThreads + tid;
+      const bool take = i < C && k[u] >= LB;
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      if (bal) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&s_cnt, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (take) buf[pos + __popc(bal & ((1u << lane) - 1u))] = k[u];
+      }
     }
   }
   __syncthreads();
@@ -459,10 +661,26 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
                                                               w.red_max, w.thr_val);
     PF_LAUNCH_CHECK("finalize_thr_kernel");
   }
+  ProfScope prof(PROF_NMS, stream);
+  if (r <= 3) {
+    // register sliding-window kernel; without NMS every pixel may survive, so strips are 16 rows tall
+    const int rows = nms_mode == POSFEAT_NMS_HARD ? 64 : 16;
+    const int use = 32 - 2 * r;
+    dim3 grid((W - 2 + kStripWarps * use - 1) / (kStripWarps * use), (H - 2 + rows - 1) / rows, B);
+#define PF_STRIP(RR)                                                                                              \
+  nms_strip_kernel<RR><<<grid, kStripWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, rows, has_thr,     \
+                                                               w.thr_val, counts, w.cand_count, w.cand, w.cand_cap)
+    if (r == 0) PF_STRIP(0);
+    else if (r == 1) PF_STRIP(1);
+    else if (r == 2) PF_STRIP(2);
+    else PF_STRIP(3);
+#undef PF_STRIP
+    PF_LAUNCH_CHECK("nms_strip_kernel");
+    return POSFEAT_OK;
+  }
   const int pw = kTileW + 2 * r, ph = kTileH + 2 * r;
   const size_t smem = sizeof(float) * (size_t)ph * (pw | 1);
   dim3 grid((W - 2 + kTileW - 1) / kTileW, (H - 2 + kTileH - 1) / kTileH, B);
-  ProfScope prof(PROF_NMS, stream);
   nms_candidates_kernel<<<grid, kNmsThreads, smem, stream>>>(score, H, W, stride_b, stride_y, nms_mode, r, has_thr,
                                                              w.thr_val, counts, w.cand_count, w.cand, w.cand_cap);
   PF_LAUNCH_CHECK("nms_candidates_kernel");

@@ -149,6 +149,30 @@ sample_nhwc_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t 
   }
 }
 
+// backward of the bilinear gather: g_fmap[taps] += w_tap * g_out (float atomics, as
+// ATen's grid_sampler_2d_backward does); gradients w.r.t. the coordinates are not
+// needed on the reference's paths (keypoint coordinates are detached).
+__global__ void __launch_bounds__(256)
+sample_bwd_kernel(const float* __restrict__ g_out, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                  const float* __restrict__ coord, int n, float* __restrict__ g_fmap) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n) return;
+  const float2 g = *reinterpret_cast<const float2*>(coord + ((int64_t)b * n + p) * 2);
+  const Taps t = make_taps(g.x, g.y, h, w);
+  float* base = g_fmap + b * sb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
+  const float* go = g_out + ((int64_t)b * n + p) * D;
+  for (int c = lane; c < D; c += 32) {
+    const float gv = __ldg(go + c);
+    float* pc = base + (int64_t)c * sc;
+    if (t.in00) atomicAdd(pc, gv * t.w00);
+    if (t.in01) atomicAdd(pc + sx, gv * t.w01);
+    if (t.in10) atomicAdd(pc + sy, gv * t.w10);
+    if (t.in11) atomicAdd(pc + sy + sx, gv * t.w11);
+  }
+}
+
 }  // namespace posfeat
 
 using namespace posfeat;
@@ -190,5 +214,17 @@ extern "C" int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h,
       sample_strided_kernel<16><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
   }
   PF_LAUNCH_CHECK("sample kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_sample_bwd_f32(const float* g_out, int B, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
+                                      int64_t sx, const float* coord_n, int n, float* g_fmap, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(g_out && coord_n && g_fmap, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && B <= 65535 && D >= 1 && h >= 1 && w >= 1 && n >= 0, "bad shape");
+  if (n == 0) return POSFEAT_OK;
+  dim3 grid((n + 7) / 8, B);
+  sample_bwd_kernel<<<grid, 256, 0, stream>>>(g_out, D, h, w, sb, sc, sy, sx, coord_n, n, g_fmap);
+  PF_LAUNCH_CHECK("sample_bwd_kernel");
   return POSFEAT_OK;
 }

@@ -78,10 +78,9 @@ class PairPipeline:
         """Inputs in (pinned) host memory; returns host tensors: kpt [2P,n,2],
         matches [P,n,2], n_matches [P].  Copies are part of the call."""
         dev = torch.device("cuda", torch.cuda.current_device())
-        key = (tuple(score_host.shape), tuple(fmap_host.shape))
+        key = (tuple(score_host.shape), tuple(fmap_host.shape), tuple(fmap_host.stride()))
         if self._host is None or self._host[0] != key:
-            self._host = (key, torch.empty(score_host.shape, dtype=torch.float32, device=dev),
-                          torch.empty(fmap_host.shape, dtype=torch.float32, device=dev))
+            self._host = (key, torch.empty_like(score_host, device=dev), torch.empty_like(fmap_host, device=dev))
         _, s_dev, f_dev = self._host
         s_dev.copy_(score_host, non_blocking=True)
         f_dev.copy_(fmap_host, non_blocking=True)

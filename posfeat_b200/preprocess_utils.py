@@ -148,9 +148,9 @@ def sample_feat_by_coord(x, coord_n, norm=False):
     """losses/preprocess_utils.py:40-53: bilinear grid_sample (zeros padding,
     align_corners=False) at coord_n [b,n,2], optional L2 norm -> [b,n,c].
     Differentiable: the backward pass is in posfeat_b200.preprocess."""
-    if x.requires_grad or coord_n.requires_grad:
-        from .preprocess import SampleFeat
-        return SampleFeat.apply(x, coord_n, bool(norm))
+    if torch.is_grad_enabled() and x.requires_grad:
+        from .preprocess import sample_feat_by_coord_grad
+        return sample_feat_by_coord_grad(x, coord_n, bool(norm))
     xd, dev = to_device(x)
     cd, _ = to_device(coord_n)
     if cd.dim() != 3 or cd.shape[-1] != 2 or cd.shape[0] != xd.shape[0]:

@@ -1,0 +1,165 @@
+"""GPU parity: training-side correlation + softmax expectation (subsystem 4)."""
+import numpy as np
+import pytest
+import torch
+
+from _checks import assert_close_vec
+import _torch_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def t(x):
+    return torch.from_numpy(np.asarray(x)).cuda()
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-30)
+
+
+def test_dense_expectation_golden(golden):
+    """get_expected_correspondence_locs vs the reference's own output (1e-5 relative)."""
+    import posfeat_b200.preprocess as PP
+    g = golden("corr")
+    e, std, kurt, prob = PP.get_expected_correspondence_locs(t(g["f1"]), t(g["fm"]), with_std=True)
+    assert rel_err(e.cpu(), g["exp"]) < 1e-5
+    assert rel_err(std.cpu(), g["std"]) < 2e-5
+    assert rel_err(prob.cpu(), g["prob"]) < 2e-5
+    e2 = PP.get_expected_correspondence_locs(t(g["f1"]), t(g["fm"]))
+    assert torch.equal(e2, e)
+
+
+def test_window_expectation_golden(golden):
+    import posfeat_b200.preprocess as PP
+    g = golden("corr")
+    for fm in (t(g["fmw"]), t(g["fmw"]).contiguous(memory_format=torch.channels_last)):
+        e, cg, std, prob = PP.get_expected_correspondence_within_window(t(g["f1w"]), fm, t(g["c2"]), 0.1, with_std=True)
+        np.testing.assert_allclose(cg.cpu().numpy(), g["cgw"], rtol=0, atol=1e-7)
+        assert rel_err(prob.cpu(), g["probw"]) < 2e-5
+        assert rel_err(e.cpu(), g["expw"]) < 1e-5
+        assert rel_err(std.cpu(), g["stdw"]) < 1e-4      # sqrt of a small variance amplifies rounding
+
+
+@pytest.mark.parametrize("B,n,m,D,C,scale", [(2, 150, 170, 128, 4, 60.0), (1, 64, 64, 32, 2, 1.0),
+                                              (3, 33, 257, 100, 3, 10.0), (8, 512, 1200, 128, 4, 60.0)])
+def test_dense_forward_backward_vs_torch(B, n, m, D, C, scale):
+    import posfeat_b200.preprocess as PP
+    g = torch.Generator().manual_seed(n + m)
+    q = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=-1).cuda().requires_grad_()
+    k = torch.nn.functional.normalize(torch.randn(B, m, D, generator=g), dim=-1).cuda().requires_grad_()
+    v = (torch.rand(B, m, C, generator=g) * 100).cuda()
+    go = torch.randn(B, n, C, generator=g).cuda()
+    out = PP.corr_expect(q, k, v, scale)
+    out.backward(go)
+    gq, gk = q.grad.clone(), k.grad.clone()
+    q64, k64 = q.detach().double().requires_grad_(), k.detach().double().requires_grad_()
+    ref = R.corr_expect_ref(q64, k64, v.double(), scale)
+    ref.backward(go.double())
+    assert rel_err(out.detach().cpu(), ref.detach().cpu()) < 1e-5
+    assert rel_err(gq.cpu(), q64.grad.cpu()) < 1e-4
+    assert rel_err(gk.cpu(), k64.grad.cpu()) < 1e-4
+    # a shared (unbatched) value table gives the same result
+    if B > 1:
+        out1 = PP.corr_expect(q.detach(), k.detach(), v[0], scale)
+        refb = R.corr_expect_ref(q.detach().double(), k.detach().double(), v[0].double(), scale)
+        assert rel_err(out1.cpu(), refb.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_window_forward_backward_vs_torch(layout):
+    import posfeat_b200.preprocess as PP
+    g = torch.Generator().manual_seed(17)
+    B, n, D, h, w = 2, 90, 128, 30, 40
+    fm = (6 * torch.nn.functional.normalize(torch.randn(B, D, h, w, generator=g), dim=1)).cuda()
+    if layout == "channels_last":
+        fm = fm.contiguous(memory_format=torch.channels_last)
+    fm.requires_grad_()
+    q = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=-1).cuda().requires_grad_()
+    c = (torch.rand(B, n, 2, generator=g) * 2.1 - 1.05).cuda()
+    off = PP.gen_grid(-0.1, 0.1, -0.1, 0.1, int(0.1 * h), int(0.1 * w)).cuda()
+    ge, gs = torch.randn(B, n, 2, generator=g).cuda(), torch.randn(B, n, generator=g).cuda()
+    e, std, prob = PP.WindowExpect.apply(q, fm, c, off)
+    (e * ge).sum().add((std * gs).sum()).backward()
+    gq, gf = q.grad.clone(), fm.grad.clone()
+    q64 = q.detach().double().requires_grad_()
+    f64 = fm.detach().double().contiguous().requires_grad_()
+    er, sr, pr = R.window_ref(q64, f64, c.double(), off.double())
+    (er * ge.double()).sum().add((sr * gs.double()).sum()).backward()
+    assert rel_err(e.detach().cpu(), er.detach().cpu()) < 1e-5
+    assert rel_err(prob.cpu(), pr.detach().cpu()) < 2e-5
+    assert rel_err(std.detach().cpu(), sr.detach().cpu()) < 1e-4
+    assert rel_err(gq.cpu(), q64.grad.cpu()) < 2e-4
+    assert rel_err(gf.cpu(), f64.grad.cpu()) < 2e-4
+
+
+def test_sample_backward_vs_torch():
+    import posfeat_b200 as P
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 128, 20, 24, generator=g).cuda().requires_grad_()
+    c = (torch.rand(2, 300, 2, generator=g) * 2.06 - 1.03).cuda()
+    go = torch.randn(2, 300, 128, generator=g).cuda()
+    out = P.sample_feat_by_coord(x, c, True)
+    out.backward(go)
+    x64 = x.detach().double().requires_grad_()
+    ref = torch.nn.functional.normalize(
+        torch.nn.functional.grid_sample(x64, c.double().unsqueeze(2), padding_mode="zeros", align_corners=False).squeeze(-1),
+        p=2, dim=1).transpose(1, 2)
+    ref.backward(go.double())
+    assert_close_vec(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), 1e-5)
+    assert rel_err(x.grad.cpu(), x64.grad.cpu()) < 1e-4
+
+
+def test_preprocess_line2window_golden(golden):
+    """The whole Preprocess_Line2Window.forward (+ EpipolarLoss_full gradient) against
+    a run of the real reference with the same coordinates and jitter."""
+    import posfeat_b200.preprocess as PP
+    g = golden("preprocess")
+    H, W = int(g["H"]), int(g["W"])
+    cfg = dict(kps_generator="generate_kpts_regular_grid_random",
+               kps_generator_config=dict(grid_size=16, map_init="identity", keep_spatial=True, random_select="random"),
+               window_size=0.1, loss_distance="cos", use_nn_grid=False, use_line_search=True,
+               line_search_config=dict(line_step=100, use_nn=True, loc_rand=True),
+               temperature_base=60, temperature_max=60)
+    P = PP.Preprocess_Line2Window(cfg)
+    xf1, xf2 = t(g["xf1"]).requires_grad_(), t(g["xf2"]).requires_grad_()
+    B = xf1.shape[0]
+    inputs = dict(im1=torch.zeros(B, 3, H, W), im2=torch.zeros(B, 3, H, W), F1=t(g["F1"]), F2=t(g["F2"]))
+    outputs = dict(preds1=dict(local_map=xf1, local_point=torch.ones(B, 1, H, W).cuda()),
+                   preds2=dict(local_map=xf2, local_point=torch.ones(B, 1, H, W).cuda()), epoch=0)
+    pr = P(inputs, outputs, coords=(t(g["coord1_n"]), t(g["coord2_n"])), jitter=(t(g["jitter1"]), t(g["jitter2"])))
+    assert set(pr) == {"coord1", "coord2", "feat1g_corloc", "feat2g_corloc", "feat1w_corloc", "feat2w_corloc",
+                       "feat1c_corloc_org", "feat2c_corloc_org", "feat1g_std", "feat2g_std", "feat1w_std",
+                       "feat2w_std", "temperature", "valid_epi1", "valid_epi2"}
+    np.testing.assert_array_equal(pr["valid_epi1"].cpu().numpy(), g["p_valid_epi1"])
+    np.testing.assert_array_equal(pr["valid_epi2"].cpu().numpy(), g["p_valid_epi2"])
+    scale = float(max(H, W))
+    for key, tol in (("coord1", 1e-6), ("feat1g_corloc", 2e-5), ("feat2g_corloc", 2e-5), ("feat1c_corloc_org", 1e-5),
+                     ("feat2c_corloc_org", 1e-5), ("feat1w_corloc", 2e-5), ("feat2w_corloc", 2e-5)):
+        got, want = pr[key].detach().cpu().numpy(), g["p_" + key]
+        denom = scale if np.abs(want).max() > 2 else 1.0
+        assert np.max(np.abs(got - want)) / denom < tol, key
+    # std = sqrt(E[c^2] - E[c]^2) in float32 (reference :76-81, :749-750): the
+    # subtraction cancels to ~1e-7 absolute, so sqrt() turns rounding noise into up to
+    # ~5e-4 for sharply peaked windows -- in the reference as much as here.  Compare
+    # absolutely, on rows whose epipolar line is valid (the others hold inf/nan-derived
+    # garbage in the reference and are masked out of the loss).
+    for key, vkey in (("feat1g_std", "valid_epi1"), ("feat2g_std", "valid_epi2"), ("feat1w_std", "valid_epi1"),
+                      ("feat2w_std", "valid_epi2")):
+        ok = g["p_" + vkey].astype(bool)
+        got, want = pr[key].detach().cpu().numpy(), g["p_" + key]
+        assert np.max(np.abs(got - want)[ok]) < 1e-3, key
+        big = ok & (want > 0.02)
+        assert np.max(np.abs(got - want)[big] / want[big]) < 5e-3, key
+    # The loss weights are 1/std, detached (epipolarloss.py:25-36): feed the reference's
+    # own std values so the comparison of the loss and of its gradient is not dominated
+    # by that noise; everything differentiable comes from this implementation.
+    pr2 = dict(pr)
+    for key in ("feat1g_std", "feat2g_std", "feat1w_std", "feat2w_std"):
+        pr2[key] = t(g["p_" + key])
+    loss_cfg = dict(grid_cost_thr=0.5, win_cost_thr=0.1, use_std_as_weight=True, weight_grid=0.3, weight_window=1)
+    loss = R.epipolar_loss_full(inputs, pr2, loss_cfg)
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-4
+    loss.backward()
+    assert rel_err(xf1.grad.cpu(), g["gxf1"]) < 2e-3
+    assert rel_err(xf2.grad.cpu(), g["gxf2"]) < 2e-3
