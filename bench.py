@@ -125,6 +125,7 @@ def cpu_port_pair(score2, fmap2):
 
 
 def time_cpu_port(score, fmap, budget_s=12.0, max_pairs=16):
+    score, fmap = score[:8], fmap[:8]          # a bounded sample: at most the first 4 pairs are cycled through
     """Oracle on the host cores over a bounded sample of the same workload."""
     sn, fn = score.cpu().numpy(), fmap.cpu().numpy()
     P = sn.shape[0] // 2
@@ -175,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=16, help="pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fmap-layout", default="channels_last", choices=["channels_last", "nchw"])
     args = ap.parse_args()

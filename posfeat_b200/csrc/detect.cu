@@ -11,6 +11,8 @@
 //   centroid/score (:243-247), gather (:266-267) -> evaluated only at the winners
 //   gen_grid (:84-87, :217-221) -> computed in-kernel (bit exact linspace)
 // HBM-bound: the score map is read once (4 B/pixel); survivors cost 8 B each.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace posfeat {
@@ -25,6 +27,7 @@ constexpr int kSortSmemKeys = 16384;      // 128 KB of 64-bit keys
 constexpr int kFillBitmapWords = 2048;    // filler search covers the first 65536 pixels
 constexpr int kFillMax = 4096;
 constexpr int kDigitBits = 11;   // radix-select digit width (2048-bin shared histogram)
+constexpr int kBucketMax = 1024;  // boundary bucket small enough to be sorted on its own
 constexpr int kUnroll = 8;       // independent candidate loads in flight per thread
 
 struct DetectWs {
@@ -355,9 +358,11 @@ __device__ __forceinline__ void bitonic_steps_smem(u64* s, int P, int k, int j_f
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (act[u] && (up[u] ? (x[u] > y[u]) : (x[u] < y[u]))) {
-          asm volatile("st.shared.u64 [%0], %1;" ::"r"(ai[u]), "l"(y[u]) : "memory");
-          asm volatile("st.shared.u64 [%0], %1;" ::"r"(al[u]), "l"(x[u]) : "memory");
+        if (act[u]) {   // uniform except in the last partial group: always store, no divergent swap branch
+          const bool sw = up[u] ? (x[u] > y[u]) : (x[u] < y[u]);
+          const u64 a = sw ? y[u] : x[u], bq = sw ? x[u] : y[u];
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(ai[u]), "l"(a) : "memory");
+          asm volatile("st.shared.u64 [%0], %1;" ::"r"(al[u]), "l"(bq) : "memory");
         }
       }
     }
@@ -400,13 +405,14 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
               const u64* __restrict__ cand, int64_t cand_cap, u64* __restrict__ sortbuf,
               int64_t sort_cap, int32_t* __restrict__ status, int32_t* __restrict__ n_out,
               int64_t* __restrict__ idx_out, float* __restrict__ kps_out,
-              float* __restrict__ kpscore_out) {
+              float* __restrict__ kpscore_out, int debug) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* s_keys = (u64*)smem_raw;  // kSortSmemKeys
   __shared__ unsigned s_hist[1 << kDigitBits];
   __shared__ unsigned s_bitmap[kFillBitmapWords];
   __shared__ unsigned s_fill[kFillMax];
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_cnt_lo;
+  __shared__ int s_wsum[kSelThreads / 32];
   __shared__ u64 s_prefix;
   __shared__ int s_above, s_G, s_done, s_shift0;
   __shared__ u64 s_red[2][kSelThreads / 32];
@@ -415,6 +421,10 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   const int hi = H - 2, wi = W - 2;
   const int64_t n_interior = (int64_t)hi * wi;
   const int tid = threadIdx.x, lane = tid & 31;
+  long long tk[8];
+  int ntk = 0;
+#define PF_TICK() do { if (debug && b == 0 && tid == 0 && ntk < 8) tk[ntk++] = clock64(); } while (0)
+  PF_TICK();
 
   // n: :249-261 of the reference (min over the batch, then the 128 floor)
   int n;
@@ -427,6 +437,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     n = max(n, min_pts);
   }
   if (b == 0 && tid == 0) *n_out = n;
+  if (n == 0) return;
   if (n > cap_pts || (int64_t)n > n_interior) {
     if (tid == 0) atomicMax(status, n > cap_pts ? 1 : 2);
     return;
@@ -438,6 +449,11 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   // ---- lower bound LB with n_real <= #{key >= LB} = G, G small enough to sort
   u64 LB = 0;
   int G = C;
+  // after the radix walk: keys with (key >> hi_shift) > hi_prefix are certain winners (n_above of
+  // them), keys with (key >> hi_shift) == hi_prefix form the boundary bucket
+  bool split = false;
+  int hi_shift = 0, n_above = 0;
+  u64 hi_prefix = 0;
   if (C > kSortSmemKeys) {
     // common leading bits (scores of one map share sign/exponent bits): start the
     // radix walk at the first differing bit so the histogram bins actually spread
@@ -477,6 +493,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
       s_done = 0;
     }
     __syncthreads();
+    PF_TICK();
     int shift = s_shift0, bits = kDigitBits;       // current digit = key bits [shift, shift + bits)
     for (;;) {
       for (int i = tid; i < (1 << kDigitBits); i += kSelThreads) s_hist[i] = 0;
@@ -499,17 +516,37 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        int cum = s_above;
-        int d = (int)dmask;
-        for (; d > 0; --d) {
-          if (cum + (int)s_hist[d] >= n_real) break;
-          cum += (int)s_hist[d];
+      // find the digit d with  above(d) < n_real <= above(d) + hist[d]  (above = keys in higher
+      // bins): block-wide suffix sum, two bins per thread
+      {
+        const int nb = (int)dmask + 1;
+        const int b1 = 2 * tid + 1, b0 = 2 * tid;
+        const int h1 = b1 < nb ? (int)s_hist[b1] : 0, h0 = b0 < nb ? (int)s_hist[b0] : 0;
+        // inclusive scan over threads in DESCENDING tid order
+        int v = h0 + h1, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t2 = __shfl_down_sync(0xffffffffu, inc, o);
+          if (lane + o < 32) inc += t2;
         }
-        s_prefix = (prefix << bits) | (u64)d;
-        s_above = cum;
-        s_G = cum + (int)s_hist[d];
-        if (s_G <= kSortSmemKeys || shift == 0) s_done = 1;
+        if (lane == 0) s_wsum[tid >> 5] = inc;          // total of this warp
+        __syncthreads();
+        int higher = 0;                                   // sum over warps with larger index
+        for (int wq = (tid >> 5) + 1; wq < kSelThreads / 32; ++wq) higher += s_wsum[wq];
+        const int above1 = s_above + higher + (inc - v);  // keys in bins > b1
+        const int above0 = above1 + h1;                   // keys in bins > b0
+        __syncthreads();                                  // everyone has read s_above
+        const bool hit1 = b1 < nb && above1 < n_real && n_real <= above1 + h1;
+        const bool hit0 = b0 < nb && !hit1 && above0 < n_real && (n_real <= above0 + h0 || b0 == 0);
+        if (hit1 || hit0) {
+          const int d = hit1 ? b1 : b0;
+          const int cum = hit1 ? above1 : above0;
+          s_prefix = (prefix << bits) | (u64)d;
+          s_above = cum;
+          s_G = cum + (hit1 ? h1 : h0);
+          const int bucket = hit1 ? h1 : h0;
+          if ((s_G <= kSortSmemKeys && (bucket <= kBucketMax || cum + bucket == n_real)) || shift == 0) s_done = 1;
+        }
       }
       __syncthreads();
       if (s_done) break;
@@ -517,6 +554,10 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     }
     LB = s_prefix << shift;
     G = s_G;
+    hi_shift = shift;
+    hi_prefix = s_prefix;
+    n_above = s_above;
+    split = true;
   }
   const bool in_smem = G <= kSortSmemKeys;
   int P = 2;
@@ -526,8 +567,9 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     if (tid == 0) atomicMax(status, 3);
     return;
   }
-  // ---- gather keys >= LB
-  if (tid == 0) s_cnt = 0;
+  PF_TICK();
+  // ---- gather keys >= LB: certain winners from the front, boundary-bucket keys from the back
+  if (tid == 0) { s_cnt = 0; s_cnt_lo = 0; }
   __syncthreads();
   for (int base = 0; base < C; base += kSelThreads * kUnroll) {
     u64 k[kUnroll];
@@ -540,19 +582,46 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     for (int u = 0; u < kUnroll; ++u) {
       const int i = base + u * kSelThreads + tid;
       const bool take = i < C && k[u] >= LB;
-      const unsigned bal = __ballot_sync(0xffffffffu, take);
-      if (bal) {
+      const bool lo = take && split && (k[u] >> hi_shift) == hi_prefix;
+      const bool hi = take && !lo;
+      const unsigned bal_hi = __ballot_sync(0xffffffffu, hi);
+      const unsigned bal_lo = __ballot_sync(0xffffffffu, lo);
+      if (bal_hi) {
         int pos = 0;
-        if (lane == 0) pos = atomicAdd(&s_cnt, __popc(bal));
+        if (lane == 0) pos = atomicAdd(&s_cnt, __popc(bal_hi));
         pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (take) buf[pos + __popc(bal & ((1u << lane) - 1u))] = k[u];
+        if (hi) buf[pos + __popc(bal_hi & ((1u << lane) - 1u))] = k[u];
+      }
+      if (bal_lo) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&s_cnt_lo, __popc(bal_lo));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (lo) buf[G - 1 - (pos + __popc(bal_lo & ((1u << lane) - 1u)))] = k[u];
       }
     }
   }
   __syncthreads();
+  PF_TICK();
+  // ---- if the boundary bucket is small, sort it alone and keep its top (n_real - n_above):
+  // the final sort then runs on exactly n_real keys (half the network for n = 8192)
+  if (split && in_smem && G > n_real) {
+    const int pop = G - n_above;
+    int P2 = 2;
+    while (P2 < pop) P2 <<= 1;
+    if (pop <= kBucketMax && n_above + P2 <= kSortSmemKeys) {
+      for (int i = G + tid; i < n_above + P2; i += kSelThreads) buf[i] = 0;
+      __syncthreads();
+      for (int k = 2; k <= P2; k <<= 1) bitonic_steps_smem(buf + n_above, P2, k, k >> 1, 1, 0);
+      G = n_real;   // buf[0, n_real) now holds exactly the winners (unordered front + sorted bucket top)
+      P = 2;
+      while (P < G) P <<= 1;
+    }
+  }
   for (int i = G + tid; i < P; i += kSelThreads) buf[i] = 0;
   __syncthreads();
+  PF_TICK();
   bitonic_sort_desc(buf, P, s_keys, kSortSmemKeys, in_smem);
+  PF_TICK();
 
   // ---- filler for rows [n_real, n): lowest-index pixels that are not winners
   const int f = n - n_real;
@@ -611,6 +680,13 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     kps_out[2 * o + 1] = __fdiv_rn(__fdiv_rn(sy_, 9.0f), wgt);
     kpscore_out[o] = mx;
   }
+  PF_TICK();
+  if (debug && b == 0 && tid == 0) {
+    printf("select_kernel C=%d n=%d n_real=%d G=%d P=%d n_above=%d split=%d in_smem=%d shift=%d ticks:", C, n, n_real, G, P, n_above, (int)split, (int)in_smem, hi_shift);
+    for (int i = 1; i < ntk; ++i) printf(" %lld", tk[i] - tk[i - 1]);
+    printf("\n");
+  }
+#undef PF_TICK
 }
 
 static int check_common(const float* score, int B, int H, int W, int64_t sy) {
@@ -707,7 +783,8 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
   ProfScope prof(PROF_SELECT, stream);
   select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
                                                    counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,
-                                                   w.status, n_out, idx_out, kps_out, kpscore_out);
+                                                   w.status, n_out, idx_out, kps_out, kpscore_out,
+                                                   getenv("POSFEAT_SELECT_DEBUG") ? 1 : 0);
   PF_LAUNCH_CHECK("select_kernel");
   return POSFEAT_OK;
 }

@@ -496,7 +496,7 @@ struct RescoreArgs {
   int32_t* nn;                            // [pairs][NX]
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   __shared__ __align__(16) float xs[8][kD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -511,25 +511,45 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   const DirParams& d = a.d;
   const float* __restrict__ Y = a.Y + pair * a.strideY;
   const int64_t ldy = a.ldy;
-  {
-    const float* src = a.X + pair * a.strideX + (int64_t)row * a.ldx + lane * 4;
-    xs[w][lane * 4 + 0] = __ldg(src);
-    xs[w][lane * 4 + 1] = __ldg(src + 1);
-    xs[w][lane * 4 + 2] = __ldg(src + 2);
-    xs[w][lane * 4 + 3] = __ldg(src + 3);
-  }
-  // ---- pass 1 over the table row: F = max (pitch is a multiple of 16 halves; 8 per uint4)
+  // ---- pass 1 over the table row: F = max.  The row is walked in blocks of 128
+  // uint4 (1024 chunks); each lane holds 4 uint4 of a block, so rows of up to 1024
+  // chunks (M <= 8192) stay in registers for the candidate pass.
   const uint4* trow = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row) * d.pitch);
   const int nvec = d.pitch >> 3;
-  __half2 hm = __float2half2_rn(-65504.f);
-  for (int i = lane; i < nvec; i += 32) {
-    const uint4 u = trow[i];
-    hm = __hmax2(hm, __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&u.x), *reinterpret_cast<const __half2*>(&u.y)),
-                             __hmax2(*reinterpret_cast<const __half2*>(&u.z), *reinterpret_cast<const __half2*>(&u.w))));
+  const int nblk = (nvec + 127) >> 7;
+  const unsigned kNegInf2 = 0xFC00FC00u;   // half2(-inf, -inf)
+  uint4 tv[4];
+  auto load_block = [&](int blk) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = blk * 128 + r * 32 + lane;
+      tv[r] = i < nvec ? __ldg(trow + i) : make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
+    }
+  };
+  __half2 hm = *reinterpret_cast<const __half2*>(&kNegInf2);
+  load_block(0);
+  {
+    // the x row is fetched while the table loads are in flight
+    const float* xr = a.X + pair * a.strideX + (int64_t)row * a.ldx;
+    float4 xv;
+    if ((((uintptr_t)xr) & 15) == 0) {
+      xv = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+    } else {
+      xv.x = __ldg(xr + lane * 4); xv.y = __ldg(xr + lane * 4 + 1); xv.z = __ldg(xr + lane * 4 + 2); xv.w = __ldg(xr + lane * 4 + 3);
+    }
+    *reinterpret_cast<float4*>(&xs[w][lane * 4]) = xv;
+  }
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (blk > 0) load_block(blk);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      hm = __hmax2(hm, __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&tv[r].x), *reinterpret_cast<const __half2*>(&tv[r].y)),
+                               __hmax2(*reinterpret_cast<const __half2*>(&tv[r].z), *reinterpret_cast<const __half2*>(&tv[r].w))));
   }
   const float F = warp_max(fmaxf(__low2float(hm), __high2float(hm)));
   const float xn = d.xnorm[(size_t)pair * d.NXpad + row], ymax = __uint_as_float(d.ystats[2 * pair].max_norm);
   const float thr = F - (row_delta(d, pair, row) * table_scale(d, pair) + kHalfSlack);
+  const __half2 thr2 = __float2half2_rn(__half2float(__float2half_rd(thr)));   // rounded down: never drops a candidate
   const float band = 2.f * kEps32 * xn * ymax;
   const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
   __syncwarp();
@@ -593,29 +613,30 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     }
   };
 
-  // ---- pass 2: candidate chunks (the table row is re-read: it is L1/L2 resident)
-  for (int i0 = 0; i0 < nvec; i0 += 32) {
-    const int i = i0 + lane;
-    unsigned mask = 0;
-    if (i < nvec) {
-      const uint4 u = trow[i];
-      const unsigned wds[4] = {u.x, u.y, u.z, u.w};
+  // ---- pass 2: candidate chunks = table entries >= thr
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (nblk > 1) load_block(blk);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned wds[4] = {tv[r].x, tv[r].y, tv[r].z, tv[r].w};
+      unsigned mask = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wds[k]));
-        if (f.x >= thr) mask |= 1u << (2 * k);
-        if (f.y >= thr) mask |= 2u << (2 * k);
+        const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wds[k]), thr2);   // 1.0 / 0.0 per half
+        const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
+        mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * k);
+        mask |= ((bits >> 16) ? 1u : 0u) << (2 * k + 1);
       }
-    }
-    unsigned any = __ballot_sync(0xffffffffu, mask != 0);
-    while (any) {
-      const int l = __ffs(any) - 1;
-      any &= any - 1;
-      unsigned mk = __shfl_sync(0xffffffffu, mask, l);
-      while (mk) {
-        const int k = __ffs(mk) - 1;
-        mk &= mk - 1;
-        rescore(((i0 + l) * 8 + k) * kChunk);
+      unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+      while (any) {
+        const int l = __ffs(any) - 1;
+        any &= any - 1;
+        unsigned mk = __shfl_sync(0xffffffffu, mask, l);
+        while (mk) {
+          const int k = __ffs(mk) - 1;
+          mk &= mk - 1;
+          rescore(((blk * 128 + r * 32 + l) * 8 + k) * kChunk);
+        }
       }
     }
   }
