@@ -168,7 +168,7 @@ extern "C" int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, 
                                        int32_t* nn21, int64_t* matches, int32_t* n_matches, void* workspace,
                                        size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PF_CHECK_ARG(A && Bm && nn12 && nn21 && matches && n_matches && workspace, "NULL pointer");
+  PF_CHECK_ARG(A && Bm && nn12 && matches && n_matches && workspace, "NULL pointer");
   PF_CHECK_ARG(P >= 1 && P <= 65535, "pairs=%d outside [1, 65535]", P);
   PF_CHECK_ARG(N >= 1 && M >= 1 && D >= 1, "empty operand (N=%d M=%d D=%d): the reference's torch.max raises on an empty reduction too", N, M, D);
   PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
@@ -179,8 +179,10 @@ extern "C" int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, 
   if (a == POSFEAT_MNN_TC) {
     if (!tc_supported(N, M, D))
       return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
-    if (int e = mnn_tc(A, stride_a, N, lda, Bm, stride_b, M, ldb, D, P, nn12, nn21, workspace, ws_bytes, stream)) return e;
+    return mnn_tc(A, stride_a, N, lda, Bm, stride_b, M, ldb, D, P, nn12, nn21, matches, n_matches, workspace, ws_bytes,
+                  stream);
   } else {
+    PF_CHECK_ARG(nn21 != nullptr, "the exact SIMT matcher needs an nn21 buffer");
     for (int p = 0; p < P; ++p)
       if (int e = mnn_simt(A + p * stride_a, N, lda, Bm + p * stride_b, M, ldb, D, nn12 + (size_t)p * N,
                            nn21 + (size_t)p * M, workspace, stream))

@@ -67,6 +67,7 @@ struct DirParams {            // all arrays are batched over pairs: index = pair
   const MatStats* xstats;      // [pairs][2] -> element pair*2 + which (set up per direction)
   const MatStats* ystats;
   __half* table;               // [pairs][NXpad][pitch] chunk maxima, scaled by 1/(max|x| max|y|)
+  __half* tableT;              // optional transposed copy [pairs][pitch][NXpad] (matches-only path)
   int pitch;                   // y_tiles * 32 chunks per row
   int NX, NY, NXpad, NYpad;
   int splits, tiles_per_split, y_tiles;
@@ -397,6 +398,15 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           hi = reduce32<true>(vb, c0 + 32, d.NY, scale);
         }
         *reinterpret_cast<uint4*>(trow + t * 32) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        if (d.tableT) {
+          // chunk-major copy: for a fixed chunk the 32 lanes (rows) write 64 contiguous bytes
+          unsigned short* tc = reinterpret_cast<unsigned short*>(d.tableT) +
+                               ((size_t)q.pair * d.pitch + (size_t)t * 32 + j * 8) * d.NXpad + row;
+          const unsigned wv[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            tc[(size_t)c8 * d.NXpad] = (unsigned short)((c8 & 1) ? (wv[c8 >> 1] >> 16) : (wv[c8 >> 1] & 0xffffu));
+        }
       }
     }
   }
@@ -494,6 +504,7 @@ struct RescoreArgs {
   const float* X; int64_t ldx, strideX;   // pair stride in elements
   const float* Y; int64_t ldy, strideY;
   int32_t* nn;                            // [pairs][NX]
+  float* best;                            // optional [pairs][NX]: exact best similarity, rounded down
 };
 
 __global__ void __launch_bounds__(256, 4)
@@ -640,7 +651,342 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
       }
     }
   }
-  if (lane == 0) a.nn[(size_t)pair * d.NX + row] = besti == 0x7fffffff ? 0 : besti;
+  if (lane == 0) {
+    a.nn[(size_t)pair * d.NX + row] = besti == 0x7fffffff ? 0 : besti;
+    if (a.best) a.best[(size_t)pair * d.NX + row] = __double2float_rd(bestv);
+  }
+}
+
+// ------------------------------------------------------------------ matches-only path
+// When the caller does not need nn21 the second direction is not computed at all.
+// i and j = nn12[i] are mutual iff no row i' has S[i'][j] > S[i][j] (or == with i' < i).
+// The chunk-maximum table of the first direction bounds S[i'][j] from above for every
+// i', so only rows whose entry in chunk j/8 comes within the error bound of S[i][j] can
+// beat i; those few are checked exactly.  Rows are first grouped by the chunk of their
+// nearest neighbour so each chunk column of the transposed table is scanned once.
+constexpr int kVerMaxChunks = 8192;   // M <= 65536 on this path
+
+__global__ void __launch_bounds__(1024)
+tc_group_kernel(const int32_t* __restrict__ nn12, const float* __restrict__ best, int N, int nchunks,
+                int32_t* __restrict__ offsets, int4* __restrict__ members, unsigned char* __restrict__ mutual) {
+  __shared__ int cnt[kVerMaxChunks];
+  __shared__ int wsum[32];
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t* nn = nn12 + (size_t)pair * N;
+  for (int c = tid; c < nchunks; c += 1024) cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += 1024) {
+    atomicAdd(&cnt[nn[i] >> 3], 1);
+    mutual[(size_t)pair * N + i] = 1;
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..nchunks) (each thread owns a contiguous run of ceil(nchunks/1024) bins)
+  const int per = (nchunks + 1023) / 1024;
+  int local = 0;
+  for (int k = 0; k < per; ++k) {
+    const int c = tid * per + k;
+    if (c < nchunks) local += cnt[c];
+  }
+  int inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = wsum[lane];
+    int w2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w2, o);
+      if (lane >= o) w2 += t;
+    }
+    wsum[lane] = w2 - v;
+  }
+  __syncthreads();
+  int run = wsum[wid] + inc - local;
+  int32_t* off = offsets + (size_t)pair * (nchunks + 1);
+  for (int k = 0; k < per; ++k) {
+    const int c = tid * per + k;
+    if (c < nchunks) {
+      const int v = cnt[c];
+      off[c] = run;
+      cnt[c] = run;      // becomes the fill cursor
+      run += v;
+    }
+  }
+  if (tid == 1023) off[nchunks] = N;
+  __syncthreads();
+  for (int i = tid; i < N; i += 1024) {
+    const int j = nn[i];
+    const int pos = atomicAdd(&cnt[j >> 3], 1);
+    members[(size_t)pair * N + pos] = make_int4(i, j, __float_as_int(best[(size_t)pair * N + i]), 0);
+  }
+}
+
+struct VerifyArgs {
+  DirParams d;
+  const float* X; int64_t ldx, strideX;
+  const float* Y; int64_t ldy, strideY;
+  const int32_t* offsets;    // [pairs][nchunks+1]
+  const int4* members;       // [pairs][NX]: (i, j = nn12[i], bits of best[i], -) grouped by chunk of j
+  unsigned char* mutual;     // [pairs][NX]
+  int nchunks;
+};
+
+// Exact similarities of one row x (float4 per lane) to the 8 columns of a chunk (yv: float4 per
+// lane and column), float64, by the whole warp.  A fixed transposing butterfly leaves value
+// (lane >> 2) & 7 in every lane; the association tree is the same for all eight values and all
+// rows, so identical inputs give identical results.  The 8 results are written to e_out[0..7].
+__device__ __forceinline__ void warp_chunk_dots(const float4 xv, const float4* __restrict__ ysm, int lane,
+                                                double* __restrict__ e_out) {
+  double p[kChunk];
+  const double x0 = (double)xv.x, x1 = (double)xv.y, x2 = (double)xv.z, x3 = (double)xv.w;
+#pragma unroll
+  for (int r = 0; r < kChunk; ++r) {
+    const float4 y = ysm[r * 32 + lane];       // column r of the chunk, this lane's 4 components
+    double acc = x0 * (double)y.x;
+    acc = fma(x1, (double)y.y, acc);
+    acc = fma(x2, (double)y.z, acc);
+    acc = fma(x3, (double)y.w, acc);
+    p[r] = acc;
+  }
+  // xor 16: lanes with bit4 = 0 keep values 0..3, the others 4..7
+  double q4[4];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const double send = hi ? p[r] : p[r + 4];
+      const double got = __shfl_xor_sync(0xffffffffu, send, 16);
+      q4[r] = (hi ? p[r + 4] : p[r]) + got;
+    }
+  }
+  double q2[2];
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double send = hi ? q4[r] : q4[r + 2];
+      const double got = __shfl_xor_sync(0xffffffffu, send, 8);
+      q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
+    }
+  }
+  double q1;
+  {
+    const bool hi = lane & 4;
+    const double send = hi ? q2[0] : q2[1];
+    const double got = __shfl_xor_sync(0xffffffffu, send, 4);
+    q1 = (hi ? q2[1] : q2[0]) + got;
+  }
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+  // value index held by this lane: bit4 -> +4, bit3 -> +2, bit2 -> +1
+  if ((lane & 3) == 0) e_out[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = q1;
+}
+
+constexpr int kVerWarps = 4;
+// One WARP per (chunk c of Y columns, pair); no block-level barriers.  Members = rows i whose
+// nearest neighbour j lies in chunk c.  The members' exact similarities to the 8 columns of the
+// chunk settle every member-versus-member comparison (in a well-matched pair almost every high
+// entry of the chunk column belongs to a member); the remaining high entries of the transposed
+// table column (rare) are checked with the same routine.
+__global__ void __launch_bounds__(kVerWarps * 32, 5)
+tc_verify_kernel(const VerifyArgs a) {
+  __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
+  __shared__ double s_e[kVerWarps][32][kChunk];   // cached rows of the member matrix
+  __shared__ double s_tmp[kVerWarps][kChunk];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y, c = blockIdx.x * kVerWarps + warp;
+  const DirParams& d = a.d;
+  if (c >= a.nchunks) return;
+  const int32_t* off = a.offsets + (size_t)pair * (a.nchunks + 1);
+  const int m0 = off[c], m1 = off[c + 1];
+  if (m0 == m1) return;
+  const int cnt = m1 - m0;
+  const int4* mem = a.members + (size_t)pair * d.NX + m0;
+  const float* Xp = a.X + pair * a.strideX;
+  const float* Yp = a.Y + pair * a.strideY;
+  // the 8 columns of the chunk: float4 per lane and column, staged in shared memory
+  const float4* yv = &s_y[warp][0];
+#pragma unroll
+  for (int r = 0; r < kChunk; ++r) {
+    const int jj = c * kChunk + r;
+    const float* yr = Yp + (int64_t)jj * a.ldy + lane * 4;
+    s_y[warp][r * 32 + lane] =
+        jj < d.NY ? make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  const MatStats& xs = d.xstats[2 * pair];
+  const MatStats& ys = d.ystats[2 * pair];
+  const float xn = __uint_as_float(xs.max_norm), xe = __uint_as_float(xs.max_err);
+  const float yn = __uint_as_float(ys.max_norm), yb = __uint_as_float(ys.max_norm_bf), ye = __uint_as_float(ys.max_err);
+  const float eps_max = xe * yb + xn * ye + kAccSlack * xn * yn;     // bound on |S~ - S| for any row
+  const float scale = table_scale(d, pair);
+  const uint4* col = reinterpret_cast<const uint4*>(d.tableT + ((size_t)pair * d.pitch + c) * d.NXpad);
+  const int nvec = d.NXpad >> 3;
+  auto load_row = [&](int row) {
+    const float* xr = Xp + (int64_t)row * a.ldx + lane * 4;
+    return make_float4(__ldg(xr), __ldg(xr + 1), __ldg(xr + 2), __ldg(xr + 3));
+  };
+
+  for (int b0 = 0; b0 < cnt; b0 += 32) {
+    const int nb = min(32, cnt - b0);
+    const bool valid = lane < nb;
+    const int4 me = valid ? __ldg(mem + b0 + lane) : make_int4(-1, c * kChunk, 0, 0);
+    const int iq = me.x, cc = me.y - c * kChunk;
+    const float thr = valid ? (__int_as_float(me.z) - eps_max) * scale - 0.5f * kHalfSlack - 1e-6f : INFINITY;
+    bool lost = false;
+    // pass A: exact rows of this batch's members, cached
+    for (int r0 = 0; r0 < nb; r0 += 4) {
+      float4 xr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {      // four member rows in flight
+        const int ir = __shfl_sync(0xffffffffu, iq, min(r0 + k, nb - 1));
+        xr[k] = load_row(ir);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r0 + k < nb) warp_chunk_dots(xr[k], yv, lane, &s_e[warp][r0 + k][0]);
+    }
+    __syncwarp();
+    const double mine = valid ? s_e[warp][lane][cc] : 0.0;
+    // pass B: every member of the chunk against the members in the lanes
+    for (int r = 0; r < cnt; ++r) {
+      double other;
+      int ir;
+      if (r >= b0 && r < b0 + nb) {
+        ir = __shfl_sync(0xffffffffu, iq, r - b0);
+        other = s_e[warp][r - b0][cc];
+      } else {
+        ir = __ldg(mem + r).x;
+        __syncwarp();
+        warp_chunk_dots(load_row(ir), yv, lane, &s_tmp[warp][0]);
+        __syncwarp();
+        other = s_tmp[warp][cc];
+      }
+      if (valid && ir != iq && (other > mine || (other == mine && ir < iq))) lost = true;
+    }
+    // pass C: rows that are not members but whose chunk entry comes within the error bound
+    float tmin = thr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    const __half2 tmin2 = __float2half2_rn(__half2float(__float2half_rd(tmin)));
+    for (int v0 = 0; v0 < nvec; v0 += 128) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + k * 32 + lane;
+        u[k] = v < nvec ? __ldg(col + v) : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        unsigned mask = 0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wds[h]), tmin2);
+          const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
+          mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * h);
+          mask |= ((bits >> 16) ? 1u : 0u) << (2 * h + 1);
+        }
+        unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+        while (any) {
+          const int l = __ffs(any) - 1;
+          any &= any - 1;
+          unsigned mk = __shfl_sync(0xffffffffu, mask, l);
+          const uint4 ul = make_uint4(__shfl_sync(0xffffffffu, u[k].x, l), __shfl_sync(0xffffffffu, u[k].y, l),
+                                      __shfl_sync(0xffffffffu, u[k].z, l), __shfl_sync(0xffffffffu, u[k].w, l));
+          const unsigned wl[4] = {ul.x, ul.y, ul.z, ul.w};
+          while (mk) {
+            const int h = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const int ip = (v0 + k * 32 + l) * 8 + h;                 // candidate row i'
+            if (ip >= d.NX) continue;
+            // a member of this chunk?  (all members were handled in pass B)
+            bool is_member = false;
+            for (int r0 = 0; r0 < cnt; r0 += 32) {
+              const int r = r0 + lane;
+              const bool m = r < cnt && __ldg(mem + r).x == ip;
+              is_member |= __any_sync(0xffffffffu, m);
+            }
+            if (is_member) continue;
+            const float ev = __half2float(reinterpret_cast<const __half*>(wl)[h]);
+            if (!__any_sync(0xffffffffu, valid && ev >= thr)) continue;
+            __syncwarp();
+            warp_chunk_dots(load_row(ip), yv, lane, &s_tmp[warp][0]);
+            __syncwarp();
+            const double other = s_tmp[warp][cc];
+            if (valid && ev >= thr && (other > mine || (other == mine && ip < iq))) lost = true;
+          }
+        }
+      }
+    }
+    if (valid && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
+    __syncwarp();
+  }
+}
+
+// ordered compaction of the rows flagged mutual (ascending i), one CTA per pair
+__global__ void __launch_bounds__(1024)
+tc_compact_flags_kernel(const int32_t* __restrict__ nn12_, const unsigned char* __restrict__ mutual_, int N,
+                        int64_t* __restrict__ matches_, int32_t* __restrict__ n_matches) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_total;
+  constexpr int kIt = 8;
+  const int pair = blockIdx.x;
+  const int32_t* nn12 = nn12_ + (size_t)pair * N;
+  const unsigned char* mutual = mutual_ + (size_t)pair * N;
+  int64_t* matches = matches_ + (size_t)pair * N * 2;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < N; i0 += 1024 * kIt) {
+    const int first = i0 + tid * kIt;
+    int j[kIt];
+    unsigned keep = 0;
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      const bool in = first + k < N;
+      j[k] = in ? nn12[first + k] : 0;
+      keep |= (in && mutual[first + k]) ? (1u << k) : 0u;
+    }
+    const int mine = __popc(keep);
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      const int v = s_warp[lane];
+      int winc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      s_warp[lane] = winc - v;
+      if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    int pos = s_base + s_warp[wid] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < kIt; ++k)
+      if (keep & (1u << k)) {
+        matches[2 * (int64_t)pos] = first + k;
+        matches[2 * (int64_t)pos + 1] = j[k];
+        ++pos;
+      }
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+    __syncthreads();
+  }
+  if (tid == 0) n_matches[pair] = s_base;
 }
 
 // ------------------------------------------------------------------ host side
@@ -681,6 +1027,12 @@ struct TcWs {
   MatStats* stats;  // [pairs][2]: A, B
   __half* table[2];
   int pitch[2];
+  // matches-only path
+  __half* tableT;
+  float* best;
+  int32_t* offsets;
+  int4* members;
+  unsigned char* mutual;
   size_t total;
 };
 
@@ -706,6 +1058,13 @@ static TcWs carve_tc(void* base, int P, int N, int M) {
   w.pitch[1] = ((N + kYRows - 1) / kYRows) * (kYRows / kChunk);
   w.table[0] = (__half*)take(sizeof(__half) * P * Np * w.pitch[0]);
   w.table[1] = (__half*)take(sizeof(__half) * P * Mp * w.pitch[1]);
+  // matches-only path: the second table's space is reused for the transposed first table when it fits
+  const size_t need_T = sizeof(__half) * P * Np * w.pitch[0], have_1 = sizeof(__half) * P * Mp * w.pitch[1];
+  w.tableT = need_T <= have_1 ? w.table[1] : (__half*)take(need_T);
+  w.best = (float*)take(sizeof(float) * P * (size_t)N);
+  w.offsets = (int32_t*)take(sizeof(int32_t) * P * (size_t)(w.pitch[0] + 1));
+  w.members = (int4*)take(sizeof(int4) * P * (size_t)N);
+  w.mutual = (unsigned char*)take((size_t)P * N);
   w.total = off;
   return w;
 }
@@ -734,7 +1093,8 @@ static void choose_splits(int P, int rb0, int yt0, int rb1, int yt1, int G, int*
 }
 
 int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm, int64_t strideB, int M, int64_t ldb,
-           int D, int P, int32_t* nn12, int32_t* nn21, void* ws, size_t ws_bytes, cudaStream_t stream) {
+           int D, int P, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches, void* ws, size_t ws_bytes,
+           cudaStream_t stream) {
   if (D != kD) return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
   TcWs w = carve_tc(ws, P, N, M);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
@@ -760,13 +1120,16 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   const int rb0 = Np / kXRows, rb1 = Mp / kXRows;
   const int yt0 = (M + kYRows - 1) / kYRows, yt1 = (N + kYRows - 1) / kYRows;
   int s0, s1;
-  choose_splits(P, rb0, yt0, rb1, yt1, G, &s0, &s1);
+  // nn21 == NULL: matches only -> the second direction is replaced by the column verification
+  const bool one_dir = nn21 == nullptr && w.pitch[0] <= kVerMaxChunks;
+  choose_splits(P, rb0, yt0, one_dir ? 0 : rb1, yt1, G, &s0, &s1);
   auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int NYpad, int yt, int S) {
     d.xnorm = dir ? w.bnorm : w.anorm;
     d.xerr = dir ? w.berr : w.aerr;
     d.xstats = w.stats + (dir ? 1 : 0);
     d.ystats = w.stats + (dir ? 0 : 1);
     d.table = w.table[dir];
+    d.tableT = (dir == 0 && one_dir) ? w.tableT : nullptr;
     d.pitch = w.pitch[dir];
     d.NX = NX; d.NY = NY; d.NXpad = NXpad; d.NYpad = NYpad;
     d.y_tiles = yt;
@@ -778,7 +1141,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   fill(p.d[1], 1, M, N, Mp, Np, yt1, s1);
   p.pairs = P;
   p.units0 = rb0 * p.d[0].splits;
-  p.units_pair = p.units0 + rb1 * p.d[1].splits;
+  p.units_pair = p.units0 + (one_dir ? 0 : rb1 * p.d[1].splits);
   p.units_total = P * p.units_pair;
   {
     const char* dbg = getenv("POSFEAT_TC_DEBUG");
@@ -792,12 +1155,28 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   prof_end(PROF_MNN_TC, stream);
   PF_LAUNCH_CHECK("mnn_tc_kernel");
 
-  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12}, r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21};
-  const long long resc_warps = (long long)P * (N + M);
+  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr};
+  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr};
+  if (one_dir) r1.d.NX = 0;
+  const long long resc_warps = (long long)P * (N + (one_dir ? 0 : M));
   prof_begin(PROF_MNN_RESCORE, stream);
   tc_rescore_kernel<<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
   prof_end(PROF_MNN_RESCORE, stream);
   PF_LAUNCH_CHECK("tc_rescore_kernel");
+  if (!one_dir) {
+    if (nn21 == nullptr) return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher supports M <= %d", kVerMaxChunks * kChunk);
+    return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);
+  }
+  const int nchunks = (M + kChunk - 1) / kChunk;
+  prof_begin(PROF_MNN_COMPACT, stream);
+  tc_group_kernel<<<P, 1024, 0, stream>>>(nn12, w.best, N, nchunks, w.offsets, w.members, w.mutual);
+  PF_LAUNCH_CHECK("tc_group_kernel");
+  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, w.offsets, w.members, w.mutual, nchunks};
+  tc_verify_kernel<<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va);
+  PF_LAUNCH_CHECK("tc_verify_kernel");
+  tc_compact_flags_kernel<<<P, 1024, 0, stream>>>(nn12, w.mutual, N, matches, n_matches);
+  prof_end(PROF_MNN_COMPACT, stream);
+  PF_LAUNCH_CHECK("tc_compact_flags_kernel");
   return POSFEAT_OK;
 }
 

@@ -56,14 +56,17 @@ class PairPipeline:
         matches = torch.empty((P, n, 2), dtype=torch.int64, device=dev)
         nm = torch.empty(P, dtype=torch.int32, device=dev)
         nn12 = torch.empty((P, n), dtype=torch.int32, device=dev)
-        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev)
+        # nn21 is not requested: the tensor-core matcher then computes one direction and verifies
+        # mutuality by a column scan; the exact SIMT matcher (small sizes / algo=1) needs the buffer
+        use_simt = self.mnn_algo == _lib.MNN_SIMT or D != 128 or (self.mnn_algo == _lib.MNN_AUTO and n * n < 1024 * 1024)
+        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if use_simt else None
         da, db = desc[0::2], desc[1::2]          # strided views: pair stride = 2 images
         with torch.cuda.device(dev):
             ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, self.mnn_algo)
             ws = workspace("mnn", ws_bytes, dev)
             check(L.posfeat_mnn_batched_f32(da.data_ptr(), da.stride(0), n, da.stride(1), db.data_ptr(),
                                             db.stride(0), n, db.stride(1), D, P, self.mnn_algo,
-                                            nn12.data_ptr(), nn21.data_ptr(), matches.data_ptr(), nm.data_ptr(),
+                                            nn12.data_ptr(), 0 if nn21 is None else nn21.data_ptr(), matches.data_ptr(), nm.data_ptr(),
                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return matches, nm
 

@@ -159,9 +159,11 @@ def sample_feat_by_coord(x, coord_n, norm=False):
 
 
 # -------------------------------------------------------------------- matcher
-def mnn_match(desc_a, desc_b, algo=_lib.MNN_AUTO):
+def mnn_match(desc_a, desc_b, algo=_lib.MNN_AUTO, want_nn21=True):
     """Device-level matcher: returns (matches [N,2] int64 device, n_matches [1]
-    int32 device, nn12, nn21)."""
+    int32 device, nn12, nn21).  ``want_nn21=False`` lets the tensor-core path skip
+    the second direction (mutual pairs are verified by a column scan instead);
+    nn21 is then None."""
     L = lib()
     a, _ = to_device(desc_a)
     b, _ = to_device(desc_b)
@@ -178,14 +180,16 @@ def mnn_match(desc_a, desc_b, algo=_lib.MNN_AUTO):
         b = b.contiguous()
     dev = a.device
     nn12 = torch.empty(N, dtype=torch.int32, device=dev)
-    nn21 = torch.empty(M, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        tc = want_nn21 or algo == _lib.MNN_SIMT or D != 128 or (algo == _lib.MNN_AUTO and N * M < 1024 * 1024)
+    nn21 = torch.empty(M, dtype=torch.int32, device=dev) if tc else None
     matches = torch.empty((N, 2), dtype=torch.int64, device=dev)
     nm = torch.empty(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         ws_bytes = L.posfeat_mnn_workspace_bytes(N, M, D, algo)
         ws = workspace("mnn", ws_bytes, dev)
         check(L.posfeat_mnn_f32(a.data_ptr(), N, a.stride(0), b.data_ptr(), M, b.stride(0), D, algo,
-                                nn12.data_ptr(), nn21.data_ptr(), matches.data_ptr(), nm.data_ptr(),
+                                nn12.data_ptr(), ptr(nn21), matches.data_ptr(), nm.data_ptr(),
                                 ws.data_ptr(), ws.numel(), stream_ptr(dev)))
     return matches, nm, nn12, nn21
 
@@ -196,7 +200,7 @@ def mnn_matcher(descriptors_a, descriptors_b, algo=_lib.MNN_AUTO):
     nearest neighbours, rows in ascending index of descriptors_a."""
     if descriptors_a.device.type == "cpu" and descriptors_b.device.type == "cpu":
         return _mnn_host(descriptors_a, descriptors_b, algo)
-    matches, nm, _, _ = mnn_match(descriptors_a, descriptors_b, algo)
+    matches, nm, _, _ = mnn_match(descriptors_a, descriptors_b, algo, want_nn21=False)
     k = int(nm.item())
     return matches[:k].cpu().numpy()
 

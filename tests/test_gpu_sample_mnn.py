@@ -100,6 +100,35 @@ def test_mnn_vs_oracle(algo, N, M, D):
     assert np.all(np.diff(got[:, 0]) > 0)
 
 
+@pytest.mark.parametrize("N,M", [(1500, 1300), (4096, 4096), (777, 2049), (1, 5), (130, 1), (3000, 8192)])
+def test_mnn_matches_only_path(N, M):
+    """Tensor-core matcher without nn21 (one direction + column verification) must
+    return exactly the match list of the two-direction algorithm and of the oracle."""
+    import posfeat_b200 as P
+    a = unit_desc(N, 128, 31)
+    b = unit_desc(M, 128, 32, base=a if M <= N else None)
+    want = O.mnn_matcher(a.numpy(), b.numpy(), exact=True)
+    m_full, k_full, _, _ = P.mnn_match(a.cuda(), b.cuda(), algo=2, want_nn21=True)
+    m_fast, k_fast, nn12, nn21 = P.mnn_match(a.cuda(), b.cuda(), algo=2, want_nn21=False)
+    assert nn21 is None
+    got = m_fast[:int(k_fast)].cpu().numpy()
+    np.testing.assert_array_equal(got, m_full[:int(k_full)].cpu().numpy())
+    check_mnn_near_tie(a.numpy(), b.numpy(), got, want)
+
+
+def test_mnn_matches_only_duplicates(golden):
+    import posfeat_b200 as P
+    g = golden("mnn")
+    ad, bd = torch.from_numpy(g["ad"]).cuda(), torch.from_numpy(g["bd"]).cuda()
+    for x, y, key in ((ad, bd, "mnn_dup"), (bd, ad, "mnn_dup_t")):
+        m, k, _, _ = P.mnn_match(x, y, algo=2, want_nn21=False)
+        np.testing.assert_array_equal(m[:int(k)].cpu().numpy(), g[key])       # first-index tie rule in both directions
+    # many identical rows and columns
+    z = torch.nn.functional.normalize(torch.randn(4, 128), dim=1).repeat(50, 1).cuda()
+    m, k, _, _ = P.mnn_match(z, z, algo=2, want_nn21=False)
+    np.testing.assert_array_equal(m[:int(k)].cpu().numpy(), O.mnn_matcher(z.cpu().numpy(), z.cpu().numpy(), exact=True))
+
+
 def test_mnn_8k_properties():
     """BASELINE size (8192 x 8192 x 128): result is a partial permutation,
     consistent with nn12/nn21, and symmetric under swapping the operands."""
@@ -110,6 +139,7 @@ def test_mnn_8k_properties():
     k = int(nm.item())
     m = m[:k].cpu().numpy()
     assert k > 2000
+    np.testing.assert_array_equal(P.mnn_matcher(a, b), m)          # matches-only path (no nn21)
     assert len(np.unique(m[:, 0])) == k and len(np.unique(m[:, 1])) == k
     n12, n21 = nn12.cpu().numpy(), nn21.cpu().numpy()
     assert np.array_equal(n12[m[:, 0]], m[:, 1]) and np.array_equal(n21[m[:, 1]], m[:, 0])
