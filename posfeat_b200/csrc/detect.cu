@@ -340,7 +340,6 @@ nms_strip2_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, 
   const int xa = xs + 2 * lane - 2, xb = xa + 1;
   const int y0 = blockIdx.y * kStrip2Rows;
   const int y1 = min(hi, y0 + kStrip2Rows);
-  const bool la = xa >= -1 && xa <= wi, lb = xb >= -1 && xb <= wi;     // inside the reflect-padded extent
   // per-lane column pointers (always in bounds: loads are unconditional, masking happens afterwards)
   const char* pla = reinterpret_cast<const char*>(score + b * sb + 1 + reflect_idx(min(max(xa, -1), wi), wi));
   const char* plb = reinterpret_cast<const char*>(score + b * sb + 1 + reflect_idx(min(max(xb, -1), wi), wi));
@@ -366,11 +365,11 @@ nms_strip2_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, 
       const int yy = yb + k;
       const int yr = yy < 0 ? 1 : (yy >= hi ? hi - 2 : yy);        // reflect-101 for radius 1 (warp uniform)
       const int64_t ro = (int64_t)(yr + 1) * syb;                  // warp-uniform row offset in bytes
-      const float va = __ldg(reinterpret_cast<const float*>(pla + ro));
-      const float vb = __ldg(reinterpret_cast<const float*>(plb + ro));
-      const bool row_ok = yy <= y1;
-      ina[k] = (row_ok && la) ? va : -INFINITY;
-      inb[k] = (row_ok && lb) ? vb : -INFINITY;
+      // No masking: every load is in bounds (clamped row / column), and a value loaded for a
+      // position outside the reflect-padded extent can only reach pixels that are not evaluated
+      // (halo lanes beyond the right edge, centre rows >= y1).
+      ina[k] = __ldg(reinterpret_cast<const float*>(pla + ro));
+      inb[k] = __ldg(reinterpret_cast<const float*>(plb + ro));
     }
 #pragma unroll
     for (int k = 0; k < kBatch; ++k) {

@@ -367,45 +367,43 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const UnitInfo q = decode_unit(p, u);
       const DirParams& d = p.d[q.dir];
       const int row = q.rb * kXRows + row_in_block;
+      // everything the tile loop needs, read once per unit (indexed kernel-parameter loads are slow)
       const float scale = table_scale(d, q.pair);
-      __half* trow = d.table + ((size_t)q.pair * d.NXpad + row) * d.pitch + j * 8;
-      for (int t = q.t0; t < q.t1; ++t) {
+      const int NY = d.NY;
+      const size_t nxpad = (size_t)d.NXpad;
+      __half* trow = d.table + ((size_t)q.pair * nxpad + row) * d.pitch + j * 8 + (size_t)q.t0 * 32;
+      unsigned short* tcol = d.tableT ? reinterpret_cast<unsigned short*>(d.tableT) +
+                                            ((size_t)q.pair * d.pitch + (size_t)q.t0 * 32 + j * 8) * nxpad + row
+                                      : nullptr;
+      const bool skipT = p.debug & 32, skipR = p.debug & 64;
+      for (int t = q.t0; t < q.t1; ++t, trow += 32, tcol += (tcol ? 32 * nxpad : 0)) {
         mbar_wait(bar_acc_full + 8 * as, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + j * 64) + ((uint32_t)(quarter * 32) << 16);
         const int c0 = t * kYRows + j * 64;
-        uint32_t va[32], vb[32];
-        if (!(p.debug & 2)) {
-          tc_ld32(taddr, va);
-          tc_ld32(taddr + 32, vb);
-          tc_wait_ld();
-        }
-        // this thread's accumulator slice is in registers: release the TMEM stage (leader's barrier)
+        // 32 columns at a time (keeps the live register set small: no spills in this loop)
+        const bool full = c0 + 64 <= NY;
+        uint32_t v[32];
+        uint2 lo, hi;
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+        lo = full ? reduce32<false>(v, c0, NY, scale) : reduce32<true>(v, c0, NY, scale);
+        tc_ld32(taddr + 32, v);
+        tc_wait_ld();
+        // this thread's accumulator slice has been read: release the TMEM stage (leader's barrier)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(bar_acc_empty + 8 * as, 0);
         if (++as == 2) { as = 0; aph ^= 1; }
-        if (p.debug & 3) {
-          if ((p.debug & 1) && !(p.debug & 2) && (va[0] ^ vb[31]) == 0x12345678u) trow[0] = __float2half(1.f);
-          continue;
-        }
-        uint2 lo, hi;
-        if (c0 + 64 <= d.NY) {
-          lo = reduce32<false>(va, c0, d.NY, scale);
-          hi = reduce32<false>(vb, c0 + 32, d.NY, scale);
-        } else {
-          lo = reduce32<true>(va, c0, d.NY, scale);
-          hi = reduce32<true>(vb, c0 + 32, d.NY, scale);
-        }
-        *reinterpret_cast<uint4*>(trow + t * 32) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        if (d.tableT) {
+        hi = full ? reduce32<false>(v, c0 + 32, NY, scale) : reduce32<true>(v, c0 + 32, NY, scale);
+        if (!skipR) *reinterpret_cast<uint4*>(trow) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        if (tcol && !skipT) {
           // chunk-major copy: for a fixed chunk the 32 lanes (rows) write 64 contiguous bytes
-          unsigned short* tc = reinterpret_cast<unsigned short*>(d.tableT) +
-                               ((size_t)q.pair * d.pitch + (size_t)t * 32 + j * 8) * d.NXpad + row;
+          unsigned short* tc = tcol;
           const unsigned wv[4] = {lo.x, lo.y, hi.x, hi.y};
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            tc[(size_t)c8 * d.NXpad] = (unsigned short)((c8 & 1) ? (wv[c8 >> 1] >> 16) : (wv[c8 >> 1] & 0xffffu));
+          for (int c8 = 0; c8 < 8; ++c8, tc += nxpad)
+            *tc = (unsigned short)((c8 & 1) ? (wv[c8 >> 1] >> 16) : (wv[c8 >> 1] & 0xffffu));
         }
       }
     }
