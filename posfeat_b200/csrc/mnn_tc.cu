@@ -490,6 +490,14 @@ tc_prep_kernel(const PrepArgs a) {
   }
 }
 
+__device__ __forceinline__ int float_to_ordered_int(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_int_to_float(int o) {
+  return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff);
+}
+
 // ------------------------------------------------------------------ rescoring
 // One warp per row, both directions in one launch.  The row of the chunk-maximum
 // table gives the approximate row maximum F and the candidate chunks (>= F -
@@ -503,9 +511,13 @@ struct RescoreArgs {
   const float* Y; int64_t ldy, strideY;
   int32_t* nn;                            // [pairs][NX]
   float* best;                            // optional [pairs][NX]: exact best similarity, rounded down
+  // matches-only path (may be NULL): per-chunk minimum verification threshold and the mutual flags
+  int* tmin;                              // [pairs][nchunks] ordered ints, pre-set to 0x7f7f7f7f
+  unsigned char* mutual;                  // [pairs][NX], set to 1 here
+  int nchunks;
 };
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   __shared__ __align__(16) float xs[8][kD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -566,7 +578,6 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   float m32 = -INFINITY;       // running float32 maximum over everything seen
   double bestv = -INFINITY;    // exact best
   int besti = 0x7fffffff;
-  const int c = lane & 7, kq = lane >> 3;   // column within the chunk, quarter of K
   const float4* x4 = reinterpret_cast<const float4*>(&xs[w][0]);
 
   auto exact_col = [&](int col) {   // whole warp: exact <x, y_col>
@@ -581,44 +592,65 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     if (acc > bestv || (acc == bestv && col < besti)) { bestv = acc; besti = col; }
   };
 
+  // float32 similarities of x to the 8 columns of a chunk.  Every row of Y is read by the
+  // whole warp (32 x 16 B = one coalesced 512-byte row per instruction), each lane keeps the
+  // partial sums over its 4 components, and a transposing butterfly (9 shuffles) leaves the
+  // total of column ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1) in every lane.
+  const float4 xme = x4[lane];
+  const int myc = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   auto rescore = [&](int col0) {
-    const int col = col0 + c;
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-    if (col < d.NY) {
-      const float* yr = Y + (int64_t)col * ldy + kq * 32;
-      if (vec_ok) {
-        const float4* y4 = reinterpret_cast<const float4*>(yr);
-        float4 yv[8];
+    float pr[kChunk];
+    if (vec_ok) {
+      float4 yv[kChunk];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) yv[q] = __ldg(y4 + q);
+      for (int r = 0; r < kChunk; ++r) {
+        const int col = min(col0 + r, d.NY - 1);          // clamped: masked below
+        yv[r] = __ldg(reinterpret_cast<const float4*>(Y + (int64_t)col * ldy) + lane);
+      }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 xv = x4[kq * 8 + q];
-          q0 = fmaf(xv.x, yv[q].x, q0); q1 = fmaf(xv.y, yv[q].y, q1);
-          q2 = fmaf(xv.z, yv[q].z, q2); q3 = fmaf(xv.w, yv[q].w, q3);
-        }
-      } else {
-        for (int k = 0; k < 32; k += 4) {
-          q0 = fmaf(xs[w][kq * 32 + k], __ldg(yr + k), q0);
-          q1 = fmaf(xs[w][kq * 32 + k + 1], __ldg(yr + k + 1), q1);
-          q2 = fmaf(xs[w][kq * 32 + k + 2], __ldg(yr + k + 2), q2);
-          q3 = fmaf(xs[w][kq * 32 + k + 3], __ldg(yr + k + 3), q3);
-        }
+      for (int r = 0; r < kChunk; ++r)
+        pr[r] = fmaf(xme.w, yv[r].w, fmaf(xme.z, yv[r].z, fmaf(xme.y, yv[r].y, xme.x * yv[r].x)));
+    } else {
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) {
+        const float* yr = Y + (int64_t)min(col0 + r, d.NY - 1) * ldy + lane * 4;
+        pr[r] = fmaf(xme.w, __ldg(yr + 3), fmaf(xme.z, __ldg(yr + 2), fmaf(xme.y, __ldg(yr + 1), xme.x * __ldg(yr))));
       }
     }
-    float s32 = (q0 + q1) + (q2 + q3);
-    s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
-    s32 += __shfl_xor_sync(0xffffffffu, s32, 16);
-    if (col >= d.NY) s32 = -INFINITY;
+    float q4[4], q2[2], s32;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? pr[r] : pr[r + 4], 16);
+        q4[r] = (hi ? pr[r + 4] : pr[r]) + got;
+      }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 8);
+        q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
+      }
+    }
+    {
+      const bool hi = lane & 4;
+      const float got = __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 4);
+      s32 = (hi ? q2[1] : q2[0]) + got;
+    }
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 2);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
+    if (col0 + myc >= d.NY) s32 = -INFINITY;
     float cm = s32;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    for (int o = 16; o >= 4; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
     m32 = fmaxf(m32, cm);
-    unsigned need = __ballot_sync(0xffffffffu, kq == 0 && s32 >= m32 - band);
+    unsigned need = __ballot_sync(0xffffffffu, (lane & 3) == 0 && s32 >= m32 - band);
     while (need) {
       const int l = __ffs(need) - 1;
       need &= need - 1;
-      exact_col(col0 + l);
+      exact_col(col0 + ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1));
     }
   };
 
@@ -650,77 +682,90 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     }
   }
   if (lane == 0) {
-    a.nn[(size_t)pair * d.NX + row] = besti == 0x7fffffff ? 0 : besti;
+    const int bj = besti == 0x7fffffff ? 0 : besti;
+    a.nn[(size_t)pair * d.NX + row] = bj;
     if (a.best) a.best[(size_t)pair * d.NX + row] = __double2float_rd(bestv);
+    if (a.tmin) {
+      // threshold a competitor's table entry must reach to possibly beat this row at column bj
+      const MatStats& sx = d.xstats[2 * pair];
+      const MatStats& sy = d.ystats[2 * pair];
+      const float eps_max = __uint_as_float(sx.max_err) * __uint_as_float(sy.max_norm_bf) +
+                            __uint_as_float(sx.max_norm) * __uint_as_float(sy.max_err) +
+                            kAccSlack * __uint_as_float(sx.max_norm) * __uint_as_float(sy.max_norm);
+      const float thr_v = (__double2float_rd(bestv) - eps_max) * table_scale(d, pair) - 0.5f * kHalfSlack - 1e-6f;
+      atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
+      a.mutual[(size_t)pair * d.NX + row] = 1;
+    }
   }
 }
 
 // ------------------------------------------------------------------ matches-only path
 // When the caller does not need nn21 the second direction is not computed at all.
 // i and j = nn12[i] are mutual iff no row i' has S[i'][j] > S[i][j] (or == with i' < i).
-// The chunk-maximum table of the first direction bounds S[i'][j] from above for every
-// i', so only rows whose entry in chunk j/8 comes within the error bound of S[i][j] can
-// beat i; those few are checked exactly.  Rows are first grouped by the chunk of their
-// nearest neighbour so each chunk column of the transposed table is scanned once.
+// The chunk-maximum table bounds S[i'][j] from above for every i' (entry of row i' in chunk
+// j/8), so only rows whose entry comes within the error bound of S[i][j] can beat i:
+//   1. the rescoring kernel leaves, per chunk c, tmin[c] = the smallest such threshold over
+//      the rows whose nearest neighbour lies in c (atomicMin);
+//   2. tc_scan_kernel streams the table once more (coalesced) and appends every row with
+//      entry >= tmin[c] to the competitor list of chunk c -- in a well-matched pair these
+//      are the ~8 rows matched to the chunk's columns plus the odd noise row;
+//   3. tc_verify_kernel computes, per chunk, the exact similarities of the competitors to
+//      the 8 columns and settles every member (first index on exact ties).
 constexpr int kVerMaxChunks = 8192;   // M <= 65536 on this path
+constexpr int kCompCap = 256;         // competitor slots per chunk (overflow -> exhaustive fallback)
 
-__global__ void __launch_bounds__(1024)
-tc_group_kernel(const int32_t* __restrict__ nn12, const float* __restrict__ best, int N, int nchunks,
-                int32_t* __restrict__ offsets, int4* __restrict__ members, unsigned char* __restrict__ mutual) {
-  __shared__ int cnt[kVerMaxChunks];
-  __shared__ int wsum[32];
-  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int32_t* nn = nn12 + (size_t)pair * N;
-  for (int c = tid; c < nchunks; c += 1024) cnt[c] = 0;
-  __syncthreads();
-  for (int i = tid; i < N; i += 1024) {
-    atomicAdd(&cnt[nn[i] >> 3], 1);
-    mutual[(size_t)pair * N + i] = 1;
-  }
-  __syncthreads();
-  // exclusive scan of cnt[0..nchunks) (each thread owns a contiguous run of ceil(nchunks/1024) bins)
-  const int per = (nchunks + 1023) / 1024;
-  int local = 0;
-  for (int k = 0; k < per; ++k) {
-    const int c = tid * per + k;
-    if (c < nchunks) local += cnt[c];
-  }
-  int inc = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) wsum[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    const int v = wsum[lane];
-    int w2 = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w2, o);
-      if (lane >= o) w2 += t;
+struct ScanArgs {
+  DirParams d;
+  const int* tmin;        // [pairs][nchunks] ordered-int thresholds (scaled units)
+  int* comp_cnt;          // [pairs][nchunks]
+  int* comp;              // [pairs][nchunks][kCompCap]
+  int nchunks;
+};
+
+// grid (row blocks, pairs); every thread compares 8 table entries (one uint4) with the 8
+// thresholds of its chunks
+__global__ void __launch_bounds__(256)
+tc_scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(16) __half s_thr[];     // [pitch] thresholds, rounded down
+  const DirParams& d = a.d;
+  const int pair = blockIdx.y;
+  const int pitch = d.pitch, nvec = pitch >> 3;
+  for (int c = threadIdx.x; c < pitch; c += blockDim.x) {
+    float t = INFINITY;                                  // chunks without members / padding: never
+    if (c < a.nchunks) {
+      const int o = a.tmin[(size_t)pair * a.nchunks + c];
+      if (o != 0x7f7f7f7f) t = ordered_int_to_float(o);
     }
-    wsum[lane] = w2 - v;
+    s_thr[c] = __float2half_rd(t);
   }
   __syncthreads();
-  int run = wsum[wid] + inc - local;
-  int32_t* off = offsets + (size_t)pair * (nchunks + 1);
-  for (int k = 0; k < per; ++k) {
-    const int c = tid * per + k;
-    if (c < nchunks) {
-      const int v = cnt[c];
-      off[c] = run;
-      cnt[c] = run;      // becomes the fill cursor
-      run += v;
+  const int rows_per_block = 64;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(d.NX, row0 + rows_per_block);
+  const uint4* thr4 = reinterpret_cast<const uint4*>(s_thr);
+  for (int row = row0; row < row1; ++row) {
+    const uint4* trow = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row) * pitch);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint4 u = __ldg(trow + v);
+      const uint4 th = thr4[v];
+      const unsigned wu[4] = {u.x, u.y, u.z, u.w}, wt[4] = {th.x, th.y, th.z, th.w};
+      unsigned mask = 0;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wu[h]), *reinterpret_cast<const __half2*>(&wt[h]));
+        const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
+        mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * h);
+        mask |= ((bits >> 16) ? 1u : 0u) << (2 * h + 1);
+      }
+      while (mask) {
+        const int h = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int c = v * 8 + h;
+        const size_t slot = (size_t)pair * a.nchunks + c;
+        const int pos = atomicAdd(a.comp_cnt + slot, 1);
+        if (pos < kCompCap) a.comp[slot * kCompCap + pos] = row;
+      }
     }
-  }
-  if (tid == 1023) off[nchunks] = N;
-  __syncthreads();
-  for (int i = tid; i < N; i += 1024) {
-    const int j = nn[i];
-    const int pos = atomicAdd(&cnt[j >> 3], 1);
-    members[(size_t)pair * N + pos] = make_int4(i, j, __float_as_int(best[(size_t)pair * N + i]), 0);
   }
 }
 
@@ -728,86 +773,78 @@ struct VerifyArgs {
   DirParams d;
   const float* X; int64_t ldx, strideX;
   const float* Y; int64_t ldy, strideY;
-  const int32_t* offsets;    // [pairs][nchunks+1]
-  const int4* members;       // [pairs][NX]: (i, j = nn12[i], bits of best[i], -) grouped by chunk of j
+  const int32_t* nn12;       // [pairs][NX]
+  const int* comp_cnt;       // [pairs][nchunks]
+  const int* comp;           // [pairs][nchunks][kCompCap]
   unsigned char* mutual;     // [pairs][NX]
   int nchunks;
 };
 
-// Exact similarities of one row x (float4 per lane) to the 8 columns of a chunk (yv: float4 per
-// lane and column), float64, by the whole warp.  A fixed transposing butterfly leaves value
-// (lane >> 2) & 7 in every lane; the association tree is the same for all eight values and all
-// rows, so identical inputs give identical results.  The 8 results are written to e_out[0..7].
-__device__ __forceinline__ void warp_chunk_dots(const float4 xv, const float4* __restrict__ ysm, int lane,
-                                                double* __restrict__ e_out) {
-  double p[kChunk];
-  const double x0 = (double)xv.x, x1 = (double)xv.y, x2 = (double)xv.z, x3 = (double)xv.w;
+// float32 similarities of one row x (float4 per lane) to the 8 columns of a chunk staged in
+// shared memory (float4 per lane and column), by the whole warp.  A transposing butterfly
+// (9 shuffles) leaves column ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1) in every lane;
+// the 8 results are written to e_out[0..7].
+__device__ __forceinline__ void warp_chunk_dots_f32(const float4 xv, const float4* __restrict__ ysm, int lane,
+                                                    float* __restrict__ e_out) {
+  float p[kChunk];
 #pragma unroll
   for (int r = 0; r < kChunk; ++r) {
-    const float4 y = ysm[r * 32 + lane];       // column r of the chunk, this lane's 4 components
-    double acc = x0 * (double)y.x;
-    acc = fma(x1, (double)y.y, acc);
-    acc = fma(x2, (double)y.z, acc);
-    acc = fma(x3, (double)y.w, acc);
-    p[r] = acc;
+    const float4 y = ysm[r * 32 + lane];
+    p[r] = fmaf(xv.w, y.w, fmaf(xv.z, y.z, fmaf(xv.y, y.y, xv.x * y.x)));
   }
-  // xor 16: lanes with bit4 = 0 keep values 0..3, the others 4..7
-  double q4[4];
+  float q4[4], q2[2], q1;
   {
     const bool hi = lane & 16;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const double send = hi ? p[r] : p[r + 4];
-      const double got = __shfl_xor_sync(0xffffffffu, send, 16);
-      q4[r] = (hi ? p[r + 4] : p[r]) + got;
-    }
+    for (int r = 0; r < 4; ++r) q4[r] = (hi ? p[r + 4] : p[r]) + __shfl_xor_sync(0xffffffffu, hi ? p[r] : p[r + 4], 16);
   }
-  double q2[2];
   {
     const bool hi = lane & 8;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const double send = hi ? q4[r] : q4[r + 2];
-      const double got = __shfl_xor_sync(0xffffffffu, send, 8);
-      q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
-    }
+    for (int r = 0; r < 2; ++r) q2[r] = (hi ? q4[r + 2] : q4[r]) + __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 8);
   }
-  double q1;
   {
     const bool hi = lane & 4;
-    const double send = hi ? q2[0] : q2[1];
-    const double got = __shfl_xor_sync(0xffffffffu, send, 4);
-    q1 = (hi ? q2[1] : q2[0]) + got;
+    q1 = (hi ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 4);
   }
   q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
   q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-  // value index held by this lane: bit4 -> +4, bit3 -> +2, bit2 -> +1
   if ((lane & 3) == 0) e_out[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = q1;
 }
 
+// exact <x_row, y_col> (float32 operands, float64 accumulation) by the whole warp; the same
+// association tree for every call, so identical inputs give identical values
+__device__ __forceinline__ double warp_exact_dot(const float* __restrict__ xr, const float* __restrict__ yr, int lane) {
+  double acc = (double)__ldg(xr + lane * 4) * (double)__ldg(yr + lane * 4);
+  acc = fma((double)__ldg(xr + lane * 4 + 1), (double)__ldg(yr + lane * 4 + 1), acc);
+  acc = fma((double)__ldg(xr + lane * 4 + 2), (double)__ldg(yr + lane * 4 + 2), acc);
+  acc = fma((double)__ldg(xr + lane * 4 + 3), (double)__ldg(yr + lane * 4 + 3), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 constexpr int kVerWarps = 4;
-// One WARP per (chunk c of Y columns, pair); no block-level barriers.  Members = rows i whose
-// nearest neighbour j lies in chunk c.  The members' exact similarities to the 8 columns of the
-// chunk settle every member-versus-member comparison (in a well-matched pair almost every high
-// entry of the chunk column belongs to a member); the remaining high entries of the transposed
-// table column (rare) are checked with the same routine.
-__global__ void __launch_bounds__(kVerWarps * 32, 5)
-tc_verify_kernel(const VerifyArgs a) {
+// One WARP per (chunk c of Y columns, pair).  R = competitor rows of the chunk (a superset of
+// the members, the rows whose nearest neighbour lies in c).  The competitors' similarities to
+// the chunk's 8 columns are evaluated in float32; a member loses its match if another
+// competitor is larger in the member's column.  Comparisons inside the float32 error band are
+// settled exactly (float64), ties by the lower row index.
+__global__ void __launch_bounds__(kVerWarps * 32, 6)
+tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
-  __shared__ double s_e[kVerWarps][32][kChunk];   // cached rows of the member matrix
-  __shared__ double s_tmp[kVerWarps][kChunk];
+  __shared__ float s_e[kVerWarps][32][kChunk];                    // competitor matrix of short lists
+  __shared__ float s_tmp[kVerWarps][kChunk];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.y, c = blockIdx.x * kVerWarps + warp;
   const DirParams& d = a.d;
   if (c >= a.nchunks) return;
-  const int32_t* off = a.offsets + (size_t)pair * (a.nchunks + 1);
-  const int m0 = off[c], m1 = off[c + 1];
-  if (m0 == m1) return;
-  const int cnt = m1 - m0;
-  const int4* mem = a.members + (size_t)pair * d.NX + m0;
+  const size_t slot = (size_t)pair * a.nchunks + c;
+  const int total = a.comp_cnt[slot];
+  if (total == 0) return;
   const float* Xp = a.X + pair * a.strideX;
   const float* Yp = a.Y + pair * a.strideY;
-  // the 8 columns of the chunk: float4 per lane and column, staged in shared memory
+  const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
   const float4* yv = &s_y[warp][0];
 #pragma unroll
   for (int r = 0; r < kChunk; ++r) {
@@ -817,113 +854,124 @@ tc_verify_kernel(const VerifyArgs a) {
         jj < d.NY ? make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncwarp();
-  const MatStats& xs = d.xstats[2 * pair];
-  const MatStats& ys = d.ystats[2 * pair];
-  const float xn = __uint_as_float(xs.max_norm), xe = __uint_as_float(xs.max_err);
-  const float yn = __uint_as_float(ys.max_norm), yb = __uint_as_float(ys.max_norm_bf), ye = __uint_as_float(ys.max_err);
-  const float eps_max = xe * yb + xn * ye + kAccSlack * xn * yn;     // bound on |S~ - S| for any row
-  const float scale = table_scale(d, pair);
-  const uint4* col = reinterpret_cast<const uint4*>(d.tableT + ((size_t)pair * d.pitch + c) * d.NXpad);
-  const int nvec = d.NXpad >> 3;
   auto load_row = [&](int row) {
     const float* xr = Xp + (int64_t)row * a.ldx + lane * 4;
     return make_float4(__ldg(xr), __ldg(xr + 1), __ldg(xr + 2), __ldg(xr + 3));
   };
+  // two float32 similarities whose difference is below this band are compared exactly
+  const float band = 2.f * kEps32 * __uint_as_float(d.xstats[2 * pair].max_norm) * __uint_as_float(d.ystats[2 * pair].max_norm);
+  // member (in lane `member lane`) against competitor row ir with float32 value `other`
+  auto settle = [&](bool member, int iq, int jq, float mine, int ir, float other, bool& lost) {
+    const bool clear_win = member && ir != iq && other > mine + band;
+    unsigned amb = __ballot_sync(0xffffffffu, member && ir != iq && !clear_win && other >= mine - band);
+    if (clear_win) lost = true;
+    while (amb) {                                   // rare: exact comparison, one member at a time
+      const int l = __ffs(amb) - 1;
+      amb &= amb - 1;
+      const int il = __shfl_sync(0xffffffffu, iq, l), jl = __shfl_sync(0xffffffffu, jq, l);
+      const float* yr = Yp + (int64_t)jl * a.ldy;
+      const double em = warp_exact_dot(Xp + (int64_t)il * a.ldx, yr, lane);
+      const double eo = warp_exact_dot(Xp + (int64_t)ir * a.ldx, yr, lane);
+      if (lane == l && (eo > em || (eo == em && ir < il))) lost = true;
+    }
+  };
 
-  for (int b0 = 0; b0 < cnt; b0 += 32) {
-    const int nb = min(32, cnt - b0);
-    const bool valid = lane < nb;
-    const int4 me = valid ? __ldg(mem + b0 + lane) : make_int4(-1, c * kChunk, 0, 0);
-    const int iq = me.x, cc = me.y - c * kChunk;
-    const float thr = valid ? (__int_as_float(me.z) - eps_max) * scale - 0.5f * kHalfSlack - 1e-6f : INFINITY;
-    bool lost = false;
-    // pass A: exact rows of this batch's members, cached
-    for (int r0 = 0; r0 < nb; r0 += 4) {
+  if (total <= 32) {
+    // common case: the whole competitor matrix fits in shared memory; one pass over the rows
+    const int* rows = a.comp + slot * kCompCap;
+    const int iq = lane < total ? __ldg(rows + lane) : -1;
+    const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
+    for (int r0 = 0; r0 < total; r0 += 4) {
       float4 xr[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {      // four member rows in flight
-        const int ir = __shfl_sync(0xffffffffu, iq, min(r0 + k, nb - 1));
-        xr[k] = load_row(ir);
-      }
+      for (int k = 0; k < 4; ++k) xr[k] = load_row(__shfl_sync(0xffffffffu, iq, min(r0 + k, total - 1)));
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (r0 + k < nb) warp_chunk_dots(xr[k], yv, lane, &s_e[warp][r0 + k][0]);
+        if (r0 + k < total) warp_chunk_dots_f32(xr[k], yv, lane, &s_e[warp][r0 + k][0]);
     }
     __syncwarp();
-    const double mine = valid ? s_e[warp][lane][cc] : 0.0;
-    // pass B: every member of the chunk against the members in the lanes
-    for (int r = 0; r < cnt; ++r) {
-      double other;
-      int ir;
-      if (r >= b0 && r < b0 + nb) {
-        ir = __shfl_sync(0xffffffffu, iq, r - b0);
-        other = s_e[warp][r - b0][cc];
-      } else {
-        ir = __ldg(mem + r).x;
-        __syncwarp();
-        warp_chunk_dots(load_row(ir), yv, lane, &s_tmp[warp][0]);
-        __syncwarp();
-        other = s_tmp[warp][cc];
-      }
-      if (valid && ir != iq && (other > mine || (other == mine && ir < iq))) lost = true;
+    const bool member = iq >= 0 && (jq >> 3) == c;
+    if (!__any_sync(0xffffffffu, member)) return;
+    const int cc = member ? jq - c * kChunk : 0;
+    const float mine = s_e[warp][lane & 31][cc];
+    bool lost = false;
+    for (int r = 0; r < total; ++r) {
+      const int ir = __shfl_sync(0xffffffffu, iq, r);
+      settle(member, iq, jq, mine, ir, s_e[warp][r][cc], lost);
     }
-    // pass C: rows that are not members but whose chunk entry comes within the error bound
-    float tmin = thr;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-    const __half2 tmin2 = __float2half2_rn(__half2float(__float2half_rd(tmin)));
-    for (int v0 = 0; v0 < nvec; v0 += 128) {
-      uint4 u[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int v = v0 + k * 32 + lane;
-        u[k] = v < nvec ? __ldg(col + v) : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+    if (member && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
+    return;
+  }
+  if (total <= kCompCap) {
+    const int* rows = a.comp + slot * kCompCap;
+    // long list: members in batches of 32 (one per lane), competitors streamed
+    for (int q0 = 0; q0 < total; q0 += 32) {
+      const int q = q0 + lane;
+      const int iq = q < total ? __ldg(rows + q) : -1;
+      const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
+      const bool member = iq >= 0 && (jq >> 3) == c;
+      const unsigned mem = __ballot_sync(0xffffffffu, member);
+      if (!mem) continue;
+      const int cc = member ? jq - c * kChunk : 0;
+      float mine = 0.f;
+      for (unsigned mm = mem; mm;) {                      // the members' own values
+        const int l = __ffs(mm) - 1;
+        mm &= mm - 1;
+        __syncwarp();
+        warp_chunk_dots_f32(load_row(__shfl_sync(0xffffffffu, iq, l)), yv, lane, &s_tmp[warp][0]);
+        __syncwarp();
+        if (lane == l) mine = s_tmp[warp][cc];
       }
+      bool lost = false;
+      for (int r0 = 0; r0 < total; r0 += 4) {             // every competitor, four row loads in flight
+        float4 xr[4];
+        int ir[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const unsigned wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-        unsigned mask = 0;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wds[h]), tmin2);
-          const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
-          mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * h);
-          mask |= ((bits >> 16) ? 1u : 0u) << (2 * h + 1);
+        for (int k = 0; k < 4; ++k) {
+          ir[k] = __ldg(rows + min(r0 + k, total - 1));
+          xr[k] = load_row(ir[k]);
         }
-        unsigned any = __ballot_sync(0xffffffffu, mask != 0);
-        while (any) {
-          const int l = __ffs(any) - 1;
-          any &= any - 1;
-          unsigned mk = __shfl_sync(0xffffffffu, mask, l);
-          const uint4 ul = make_uint4(__shfl_sync(0xffffffffu, u[k].x, l), __shfl_sync(0xffffffffu, u[k].y, l),
-                                      __shfl_sync(0xffffffffu, u[k].z, l), __shfl_sync(0xffffffffu, u[k].w, l));
-          const unsigned wl[4] = {ul.x, ul.y, ul.z, ul.w};
-          while (mk) {
-            const int h = __ffs(mk) - 1;
-            mk &= mk - 1;
-            const int ip = (v0 + k * 32 + l) * 8 + h;                 // candidate row i'
-            if (ip >= d.NX) continue;
-            // a member of this chunk?  (all members were handled in pass B)
-            bool is_member = false;
-            for (int r0 = 0; r0 < cnt; r0 += 32) {
-              const int r = r0 + lane;
-              const bool m = r < cnt && __ldg(mem + r).x == ip;
-              is_member |= __any_sync(0xffffffffu, m);
-            }
-            if (is_member) continue;
-            const float ev = __half2float(reinterpret_cast<const __half*>(wl)[h]);
-            if (!__any_sync(0xffffffffu, valid && ev >= thr)) continue;
-            __syncwarp();
-            warp_chunk_dots(load_row(ip), yv, lane, &s_tmp[warp][0]);
-            __syncwarp();
-            const double other = s_tmp[warp][cc];
-            if (valid && ev >= thr && (other > mine || (other == mine && ip < iq))) lost = true;
-          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (r0 + k >= total) break;
+          __syncwarp();
+          warp_chunk_dots_f32(xr[k], yv, lane, &s_tmp[warp][0]);
+          __syncwarp();
+          settle(member, iq, jq, mine, ir[k], s_tmp[warp][cc], lost);
         }
       }
+      if (member && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
     }
-    if (valid && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
-    __syncwarp();
+    return;
+  }
+
+  if (lane == 0 && getenv_dbg) printf("verify fallback pair %d chunk %d total %d\n", pair, c, total);
+  // ---- fallback (competitor list overflowed, e.g. many duplicated descriptors): exhaustive.
+  // Members are found by scanning nn12; every row of X is checked against them.
+  for (int m0 = 0; m0 < d.NX; m0 += 32) {
+    const int i = m0 + lane;
+    const int ji = i < d.NX ? __ldg(nn + i) : -1;
+    const bool member = ji >= 0 && (ji >> 3) == c;
+    const unsigned mem = __ballot_sync(0xffffffffu, member);
+    if (!mem) continue;
+    const int cc = member ? ji - c * kChunk : 0;
+    float mine = 0.f;
+    for (unsigned mm = mem; mm;) {
+      const int l = __ffs(mm) - 1;
+      mm &= mm - 1;
+      __syncwarp();
+      warp_chunk_dots_f32(load_row(m0 + l), yv, lane, &s_tmp[warp][0]);
+      __syncwarp();
+      if (lane == l) mine = s_tmp[warp][cc];
+    }
+    bool lost = false;
+    for (int ip = 0; ip < d.NX; ++ip) {
+      __syncwarp();
+      warp_chunk_dots_f32(load_row(ip), yv, lane, &s_tmp[warp][0]);
+      __syncwarp();
+      settle(member, i, ji, mine, ip, s_tmp[warp][cc], lost);
+    }
+    if (member && lost) a.mutual[(size_t)pair * d.NX + i] = 0;
   }
 }
 
@@ -1026,10 +1074,8 @@ struct TcWs {
   __half* table[2];
   int pitch[2];
   // matches-only path
-  __half* tableT;
   float* best;
-  int32_t* offsets;
-  int4* members;
+  int *tmin, *comp_cnt, *comp;
   unsigned char* mutual;
   size_t total;
 };
@@ -1056,12 +1102,12 @@ static TcWs carve_tc(void* base, int P, int N, int M) {
   w.pitch[1] = ((N + kYRows - 1) / kYRows) * (kYRows / kChunk);
   w.table[0] = (__half*)take(sizeof(__half) * P * Np * w.pitch[0]);
   w.table[1] = (__half*)take(sizeof(__half) * P * Mp * w.pitch[1]);
-  // matches-only path: the second table's space is reused for the transposed first table when it fits
-  const size_t need_T = sizeof(__half) * P * Np * w.pitch[0], have_1 = sizeof(__half) * P * Mp * w.pitch[1];
-  w.tableT = need_T <= have_1 ? w.table[1] : (__half*)take(need_T);
+  // matches-only path
   w.best = (float*)take(sizeof(float) * P * (size_t)N);
-  w.offsets = (int32_t*)take(sizeof(int32_t) * P * (size_t)(w.pitch[0] + 1));
-  w.members = (int4*)take(sizeof(int4) * P * (size_t)N);
+  const size_t nch = (size_t)(M + kChunk - 1) / kChunk;
+  w.tmin = (int*)take(sizeof(int) * P * nch * 2);            // tmin followed by comp_cnt
+  w.comp_cnt = w.tmin + P * nch;
+  w.comp = (int*)take(sizeof(int) * P * nch * kCompCap);
   w.mutual = (unsigned char*)take((size_t)P * N);
   w.total = off;
   return w;
@@ -1127,7 +1173,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     d.xstats = w.stats + (dir ? 1 : 0);
     d.ystats = w.stats + (dir ? 0 : 1);
     d.table = w.table[dir];
-    d.tableT = (dir == 0 && one_dir) ? w.tableT : nullptr;
+    d.tableT = nullptr;
     d.pitch = w.pitch[dir];
     d.NX = NX; d.NY = NY; d.NXpad = NXpad; d.NYpad = NYpad;
     d.y_tiles = yt;
@@ -1153,8 +1199,14 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   prof_end(PROF_MNN_TC, stream);
   PF_LAUNCH_CHECK("mnn_tc_kernel");
 
-  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr};
-  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr};
+  const int nchunks = (M + kChunk - 1) / kChunk;
+  if (one_dir) {
+    PF_CUDA(cudaMemsetAsync(w.tmin, 0x7f, sizeof(int) * (size_t)P * nchunks, stream));
+    PF_CUDA(cudaMemsetAsync(w.comp_cnt, 0, sizeof(int) * (size_t)P * nchunks, stream));
+  }
+  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr,
+                 one_dir ? w.tmin : nullptr, w.mutual, nchunks};
+  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
   const long long resc_warps = (long long)P * (N + (one_dir ? 0 : M));
   prof_begin(PROF_MNN_RESCORE, stream);
@@ -1165,13 +1217,17 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     if (nn21 == nullptr) return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher supports M <= %d", kVerMaxChunks * kChunk);
     return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);
   }
-  const int nchunks = (M + kChunk - 1) / kChunk;
-  prof_begin(PROF_MNN_COMPACT, stream);
-  tc_group_kernel<<<P, 1024, 0, stream>>>(nn12, w.best, N, nchunks, w.offsets, w.members, w.mutual);
-  PF_LAUNCH_CHECK("tc_group_kernel");
-  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, w.offsets, w.members, w.mutual, nchunks};
-  tc_verify_kernel<<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va);
+  ScanArgs sa{p.d[0], w.tmin, w.comp_cnt, w.comp, nchunks};
+  prof_begin(PROF_MNN_SCAN, stream);
+  tc_scan_kernel<<<dim3((N + 63) / 64, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
+  prof_end(PROF_MNN_SCAN, stream);
+  PF_LAUNCH_CHECK("tc_scan_kernel");
+  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.mutual, nchunks};
+  prof_begin(PROF_MNN_VERIFY, stream);
+  tc_verify_kernel<<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
+  prof_end(PROF_MNN_VERIFY, stream);
   PF_LAUNCH_CHECK("tc_verify_kernel");
+  prof_begin(PROF_MNN_COMPACT, stream);
   tc_compact_flags_kernel<<<P, 1024, 0, stream>>>(nn12, w.mutual, N, matches, n_matches);
   prof_end(PROF_MNN_COMPACT, stream);
   PF_LAUNCH_CHECK("tc_compact_flags_kernel");
