@@ -278,7 +278,10 @@ def main():
         if tc_ms:
             ach = flops / (tc_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "mnn_tc_kernel", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " (burst bf16)",
+                    "frac": ach / pk["bf16"],
+                    # dram read+write of mnn_tc_kernel from the ncu --set full capture (113.8 MB per 8-pair launch,
+                    # profiles/r01_ncu_full_mnn_tc_kernel_P8.csv), scaled to this launch's pair count
+                    "traffic": 14.23e6 * pairs_per_launch, "peak_source": pk["src"] + " (burst bf16)",
                     "algorithmic_flops_per_launch": flops}
         nms_ms = kern.get("nms_candidates", {}).get("ms_per_launch")
         extra = {}
