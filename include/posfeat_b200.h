@@ -36,6 +36,11 @@ extern "C" {
  * (losses/preprocess_utils.py:225-230). */
 #define POSFEAT_NMS_NONE 0
 #define POSFEAT_NMS_HARD 1
+#define POSFEAT_NMS_SOFT 2          /* use_nms='softnms' (soft_nms, losses/preprocess_utils.py:431-447) */
+/* or-ed into nms_mode / mode: NMS, threshold and top-k over the WHOLE map, outputs are the
+ * pixel's own grid coordinate and score (generate_kpts_single_noavg, :280-336); idx_out then
+ * indexes the H x W map and workspaces are sized with (H+2, W+2). */
+#define POSFEAT_DETECT_FULLMAP 0x10
 /* thr_mode: thr=False, thr_mod='abs'|'max'|'mean' (:232-240). */
 #define POSFEAT_THR_NONE 0
 #define POSFEAT_THR_ABS 1
@@ -86,7 +91,7 @@ int posfeat_detect_candidates_f32(const float* score, int B, int H, int W,
                                   void* stream);
 
 int posfeat_detect_select_f32(const float* score, int B, int H, int W,
-                              int64_t stride_b, int64_t stride_y,
+                              int64_t stride_b, int64_t stride_y, int mode,
                               int num_pts, int min_pts, int cap_pts, int n_fixed,
                               const int32_t* counts, int32_t* n_out,
                               int64_t* idx_out, float* kps_out, float* kpscore_out,
@@ -160,6 +165,17 @@ int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, int64_t lda
                             int D, int P, int algo, int32_t* nn12, int32_t* nn21,
                             int64_t* matches, int32_t* n_matches,
                             void* workspace, size_t ws_bytes, void* stream);
+
+/* Ratio-test matchers: ratio_matcher / mutual_nn_ratio_matcher,
+ * evaluations/aachen/matchers.py:17-75 (ETH copy custom_matcher.py:16-73).  Top-2
+ * similarities per row and per column (exact kernel), dist = sqrt(2 - 2 sim),
+ * ratio = d0 / (d1 + 1e-8); row i is kept iff ratio12[i] <= ratio and
+ * ratio21[nn12[i]] <= ratio, and for mutual != 0 also nn21[nn12[i]] == i.
+ * N, M >= 2 (torch.topk(2) raises otherwise). */
+size_t posfeat_ratio_match_workspace_bytes(int N, int M, int D);
+int posfeat_ratio_match_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb,
+                            int D, float ratio, int mutual, int32_t* nn12, int64_t* matches,
+                            int32_t* n_matches, void* workspace, size_t ws_bytes, void* stream);
 
 /* Same, operands and results in HOST memory (pageable or pinned): copies in,
  * runs, copies back and synchronises `stream`.  This is the call a reader of

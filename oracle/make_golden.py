@@ -93,6 +93,72 @@ def golden_detect():
     print("detect:", list(cases))
 
 
+def ref_detect_noavg(kp_map, **cfg):
+    kps, sc = pu.generate_kpts_single_noavg(kp_map, **cfg)
+    b = kp_map.shape[0]
+    use_nms = cfg.get("use_nms", True)
+    if use_nms == "softnms":
+        mask = pu.soft_nms(kp_map, cfg["nms_radius"])
+    elif use_nms:
+        mask = pu.nms(kp_map, cfg["nms_radius"])
+    else:
+        mask = torch.ones_like(kp_map)
+    thr = cfg.get("thr", False)
+    cnt_mask = mask
+    if thr:
+        mod = cfg.get("thr_mod", "mean")
+        t = kp_map.reshape(b, 1, -1).max(2)[0] if mod == "max" else kp_map.reshape(b, 1, -1).mean(2)
+        thr_mask = kp_map > thr * t.view(b, 1, 1, 1)
+        mask = thr_mask * mask
+        cnt_mask = thr_mask if use_nms == "softnms" else mask
+    key = (mask * kp_map).reshape(b, -1)
+    _, idx = key.topk(kps.shape[1])
+    return dict(kps=kps.numpy(), score=sc.numpy(), idx=idx.numpy(), key=key.numpy(),
+                count=np.asarray(cnt_mask.reshape(b, -1).sum(1).numpy()))
+
+
+def golden_detect_ext():
+    """soft NMS (use_nms='softnms') and generate_kpts_single_noavg -- the remaining
+    detector_config options of the plugin slot."""
+    g = gen(111)
+    base = F.softplus(torch.randn(2, 1, 48, 64, generator=g))
+    odd = F.softplus(2 * torch.randn(1, 1, 37, 131, generator=g))
+    soft = {
+        "soft_r1_mean": (base, dict(nms_radius=1, num_pts=300, use_nms="softnms", thr=1.0, thr_mod="mean")),
+        "soft_r2_abs": (base, dict(nms_radius=2, num_pts=False, use_nms="softnms", thr=1.2, thr_mod="abs")),
+        "soft_r4_max": (odd, dict(nms_radius=4, num_pts=500, use_nms="softnms", thr=0.2, thr_mod="max")),
+    }
+    noavg = {
+        "noavg_r1": (base, dict(nms_radius=1, num_pts=300)),
+        "noavg_r2_mean": (base, dict(nms_radius=2, num_pts=False, thr=1.1, thr_mod="mean")),
+        "noavg_r5_max": (odd, dict(nms_radius=5, num_pts=200, thr=0.1, thr_mod="max")),
+        "noavg_nonms": (base, dict(nms_radius=1, num_pts=256, use_nms=False, thr=1.5, thr_mod="mean")),
+        "noavg_soft": (odd, dict(nms_radius=2, num_pts=400, use_nms="softnms", thr=1.0, thr_mod="mean")),
+    }
+    out = {}
+    for name, (m, cfg) in soft.items():
+        r = ref_detect(m, **cfg)
+        b = m.shape[0]
+        inter = m[:, :, 1:-1, 1:-1]
+        mod = cfg["thr_mod"]
+        t = (inter.reshape(b, 1, -1).max(2)[0] if mod == "max" else inter.reshape(b, 1, -1).mean(2)
+             if mod == "mean" else torch.tensor(1.).repeat(b))
+        r["count"] = (inter > cfg["thr"] * t.view(b, 1, 1, 1)).reshape(b, -1).sum(1).numpy()   # thr_mask count (:253,:258)
+        del r["nms_mask"]
+        out[name + "/map"] = m.numpy()
+        out[name + "/cfg"] = np.array(repr(cfg))
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+    for name, (m, cfg) in noavg.items():
+        r = ref_detect_noavg(m, **cfg)
+        out[name + "/map"] = m.numpy()
+        out[name + "/cfg"] = np.array(repr(cfg))
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "detect_ext.npz"), **out)
+    print("detect_ext:", list(soft) + list(noavg))
+
+
 def golden_sample():
     g = gen(202)
     x = torch.randn(2, 24, 12, 15, generator=g)
@@ -227,10 +293,9 @@ def golden_preprocess():
 
 
 if __name__ == "__main__":
-    golden_detect()
-    golden_sample()
-    golden_mnn()
-    golden_corr()
-    golden_preprocess()
+    only = set(sys.argv[1:])                      # e.g. `python oracle/make_golden.py detect_ext`
+    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_preprocess):
+        if not only or fn.__name__[len("golden_"):] in only:
+            fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes:", tot)

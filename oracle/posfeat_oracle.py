@@ -239,6 +239,42 @@ def generate_kpts_single(kp_map, nms_radius, num_pts=False, scale=4, stable=True
     return kps, sc
 
 
+def generate_kpts_single_noavg(kp_map, nms_radius, num_pts=False, scale=4, stable=True,
+                               temperature=1, stride=1, use_nms=True, thr=False,
+                               thr_mod="mean", return_idx=False):
+    """losses/preprocess_utils.py:280-336, ``stable=True`` branch: NMS, threshold and
+    top-k over the WHOLE map (no border crop), keypoints are the winners' own grid
+    coordinates and scores (no 3x3 centroid / max).  idx indexes the h x w map."""
+    assert stable
+    kp_map = np.asarray(kp_map, dtype=F32)
+    b, _, h, w = kp_map.shape
+    if thr and thr_mod not in ("max", "mean"):
+        raise ValueError(thr_mod)                      # kp_thr is unset in the reference
+    keys, counts = [], []
+    for i in range(b):
+        # detect_keys crops one border pixel; present the map as the interior of a padded one
+        k, c = detect_keys(np.pad(kp_map[i, 0], 1), nms_radius, use_nms, thr, thr_mod)
+        keys.append(k.reshape(-1))
+        counts.append(c)
+    n = min(counts) if not num_pts else min(int(num_pts), min(counts))
+    if n < 128:
+        n = 128
+    ys = linspace_f32(-1, 1, h)
+    xs = linspace_f32(-1, 1, w)
+    kps = np.empty((b, n, 2), dtype=F32)
+    sc = np.empty((b, n, 1), dtype=F32)
+    idxs = np.empty((b, n), dtype=np.int64)
+    for i in range(b):
+        idx = topk_desc(keys[i], n)
+        kps[i, :, 0] = xs[idx % w]
+        kps[i, :, 1] = ys[idx // w]
+        sc[i, :, 0] = kp_map[i, 0].reshape(-1)[idx]
+        idxs[i] = idx
+    if return_idx:
+        return kps, sc, idxs, np.array(counts)
+    return kps, sc
+
+
 # --------------------------------------------------------------------------
 # subsystem 2: bilinear descriptor sampling + L2 normalisation
 # --------------------------------------------------------------------------
@@ -332,11 +368,12 @@ def ratio_matchers(desc_a, desc_b, ratio=0.95, mutual=True, exact=False):
     evaluations/aachen/matchers.py:17-75 (ETH copy: custom_matcher.py:16-73)."""
     sim = similarity(np.asarray(desc_a), np.asarray(desc_b), exact).astype(F32)
     v12, n12 = _top2(sim)
-    d12 = np.sqrt(np.maximum(F32(2) - F32(2) * v12, 0), dtype=F32)
-    r12 = d12[:, 0] / (d12[:, 1] + F32(1e-8))
-    v21, n21 = _top2(sim.T)
-    d21 = np.sqrt(np.maximum(F32(2) - F32(2) * v21, 0), dtype=F32)
-    r21 = d21[:, 0] / (d21[:, 1] + F32(1e-8))
+    with np.errstate(invalid="ignore"):      # sim > 1 by rounding -> NaN -> fails the test, as in torch
+        d12 = np.sqrt(F32(2) - F32(2) * v12, dtype=F32)
+        r12 = d12[:, 0] / (d12[:, 1] + F32(1e-8))
+        v21, n21 = _top2(sim.T)
+        d21 = np.sqrt(F32(2) - F32(2) * v21, dtype=F32)
+        r21 = d21[:, 0] / (d21[:, 1] + F32(1e-8))
     nn12, nn21 = n12[:, 0], n21[:, 0]
     ids = np.arange(sim.shape[0])
     keep = (r12 <= F32(ratio)) & (r21[nn12] <= F32(ratio))

@@ -30,7 +30,7 @@ SIGNATURES = {
     "posfeat_profile_read": (_i, [_i, C.POINTER(C.c_double), c_i32p]),
     "posfeat_detect_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_detect_candidates_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
-    "posfeat_detect_select_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+    "posfeat_detect_select_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp]),
     "posfeat_detect_topk_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _sz, _vp]),
@@ -43,6 +43,8 @@ SIGNATURES = {
     "posfeat_mnn_batched_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "posfeat_mnn_batched_f32": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                      _sz, _vp]),
+    "posfeat_ratio_match_workspace_bytes": (_sz, [_i, _i, _i]),
+    "posfeat_ratio_match_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_mnn_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_host_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
@@ -54,7 +56,8 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
-NMS_NONE, NMS_HARD = 0, 1
+NMS_NONE, NMS_HARD, NMS_SOFT = 0, 1, 2
+DETECT_FULLMAP = 0x10
 THR_NONE, THR_ABS, THR_MAX, THR_MEAN = 0, 1, 2, 3
 MNN_AUTO, MNN_SIMT, MNN_TC = 0, 1, 2
 

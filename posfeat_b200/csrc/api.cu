@@ -198,6 +198,34 @@ extern "C" int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* 
                                  ws_bytes, stream);
 }
 
+// ---- ratio-test matchers (evaluations/aachen/matchers.py:17-75, ETH custom_matcher.py:16-73)
+extern "C" size_t posfeat_ratio_match_workspace_bytes(int N, int M, int D) {
+  if (N < 2 || M < 2 || D < 1) return 0;
+  return simt_workspace_bytes(N, M) + align_up(sizeof(int32_t) * (size_t)M, 256) +
+         align_up(sizeof(float) * 2 * (size_t)N, 256) + align_up(sizeof(float) * 2 * (size_t)M, 256) +
+         align_up((size_t)N, 256);
+}
+
+extern "C" int posfeat_ratio_match_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D,
+                                       float ratio, int mutual, int32_t* nn12, int64_t* matches, int32_t* n_matches,
+                                       void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(A && Bm && nn12 && matches && n_matches && workspace, "NULL pointer");
+  PF_CHECK_ARG(N >= 2 && M >= 2 && D >= 1, "the ratio test needs at least two descriptors on each side (torch.topk(2) raises otherwise)");
+  PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
+  const size_t need = posfeat_ratio_match_workspace_bytes(N, M, D);
+  if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "ratio workspace: need %zu bytes, got %zu", need, ws_bytes);
+  char* w = (char*)workspace;
+  void* simt_ws = w; w += simt_workspace_bytes(N, M);
+  int32_t* nn21 = (int32_t*)w; w += align_up(sizeof(int32_t) * (size_t)M, 256);
+  float* top12 = (float*)w; w += align_up(sizeof(float) * 2 * (size_t)N, 256);
+  float* top21 = (float*)w; w += align_up(sizeof(float) * 2 * (size_t)M, 256);
+  unsigned char* flags = (unsigned char*)w;
+  if (int e = mnn_simt_top2(A, N, lda, Bm, M, ldb, D, nn12, nn21, top12, top21, simt_ws, stream)) return e;
+  if (int e = launch_ratio_flags(nn12, nn21, top12, top21, N, M, ratio, mutual, flags, stream)) return e;
+  return launch_compact_flags(nn12, flags, 1, N, matches, n_matches, stream);
+}
+
 extern "C" size_t posfeat_mnn_host_scratch_bytes(int N, int M, int D, int algo) {
   if (N < 1 || M < 1 || D < 1) return 0;
   return carve_host_scratch(nullptr, N, M, D, algo).total;

@@ -183,6 +183,17 @@ nms_candidates_kernel(const float* __restrict__ score, int H, int W, int64_t sb,
         }
       }
     }
+    if (keep && nms_mode == POSFEAT_NMS_SOFT) {
+      // soft_nms (:431-447): alpha = softplus(c - avg_pool(reflect-padded window)); the top-k key
+      // is (thr_mask * alpha) * score (:240, :263).  Window summed row-major in fp32 like avg_pool2d.
+      const float* base = tile + ly * pitch + lx;
+      float sum = 0.f;
+      for (int dy = 0; dy <= 2 * r; ++dy)
+        for (int dx = 0; dx <= 2 * r; ++dx) sum = __fadd_rn(sum, base[dy * pitch + dx]);
+      const float a = __fsub_rn(c, __fdiv_rn(sum, (float)((2 * r + 1) * (2 * r + 1))));
+      const float alpha = a > 20.f ? a : log1pf(expf(a));
+      c = __fmul_rn(alpha, c);
+    }
     n_all += keep ? 1 : 0;
     const bool emit = keep && c > 0.f;
     const unsigned bal = __ballot_sync(0xffffffffu, emit);
@@ -510,7 +521,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
               const u64* __restrict__ cand, int64_t cand_cap, u64* __restrict__ sortbuf,
               int64_t sort_cap, int32_t* __restrict__ status, int32_t* __restrict__ n_out,
               int64_t* __restrict__ idx_out, float* __restrict__ kps_out,
-              float* __restrict__ kpscore_out, int debug) {
+              float* __restrict__ kpscore_out, int fullmap, int debug) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* s_keys = (u64*)smem_raw;  // kSortSmemKeys
   __shared__ unsigned s_hist[1 << kDigitBits];
@@ -763,6 +774,16 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   for (int i = tid; i < n; i += kSelThreads) {
     const unsigned idx = i < n_real ? 0xffffffffu - (unsigned)buf[i] : s_fill[i - n_real];
     const int y0 = idx / wi, x0 = idx - y0 * wi;
+    if (fullmap) {
+      // generate_kpts_single_noavg (:280-336): the pixel's own grid coordinate and score; (H, W) here
+      // are the virtual padded sizes, the real map is the hi x wi "interior"
+      const int64_t o = (int64_t)b * cap_pts + i;
+      idx_out[o] = (int64_t)idx;
+      kps_out[2 * o + 0] = linspace_pm1(x0, wi, 2.0f / (float)(wi - 1));
+      kps_out[2 * o + 1] = linspace_pm1(y0, hi, 2.0f / (float)(hi - 1));
+      kpscore_out[o] = __ldg(img + (int64_t)(y0 + 1) * sy + x0 + 1);
+      continue;
+    }
     float sx = 0.f, sy_ = 0.f, sw = 0.f, mx = -INFINITY;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
@@ -794,12 +815,20 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
 #undef PF_TICK
 }
 
-static int check_common(const float* score, int B, int H, int W, int64_t sy) {
+// POSFEAT_DETECT_FULLMAP: the whole map plays the role of the interior.  The kernels only ever read
+// interior pixels (reflect padding is about the interior), so the map is presented as the interior of a
+// virtual (H+2) x (W+2) map whose origin lies one row and one column before the real one.
+static int check_common(const float*& score, int B, int& H, int& W, int64_t sy, int mode) {
   PF_CHECK_ARG(score != nullptr, "score is NULL");
   PF_CHECK_ARG(B >= 1, "B must be >= 1 (got %d)", B);
+  PF_CHECK_ARG(sy >= W, "row stride %lld smaller than W=%d", (long long)sy, W);
+  if (mode & POSFEAT_DETECT_FULLMAP) {
+    score -= sy + 1;
+    H += 2;
+    W += 2;
+  }
   PF_CHECK_ARG(H >= 4 && W >= 4, "score map must be at least 4x4 (got %dx%d)", H, W);
   PF_CHECK_ARG((int64_t)(H - 2) * (W - 2) < 0xffffffffLL, "interior grid too large for 32-bit indices");
-  PF_CHECK_ARG(sy >= W, "row stride %lld smaller than W=%d", (long long)sy, W);
   return 0;
 }
 
@@ -817,8 +846,11 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
                                              float thr, int32_t* counts, void* workspace, size_t ws_bytes,
                                              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (int e = check_common(score, B, H, W, stride_y)) return e;
-  PF_CHECK_ARG(nms_mode == POSFEAT_NMS_NONE || nms_mode == POSFEAT_NMS_HARD, "unsupported nms_mode %d", nms_mode);
+  if (int e = check_common(score, B, H, W, stride_y, nms_mode)) return e;
+  nms_mode &= ~POSFEAT_DETECT_FULLMAP;
+  PF_CHECK_ARG(nms_mode >= POSFEAT_NMS_NONE && nms_mode <= POSFEAT_NMS_SOFT, "unsupported nms_mode %d", nms_mode);
+  PF_CHECK_ARG(nms_mode != POSFEAT_NMS_SOFT || thr_mode != POSFEAT_THR_NONE,
+               "soft NMS needs a threshold (the reference's thr_mask is undefined otherwise)");
   PF_CHECK_ARG(thr_mode >= POSFEAT_THR_NONE && thr_mode <= POSFEAT_THR_MEAN, "unsupported thr_mode %d", thr_mode);
   PF_CHECK_ARG(radius >= 0 && radius <= 16, "nms radius %d outside [0,16]", radius);
   PF_CHECK_ARG(nms_mode == POSFEAT_NMS_NONE || (radius <= H - 3 && radius <= W - 3),
@@ -826,7 +858,7 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
   PF_CHECK_ARG(counts && workspace, "counts/workspace is NULL");
   DetectWs w = carve(workspace, B, H, W, 1);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", w.total, ws_bytes);
-  const int r = nms_mode == POSFEAT_NMS_HARD ? radius : 0;
+  const int r = nms_mode != POSFEAT_NMS_NONE ? radius : 0;
 
   // zero the small header (cand_count, thr_val, red_sum, red_max, status) and counts
   PF_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char*)w.cand - (char*)workspace), stream));
@@ -843,7 +875,7 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
     PF_LAUNCH_CHECK("finalize_thr_kernel");
   }
   ProfScope prof(PROF_NMS, stream);
-  if (r <= 3) {
+  if (r <= 3 && nms_mode != POSFEAT_NMS_SOFT) {
     // register sliding-window kernel; without NMS every pixel may survive, so strips are 16 rows tall
     const int rows = nms_mode == POSFEAT_NMS_HARD ? 64 : 16;
     const int use = 32 - 2 * r;
@@ -877,11 +909,11 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
 }
 
 extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W, int64_t stride_b, int64_t stride_y,
-                                         int num_pts, int min_pts, int cap_pts, int n_fixed, const int32_t* counts,
+                                         int mode, int num_pts, int min_pts, int cap_pts, int n_fixed, const int32_t* counts,
                                          int32_t* n_out, int64_t* idx_out, float* kps_out, float* kpscore_out,
                                          void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (int e = check_common(score, B, H, W, stride_y)) return e;
+  if (int e = check_common(score, B, H, W, stride_y, mode)) return e;
   PF_CHECK_ARG(cap_pts >= 1 && num_pts >= 0 && min_pts >= 0, "bad num_pts/min_pts/cap_pts");
   PF_CHECK_ARG(n_fixed <= cap_pts, "n_fixed %d exceeds cap_pts %d", n_fixed, cap_pts);
   PF_CHECK_ARG(counts && n_out && idx_out && kps_out && kpscore_out && workspace, "NULL output pointer");
@@ -897,6 +929,7 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
   select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
                                                    counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,
                                                    w.status, n_out, idx_out, kps_out, kpscore_out,
+                                                   (mode & POSFEAT_DETECT_FULLMAP) ? 1 : 0,
                                                    getenv("POSFEAT_SELECT_DEBUG") ? 1 : 0);
   PF_LAUNCH_CHECK("select_kernel");
   return POSFEAT_OK;
@@ -906,12 +939,13 @@ extern "C" int posfeat_detect_topk_f32(const float* score, int B, int H, int W, 
                                        int nms_mode, int radius, int thr_mode, float thr, int num_pts, int min_pts,
                                        int cap_pts, int32_t* counts, int32_t* n_out, int64_t* idx_out, float* kps_out,
                                        float* kpscore_out, void* workspace, size_t ws_bytes, void* stream) {
-  size_t need = posfeat_detect_workspace_bytes(B, H, W, cap_pts);
+  const int pad = (nms_mode & POSFEAT_DETECT_FULLMAP) ? 2 : 0;
+  size_t need = posfeat_detect_workspace_bytes(B, H + pad, W + pad, cap_pts);
   if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", need, ws_bytes);
   int e = posfeat_detect_candidates_f32(score, B, H, W, stride_b, stride_y, nms_mode, radius, thr_mode, thr, counts,
                                         workspace, ws_bytes, stream);
   if (e) return e;
-  return posfeat_detect_select_f32(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, -1, counts, n_out,
+  return posfeat_detect_select_f32(score, B, H, W, stride_b, stride_y, nms_mode, num_pts, min_pts, cap_pts, -1, counts, n_out,
                                    idx_out, kps_out, kpscore_out, workspace, ws_bytes, stream);
 }
 

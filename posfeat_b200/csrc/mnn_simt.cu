@@ -22,7 +22,7 @@ constexpr int kBM = 64, kBN = 64, kBK = 32, kPitch = 66;
 __global__ void __launch_bounds__(256)
 rowbest_simt_kernel(const float* __restrict__ X, int NX, int64_t ldx, const float* __restrict__ Y, int NY,
                     int64_t ldy, int D, int cols_per_split, double* __restrict__ part_val,
-                    int32_t* __restrict__ part_idx) {
+                    int32_t* __restrict__ part_idx, double* __restrict__ part_sec) {
   __shared__ __align__(16) double Xs[kBK][kPitch];
   __shared__ __align__(16) double Ys[kBK][kPitch];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -31,10 +31,10 @@ rowbest_simt_kernel(const float* __restrict__ X, int NX, int64_t ldx, const floa
   const int c_begin = split * cols_per_split;
   const int c_end = min(NY, c_begin + cols_per_split);
 
-  double bestv[4];
+  double bestv[4], secv[4];      // best and second best value per row (second: Lowe ratio test)
   int besti[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { bestv[i] = -INFINITY; besti[i] = 0x7fffffff; }
+  for (int i = 0; i < 4; ++i) { bestv[i] = -INFINITY; secv[i] = -INFINITY; besti[i] = 0x7fffffff; }
 
   for (int col0 = c_begin; col0 < c_end; col0 += kBN) {
     double acc[4][4];
@@ -75,7 +75,10 @@ rowbest_simt_kernel(const float* __restrict__ X, int NX, int64_t ldx, const floa
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = col0 + tx * 4 + j;
-        if (c < c_end && acc[i][j] > bestv[i]) { bestv[i] = acc[i][j]; besti[i] = c; }
+        if (c < c_end) {
+          if (acc[i][j] > bestv[i]) { secv[i] = bestv[i]; bestv[i] = acc[i][j]; besti[i] = c; }
+          else if (acc[i][j] > secv[i]) secv[i] = acc[i][j];
+        }
       }
   }
   // reduce over the 16 threads (tx) that share a row group: half-warp butterflies
@@ -85,28 +88,53 @@ rowbest_simt_kernel(const float* __restrict__ X, int NX, int64_t ldx, const floa
     for (int o = 8; o > 0; o >>= 1) {
       const double ov = __shfl_xor_sync(0xffffffffu, bestv[i], o);
       const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
+      const double os = __shfl_xor_sync(0xffffffffu, secv[i], o);
+      secv[i] = fmax(fmax(secv[i], os), fmin(bestv[i], ov));
       if (ov > bestv[i] || (ov == bestv[i] && oi < besti[i])) { bestv[i] = ov; besti[i] = oi; }
     }
     const int r = row0 + ty * 4 + i;
     if (tx == 0 && r < NX) {
       part_val[(int64_t)split * NX + r] = bestv[i];
       part_idx[(int64_t)split * NX + r] = besti[i];
+      if (part_sec) part_sec[(int64_t)split * NX + r] = secv[i];
     }
   }
 }
 
 __global__ void rowbest_finalize_kernel(const double* __restrict__ part_val, const int32_t* __restrict__ part_idx,
-                                        int NX, int splits, int32_t* __restrict__ nn) {
+                                        const double* __restrict__ part_sec, int NX, int splits,
+                                        int32_t* __restrict__ nn, float* __restrict__ top2) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= NX) return;
-  double bv = -INFINITY;
+  double bv = -INFINITY, sv = -INFINITY;
   int bi = 0x7fffffff;
   for (int s = 0; s < splits; ++s) {
     const double v = part_val[(int64_t)s * NX + r];
     const int i = part_idx[(int64_t)s * NX + r];
+    if (part_sec) sv = fmax(fmax(sv, part_sec[(int64_t)s * NX + r]), fmin(bv, v));
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
   nn[r] = bi == 0x7fffffff ? 0 : bi;   // all-NaN rows: torch.max also reports an index
+  if (top2) { top2[2 * r] = (float)bv; top2[2 * r + 1] = (float)sv; }   // the reference's sim is float32
+}
+
+// Lowe ratio test of evaluations/aachen/matchers.py:17-75 on the top-2 similarities:
+// dist = sqrt(2 - 2 sim), ratio = d0 / (d1 + 1e-8); keep i iff ratio12[i] <= ratio and
+// ratio21[nn12[i]] <= ratio (and, for the mutual variant, nn21[nn12[i]] == i).
+__global__ void ratio_flags_kernel(const int32_t* __restrict__ nn12, const int32_t* __restrict__ nn21,
+                                   const float* __restrict__ top12, const float* __restrict__ top21, int N, int M,
+                                   float ratio, int mutual, unsigned char* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  auto lowe = [](float s0, float s1) {
+    const float d0 = sqrtf(2.f - 2.f * s0), d1 = sqrtf(2.f - 2.f * s1);
+    return d0 / (d1 + 1e-8f);
+  };
+  const int j = nn12[i];
+  bool keep = lowe(top12[2 * i], top12[2 * i + 1]) <= ratio;
+  keep = keep && j >= 0 && j < M && lowe(top21[2 * j], top21[2 * j + 1]) <= ratio;   // NaN ratios fail like torch
+  if (mutual) keep = keep && nn21[j] == i;
+  flags[i] = keep ? 1 : 0;
 }
 
 // keep rows with nn21[nn12[i]] == i, ordered compaction (ascending i); one CTA per
@@ -194,35 +222,48 @@ static int choose_splits(int NX, int NY) {
 }
 
 size_t simt_workspace_bytes(int N, int M) {
-  // partial (value, index) per split and row, both directions (splits <= 64)
-  const size_t per = sizeof(double) + sizeof(int32_t);
-  return align_up((size_t)64 * N * per, 256) + align_up((size_t)64 * M * per, 256) + 512;
+  // partial (value, second value, index) per split and row, both directions (splits <= 64)
+  const size_t per = 2 * sizeof(double) + sizeof(int32_t);
+  return align_up((size_t)64 * N * per, 256) + align_up((size_t)64 * M * per, 256) + 1024;
 }
 
 int run_rowbest_simt(const float* X, int NX, int64_t ldx, const float* Y, int NY, int64_t ldy, int D,
-                     int32_t* nn, void* ws, cudaStream_t stream) {
+                     int32_t* nn, float* top2, void* ws, cudaStream_t stream) {
   const int splits = choose_splits(NX, NY);
   const int col_tiles = (NY + kBN - 1) / kBN;
   const int cols_per_split = ((col_tiles + splits - 1) / splits) * kBN;
   const int used = (NY + cols_per_split - 1) / cols_per_split;
   double* pv = (double*)ws;
-  int32_t* pi = (int32_t*)((char*)ws + align_up(sizeof(double) * (size_t)64 * NX, 256));
+  double* ps = top2 ? pv + (size_t)64 * NX : nullptr;
+  int32_t* pi = (int32_t*)((char*)ws + align_up(2 * sizeof(double) * (size_t)64 * NX, 256));
   dim3 grid((NX + kBM - 1) / kBM, used);
   ProfScope prof(PROF_MNN_SIMT, stream);
-  rowbest_simt_kernel<<<grid, 256, 0, stream>>>(X, NX, ldx, Y, NY, ldy, D, cols_per_split, pv, pi);
+  rowbest_simt_kernel<<<grid, 256, 0, stream>>>(X, NX, ldx, Y, NY, ldy, D, cols_per_split, pv, pi, ps);
   PF_LAUNCH_CHECK("rowbest_simt_kernel");
-  rowbest_finalize_kernel<<<(NX + 255) / 256, 256, 0, stream>>>(pv, pi, NX, used, nn);
+  rowbest_finalize_kernel<<<(NX + 255) / 256, 256, 0, stream>>>(pv, pi, ps, NX, used, nn, top2);
   PF_LAUNCH_CHECK("rowbest_finalize_kernel");
   return POSFEAT_OK;
 }
 
 int mnn_simt(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
              int32_t* nn21, void* ws, cudaStream_t stream) {
+  return mnn_simt_top2(A, N, lda, Bm, M, ldb, D, nn12, nn21, nullptr, nullptr, ws, stream);
+}
+
+int mnn_simt_top2(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb, int D, int32_t* nn12,
+                  int32_t* nn21, float* top12, float* top21, void* ws, cudaStream_t stream) {
   char* w = (char*)ws;
-  const size_t per = sizeof(double) + sizeof(int32_t);
-  if (int e = run_rowbest_simt(A, N, lda, Bm, M, ldb, D, nn12, w, stream)) return e;
-  w += align_up((size_t)64 * N * per, 256) + 256;
-  return run_rowbest_simt(Bm, M, ldb, A, N, lda, D, nn21, w, stream);
+  const size_t per = 2 * sizeof(double) + sizeof(int32_t);
+  if (int e = run_rowbest_simt(A, N, lda, Bm, M, ldb, D, nn12, top12, w, stream)) return e;
+  w += align_up((size_t)64 * N * per, 256) + 512;
+  return run_rowbest_simt(Bm, M, ldb, A, N, lda, D, nn21, top21, w, stream);
+}
+
+int launch_ratio_flags(const int32_t* nn12, const int32_t* nn21, const float* top12, const float* top21, int N, int M,
+                       float ratio, int mutual, unsigned char* flags, cudaStream_t stream) {
+  ratio_flags_kernel<<<(N + 255) / 256, 256, 0, stream>>>(nn12, nn21, top12, top21, N, M, ratio, mutual, flags);
+  PF_LAUNCH_CHECK("ratio_flags_kernel");
+  return POSFEAT_OK;
 }
 
 }  // namespace posfeat

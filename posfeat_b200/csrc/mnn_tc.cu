@@ -1035,6 +1035,13 @@ tc_compact_flags_kernel(const int32_t* __restrict__ nn12_, const unsigned char* 
   if (tid == 0) n_matches[pair] = s_base;
 }
 
+int launch_compact_flags(const int32_t* nn12, const unsigned char* flags, int P, int N, int64_t* matches,
+                         int32_t* n_matches, cudaStream_t stream) {
+  tc_compact_flags_kernel<<<P, 1024, 0, stream>>>(nn12, flags, N, matches, n_matches);
+  PF_LAUNCH_CHECK("tc_compact_flags_kernel");
+  return POSFEAT_OK;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

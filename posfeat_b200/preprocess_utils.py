@@ -44,13 +44,15 @@ def _thr_mode(thr, thr_mod):
 
 
 def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_mod="mean",
-                sync=True):
+                sync=True, fullmap=False):
     """Kernel-level detector.  Returns a dict with device tensors
     ``kps [b,cap,2]``, ``score [b,cap]``, ``idx [b,cap]`` (int64 linear index into
     the interior grid), ``counts [b]``, ``n`` (python int when ``sync`` else a
-    device int32 tensor).  Rows >= n are undefined."""
-    if use_nms == "softnms":
-        raise NotImplementedError("use_nms='softnms' is not built yet (SURVEY.md section 8f-3)")
+    device int32 tensor).  Rows >= n are undefined.  ``fullmap`` selects the
+    ``generate_kpts_single_noavg`` variant (whole map, no 3x3 centroid)."""
+    if use_nms == "softnms" and not thr:
+        # the reference reads thr_mask, which only exists under `if thr:` (:232-240, :251-259)
+        raise UnboundLocalError("use_nms='softnms' needs thr (thr_mask is referenced before assignment otherwise)")
     x, _ = to_device(kp_map)
     if x.dim() != 4 or x.shape[1] != 1:
         raise ValueError(f"kp_map must be [b,1,h,w], got {tuple(x.shape)}")
@@ -59,15 +61,21 @@ def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_
     b, _, h, w = x.shape
     L = lib()
     dev = x.device
-    nms_mode = _lib.NMS_HARD if use_nms else _lib.NMS_NONE
+    nms_mode = _lib.NMS_SOFT if use_nms == "softnms" else _lib.NMS_HARD if use_nms else _lib.NMS_NONE
     thr_mode, thr_val = _thr_mode(thr, thr_mod)
+    pad = 0
+    if fullmap:
+        if thr_mode == _lib.THR_ABS:
+            raise UnboundLocalError("generate_kpts_single_noavg has no thr_mod='abs' (kp_thr unset in the reference)")
+        nms_mode |= _lib.DETECT_FULLMAP
+        pad = 2
     counts = torch.empty(b, dtype=torch.int32, device=dev)
     n_out = torch.empty(1, dtype=torch.int32, device=dev)
     st = stream_ptr(dev)
     with torch.cuda.device(dev):
         if num_pts:
             cap = max(int(num_pts), MIN_PTS)
-            ws_bytes = L.posfeat_detect_workspace_bytes(b, h, w, cap)
+            ws_bytes = L.posfeat_detect_workspace_bytes(b, h + pad, w + pad, cap)
             ws = workspace("detect", ws_bytes, dev)
             idx = torch.empty((b, cap), dtype=torch.int64, device=dev)
             kps = torch.empty((b, cap, 2), dtype=torch.float32, device=dev)
@@ -78,19 +86,20 @@ def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_
                                             kps.data_ptr(), sc.data_ptr(), ws.data_ptr(), ws.numel(), st))
         else:
             # num_pts=False: n is the smallest survivor count -> read it, then select
-            ws_bytes = L.posfeat_detect_workspace_bytes(b, h, w, 1)
+            ws_bytes = L.posfeat_detect_workspace_bytes(b, h + pad, w + pad, 1)
             ws = workspace("detect", ws_bytes, dev)
             check(L.posfeat_detect_candidates_f32(x.data_ptr(), b, h, w, x.stride(0), x.stride(2), nms_mode,
                                                   int(nms_radius), thr_mode, thr_val, counts.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), st))
             cap = max(int(counts.min().item()), MIN_PTS)
-            ws_bytes = L.posfeat_detect_workspace_bytes(b, h, w, cap)
+            ws_bytes = L.posfeat_detect_workspace_bytes(b, h + pad, w + pad, cap)
             if ws_bytes > ws.numel():
                 raise _lib.PosfeatError("detect workspace grew between phases")  # cannot happen: cand dominates
             idx = torch.empty((b, cap), dtype=torch.int64, device=dev)
             kps = torch.empty((b, cap, 2), dtype=torch.float32, device=dev)
             sc = torch.empty((b, cap), dtype=torch.float32, device=dev)
-            check(L.posfeat_detect_select_f32(x.data_ptr(), b, h, w, x.stride(0), x.stride(2), 0, MIN_PTS, cap,
+            check(L.posfeat_detect_select_f32(x.data_ptr(), b, h, w, x.stride(0), x.stride(2), nms_mode, 0, MIN_PTS,
+                                              cap,
                                               cap, counts.data_ptr(), n_out.data_ptr(), idx.data_ptr(),
                                               kps.data_ptr(), sc.data_ptr(), ws.data_ptr(), ws.numel(), st))
         n = n_out
@@ -111,6 +120,22 @@ def generate_kpts_single(kp_map, nms_radius, num_pts=False, scale=4, stable=True
     if stride != 1:
         raise NotImplementedError("stride != 1 is not supported (the reference's own shapes break there)")
     r = detect_topk(kp_map, nms_radius, num_pts, use_nms, thr, thr_mod, sync=True)
+    n = r["n"]
+    dev = kp_map.device
+    kps = r["kps"][:, :n].to(dev)
+    sc = r["score"][:, :n, None].to(dev)
+    if return_idx:
+        return kps, sc, r["idx"][:, :n].to(dev), r["counts"].to(dev)
+    return kps, sc
+
+
+def generate_kpts_single_noavg(kp_map, nms_radius, num_pts=False, scale=4, stable=True, temperature=1, stride=1,
+                               use_nms=True, thr=False, thr_mod="mean", return_idx=False):
+    """losses/preprocess_utils.py:280-336 (stable branch): NMS / threshold / top-k over the
+    whole map; ``kps`` are the winners' own grid coordinates, ``kp_score`` their scores."""
+    if not stable:
+        raise NotImplementedError("stable=False (gumbel soft selection, training only) is out of scope")
+    r = detect_topk(kp_map, nms_radius, num_pts, use_nms, thr, thr_mod, sync=True, fullmap=True)
     n = r["n"]
     dev = kp_map.device
     kps = r["kps"][:, :n].to(dev)

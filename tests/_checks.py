@@ -35,6 +35,32 @@ def check_detect(ref_key, ref_idx, ref_kps, ref_score, ref_counts, kps, sc, idx,
                 assert np.all(np.diff(idx[b][rv == v]) > 0), "tie policy: index ascending"
 
 
+def check_detect_float_key(ref_key, ref_idx, ref_kps, ref_score, ref_counts, kps, sc, idx, counts, rel=1e-5):
+    """Soft-NMS variant of check_detect: the selection key softplus(score - boxmean) * score
+    is a float32 computation (avg_pool summation, exp/log1p), so two implementations
+    agree to a few ulp and may swap neighbours whose keys are that close.  Counts (the
+    threshold mask) are exact; the chosen keys must equal the reference's sequence within
+    `rel`, everything clearly above the cut must be chosen, and coordinates / scores of
+    commonly chosen pixels must agree."""
+    assert kps.shape == ref_kps.shape, (kps.shape, ref_kps.shape)
+    np.testing.assert_array_equal(np.asarray(counts, dtype=np.int64), np.asarray(ref_counts, dtype=np.int64))
+    sc = sc.reshape(sc.shape[0], -1)
+    ref_score = ref_score.reshape(ref_score.shape[0], -1)
+    for b in range(ref_idx.shape[0]):
+        rv = ref_key[b][ref_idx[b]].astype(np.float64)
+        ov = ref_key[b][idx[b]].astype(np.float64)
+        np.testing.assert_allclose(ov, rv, rtol=rel, atol=0)
+        assert len(set(idx[b].tolist())) == idx.shape[1]
+        sure = rv > rv[-1] * (1 + rel)
+        assert set(ref_idx[b][sure].tolist()) <= set(idx[b].tolist())
+        pos = {int(j): i for i, j in enumerate(idx[b])}
+        common = [(i, pos[int(j)]) for i, j in enumerate(ref_idx[b]) if rv[i] > 0 and int(j) in pos]
+        assert len(common) >= int(sure.sum())
+        ri, oi = np.array([c[0] for c in common]), np.array([c[1] for c in common])
+        np.testing.assert_allclose(kps[b][oi], ref_kps[b][ri], rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(sc[b][oi], ref_score[b][ri])
+
+
 def check_mnn_near_tie(a, b, got, want, tol=1e-6):
     """Match lists must be identical; if they differ, every disagreeing row or
     column must be a genuine near tie of the exact (float64) similarity."""
@@ -64,3 +90,31 @@ def assert_close_vec(got, want, rel=1e-5, axis=-1):
     err = np.abs(got - want)
     bad = err > rel * scale + 1e-12
     assert not bad.any(), f"{bad.sum()} elements off; worst err/scale = {np.max(err / np.maximum(scale, 1e-30)):.3e}"
+
+
+def check_ratio_near_tie(a, b, got, want, ratio, mutual, band=2e-4):
+    """Ratio-test matches may differ from the reference only on rows whose Lowe
+    ratio sits within float32 noise of the threshold (or whose nearest neighbour is a
+    float32 near tie): sqrt(2 - 2 sim) amplifies 1e-7 similarity noise near sim = 1."""
+    sim = a.astype(np.float64) @ b.astype(np.float64).T
+
+    def ratios(s):
+        part = np.sort(s, axis=1)[:, -2:]
+        d0, d1 = np.sqrt(np.maximum(2 - 2 * part[:, 1], 0)), np.sqrt(np.maximum(2 - 2 * part[:, 0], 0))
+        return d0 / (d1 + 1e-8), part[:, 1] - part[:, 0], part[:, 1]
+    r12, gap12, top12 = ratios(sim)
+    r21, gap21, top21 = ratios(sim.T)
+    nn12 = sim.argmax(1)
+    # noise of the ratio: d(sqrt(2-2s)) = ds / sqrt(2-2s)
+    tol12 = band + 4e-7 / np.maximum(2 - 2 * top12, 1e-12)
+    tol21 = band + 4e-7 / np.maximum(2 - 2 * top21, 1e-12)
+    amb = (np.abs(r12 - ratio) < tol12) | (np.abs(r21[nn12] - ratio) < tol21[nn12]) | (gap12 < 1e-6)
+    if mutual:
+        amb |= gap21[nn12] < 1e-6
+    sure = ~amb
+    g = {int(i): int(j) for i, j in got}
+    w = {int(i): int(j) for i, j in want}
+    for i in np.nonzero(sure)[0]:
+        assert g.get(int(i)) == w.get(int(i)), (i, g.get(int(i)), w.get(int(i)), r12[i], r21[nn12[i]])
+    assert np.all(np.diff(got[:, 0]) > 0) if len(got) > 1 else True
+    return int(amb.sum())

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from _checks import check_detect
+from _checks import check_detect, check_detect_float_key
 from oracle import posfeat_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -26,6 +26,58 @@ def test_detect_golden(golden, name):
     assert sc.shape[-1] == 1
     check_detect(g[name + "/key"], g[name + "/idx"], g[name + "/kps"], g[name + "/score"],
                  g[name + "/count"], kps, sc, idx, counts)
+
+
+EXT_CASES = ["soft_r1_mean", "soft_r2_abs", "soft_r4_max", "noavg_r1", "noavg_r2_mean", "noavg_r5_max",
+             "noavg_nonms", "noavg_soft"]
+
+
+def run_gpu_noavg(m, **cfg):
+    from posfeat_b200.preprocess_utils import generate_kpts_single_noavg
+    kps, sc, idx, counts = generate_kpts_single_noavg(torch.from_numpy(m).cuda(), return_idx=True, **cfg)
+    return kps.cpu().numpy(), sc.cpu().numpy(), idx.cpu().numpy(), counts.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", EXT_CASES)
+def test_detect_ext_golden(golden, name):
+    """use_nms='softnms' and generate_kpts_single_noavg against reference outputs."""
+    g = golden("detect_ext")
+    cfg = eval(str(g[name + "/cfg"]))
+    run = run_gpu_noavg if name.startswith("noavg") else run_gpu
+    kps, sc, idx, counts = run(g[name + "/map"], **cfg)
+    chk = check_detect_float_key if cfg.get("use_nms", True) == "softnms" else check_detect
+    chk(g[name + "/key"], g[name + "/idx"], g[name + "/kps"], g[name + "/score"], g[name + "/count"],
+        kps, sc, idx, counts)
+
+
+@pytest.mark.parametrize("noavg", [False, True])
+@pytest.mark.parametrize("shape,cfg", [
+    ((2, 480, 640), dict(nms_radius=1, num_pts=4096, use_nms="softnms", thr=1.0, thr_mod="mean")),
+    ((1, 896, 1200), dict(nms_radius=2, num_pts=8192, use_nms="softnms", thr=0.3, thr_mod="max")),
+    ((1, 300, 400), dict(nms_radius=1, num_pts=5000)),
+    ((2, 131, 77), dict(nms_radius=4, num_pts=False, thr=1.2, thr_mod="mean")),
+])
+def test_detect_ext_vs_oracle(noavg, shape, cfg):
+    m = softplus_map(*shape, seed=4321 + shape[1])
+    soft = cfg.get("use_nms", True) == "softnms"
+    if not noavg and not soft:
+        pytest.skip("hard NMS through generate_kpts_single is covered by test_detect_vs_oracle")
+    ofn = O.generate_kpts_single_noavg if noavg else O.generate_kpts_single
+    okps, osc, oidx, ocnt = ofn(m, return_idx=True, **cfg)
+    src = [np.pad(m[b, 0], 1) if noavg else m[b, 0] for b in range(m.shape[0])]
+    keys = np.stack([O.detect_keys(x, cfg["nms_radius"], cfg.get("use_nms", True), cfg.get("thr", False),
+                                   cfg.get("thr_mod", "mean"))[0].reshape(-1) for x in src])
+    kps, sc, idx, counts = (run_gpu_noavg if noavg else run_gpu)(m, **cfg)
+    (check_detect_float_key if soft else check_detect)(keys, oidx, okps, osc, ocnt, kps, sc, idx, counts)
+
+
+def test_detect_ext_errors():
+    from posfeat_b200.preprocess_utils import generate_kpts_single, generate_kpts_single_noavg
+    m = torch.rand(1, 1, 40, 40, device="cuda")
+    with pytest.raises(UnboundLocalError):          # thr_mask undefined in the reference without thr
+        generate_kpts_single(m, 1, 200, use_nms="softnms")
+    with pytest.raises(UnboundLocalError):          # noavg has no 'abs' mode
+        generate_kpts_single_noavg(m, 1, 200, thr=0.5, thr_mod="abs")
 
 
 def softplus_map(b, h, w, seed):
@@ -84,8 +136,8 @@ def test_detect_errors():
     x = torch.ones(1, 1, 32, 32, device="cuda")
     with pytest.raises(NotImplementedError):
         P.generate_kpts_single(x, 1, stable=False)
-    with pytest.raises(NotImplementedError):
-        P.generate_kpts_single(x, 1, use_nms="softnms", thr=0.5)
+    k, s = P.generate_kpts_single(x, 1, use_nms="softnms", thr=0.5)       # every pixel passes 0.5 * mean
+    assert k.shape == (1, 900, 2)
     with pytest.raises(Exception):
         P.generate_kpts_single(torch.ones(1, 1, 8, 8, device="cuda"), 1)   # 128 > 36 interior pixels
     # cpu tensors are accepted and results come back on the cpu

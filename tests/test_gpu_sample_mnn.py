@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from _checks import assert_close_vec, check_mnn_near_tie
+from _checks import assert_close_vec, check_mnn_near_tie, check_ratio_near_tie
 from oracle import posfeat_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -165,3 +165,52 @@ def test_mnn_host_entry_and_errors():
     wide[:, :128] = v
     assert wide[:, :128].stride(0) == 256
     np.testing.assert_array_equal(P.mnn_matcher(wide[:, :128], v), P.mnn_matcher(v, v))
+
+
+def test_ratio_matchers_golden(golden):
+    """ratio_matcher / mutual_nn_ratio_matcher against outputs of the reference functions
+    (evaluations/aachen/matchers.py:17-75) stored by oracle/make_golden.py."""
+    from posfeat_b200.matchers import mutual_nn_ratio_matcher, ratio_matcher
+    g = golden("mnn")
+    a, b = torch.from_numpy(g["a"]).cuda(), torch.from_numpy(g["b"]).cuda()
+    got = ratio_matcher(a, b, ratio=0.95)
+    assert got.dtype == np.int64 and got.shape[1] == 2
+    check_ratio_near_tie(g["a"], g["b"], got, g["ratio"], 0.95, False)
+    got = mutual_nn_ratio_matcher(a, b, ratio=0.9)
+    check_ratio_near_tie(g["a"], g["b"], got, g["mutual_ratio"], 0.9, True)
+
+
+def ratio_pair(N, M, D):
+    """b = copies of rows of a under per-row noise levels (Lowe ratios spread over
+    roughly 0.3..1), scattered among distractors when M > N."""
+    g = torch.Generator().manual_seed(42)
+    a = unit_desc(N, D, 41)
+    k = min(N, M)
+    lvl = (0.05 + 0.2 * torch.rand(k, 1, generator=g)) * (128.0 / D) ** 0.5
+    b = a[torch.randperm(N, generator=g)[:k]] + lvl * torch.randn(k, D, generator=g)
+    if M > k:
+        b = torch.cat([b, torch.randn(M - k, D, generator=g)])[torch.randperm(M, generator=g)]
+    return a, torch.nn.functional.normalize(b, dim=1)
+
+
+@pytest.mark.parametrize("mutual", [False, True])
+@pytest.mark.parametrize("N,M,D,ratio", [(1500, 1300, 128, 0.9), (777, 2049, 128, 0.75), (2, 2, 16, 0.95),
+                                         (300, 5000, 64, 0.8), (4096, 4096, 128, 0.95)])
+def test_ratio_matchers_vs_oracle(mutual, N, M, D, ratio):
+    from posfeat_b200.matchers import mutual_nn_ratio_matcher, ratio_matcher
+    a, b = ratio_pair(N, M, D)
+    want = O.ratio_matchers(a.numpy(), b.numpy(), ratio=ratio, mutual=mutual, exact=True)
+    fn = mutual_nn_ratio_matcher if mutual else ratio_matcher
+    got = fn(a.cuda(), b.cuda(), ratio=ratio)
+    amb = check_ratio_near_tie(a.numpy(), b.numpy(), got, want, ratio, mutual)
+    assert amb < max(4, N // 50)                      # the check is not vacuous
+    if N > 100:
+        assert len(want) > 0
+
+
+def test_ratio_matchers_errors():
+    from posfeat_b200.matchers import ratio_matcher
+    with pytest.raises(RuntimeError):                  # torch.topk(sim, 2) raises on a single column
+        ratio_matcher(torch.zeros(5, 128, device="cuda"), torch.zeros(1, 128, device="cuda"))
+    with pytest.raises(ValueError):
+        ratio_matcher(torch.zeros(5, 128, device="cuda"), torch.zeros(5, 64, device="cuda"))

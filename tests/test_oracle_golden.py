@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import posfeat_oracle as O
-from _checks import check_detect
+from _checks import check_detect, check_detect_float_key
 
 DETECT_CASES = ["r1_abs", "r3_abs", "r2_max", "r1_mean", "r1_nothr", "nonms_abs",
                 "ties_r1", "ties_r2", "few", "const", "odd_r1", "odd_r5"]
@@ -30,6 +30,22 @@ def test_detect(golden, name):
             np.testing.assert_array_equal(keep, g[name + "/nms_mask"][b, 0] > 0)
     kps, sc, idx, counts = O.generate_kpts_single(m, return_idx=True, **cfg)
     check_detect_against(g, name, kps, sc, idx, counts)
+
+
+EXT_CASES = ["soft_r1_mean", "soft_r2_abs", "soft_r4_max", "noavg_r1", "noavg_r2_mean", "noavg_r5_max",
+             "noavg_nonms", "noavg_soft"]
+
+
+@pytest.mark.parametrize("name", EXT_CASES)
+def test_detect_ext(golden, name):
+    """soft NMS and generate_kpts_single_noavg against the reference's outputs."""
+    g = golden("detect_ext")
+    cfg = _cfg(g, name)
+    fn = O.generate_kpts_single_noavg if name.startswith("noavg") else O.generate_kpts_single
+    kps, sc, idx, counts = fn(g[name + "/map"], return_idx=True, **cfg)
+    chk = check_detect_float_key if cfg.get("use_nms", True) == "softnms" else check_detect
+    chk(g[name + "/key"], g[name + "/idx"], g[name + "/kps"], g[name + "/score"], g[name + "/count"],
+        kps, sc, idx, counts)
 
 
 def test_linspace_matches_torch():
