@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 comparison leg")
     ap.add_argument("--fmap-layout", default="channels_last", choices=["channels_last", "nchw"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -254,6 +255,18 @@ def main():
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- the same pipeline in stock PyTorch ops on this GPU (rank 0, bounded sample; not part of `value`) ----
+    eager = None
+    if rank == 0 and not args.no_eager:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import torch_eager_pipeline as tep
+        n_eager = min(P, 8)
+        ev, (eidx, ematch) = tep.time_pairs(score, fmap, DET_CFG, n_eager)
+        k0 = int(nm[0].item())
+        eager = {"value": ev, "unit": "pairs/s", "sample": f"{n_eager} pairs of the same workload, device-resident, fp32 matmul",
+                 "keypoint_idx_equal_pair0": bool(torch.equal(eidx, feats["idx"][:2, :eidx.shape[1]])),
+                 "matches_differing_pair0": len({tuple(x) for x in ematch.tolist()} ^
+                                                {tuple(x) for x in matches[0, :k0].tolist()})}
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -291,7 +304,7 @@ def main():
             extra["nms_hbm"] = {"bound": "hbm", "kernel": "nms_candidates_kernel", "achieved": gbs, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": gbs / pk["hbm"], "algorithmic_bytes_per_launch": nbytes}
         mnn_ms = sum(kern.get(k, {}).get("ms_per_launch", 0) * kern.get(k, {}).get("launches_per_step", 0)
-                     for k in ("mnn_prep", "mnn_tc", "mnn_rescore", "mnn_compact")) / max(P, 1)
+                     for k in ("mnn_prep", "mnn_tc", "mnn_rescore", "mnn_scan", "mnn_verify", "mnn_compact")) / max(P, 1)
         if mnn_ms:
             f1 = 2.0 * n_kp * n_kp * D
             extra["mnn_total"] = {"ms_per_pair": mnn_ms, "achieved_tflops": f1 / (mnn_ms * 1e-3) / 1e12,
@@ -324,7 +337,7 @@ def main():
                        "h2d_bytes_per_step": PairPipeline.h2d_bytes(score, fmap),
                        "d2h_bytes_per_step": PairPipeline.d2h_bytes(2 * P, int(n_kp), P)},
                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-               "kernels": kern, "extra_rooflines": extra}
+               "torch_eager_b200": eager, "kernels": kern, "extra_rooflines": extra}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

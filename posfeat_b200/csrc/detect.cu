@@ -30,8 +30,10 @@ constexpr int kDigitBits = 11;   // radix-select digit width (2048-bin shared hi
 constexpr int kBucketMax = 1024;  // boundary bucket small enough to be sorted on its own
 constexpr int kUnroll = 8;       // independent candidate loads in flight per thread
 
+constexpr int kCntStride = 32;   // int32 slots between the per-image candidate counters
 struct DetectWs {
-  int32_t* cand_count;   // [B] positive-score survivors written to cand
+  int32_t* cand_count;   // [B * kCntStride] positive-score survivors written to cand (one 128-byte line per image:
+                         // same-line atomics serialise in the L2 atomic unit)
   float* thr_val;        // [B]
   double* red_sum;       // [B]
   unsigned* red_max;     // [B] order-preserving uint of the max
@@ -58,7 +60,7 @@ static DetectWs carve(void* base, int B, int H, int W, int cap_pts) {
     off += align_up(bytes, 256);
     return r;
   };
-  w.cand_count = (int32_t*)take(sizeof(int32_t) * B);
+  w.cand_count = (int32_t*)take(sizeof(int32_t) * B * kCntStride);
   w.thr_val = (float*)take(sizeof(float) * B);
   w.red_sum = (double*)take(sizeof(double) * B);
   w.red_max = (unsigned*)take(sizeof(unsigned) * B);
@@ -212,7 +214,7 @@ nms_candidates_kernel(const float* __restrict__ score, int H, int W, int64_t sb,
   if (lane == 0 && n_all) atomicAdd(&s_nall, n_all);
   __syncthreads();
   if (threadIdx.x == 0) {
-    s_base = s_n ? atomicAdd(cand_count + b, s_n) : 0;
+    s_base = s_n ? atomicAdd(cand_count + b * kCntStride, s_n) : 0;
     if (s_nall) atomicAdd(counts + b, s_nall);
   }
   __syncthreads();
@@ -320,7 +322,7 @@ nms_strip_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int6
   __syncwarp();
   int base = 0;
   if (lane == 0) {
-    if (cnt) base = atomicAdd(cand_count + b, cnt);
+    if (cnt) base = atomicAdd(cand_count + b * kCntStride, cnt);
     if (n_all) atomicAdd(counts + b, n_all);
   }
   base = __shfl_sync(kFull, base, 0);
@@ -425,12 +427,189 @@ nms_strip2_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, 
   n_all += total;
   int base = 0;
   if (lane == 0) {
-    if (total) base = atomicAdd(cand_count + b, total);
+    if (total) base = atomicAdd(cand_count + b * kCntStride, total);
     if (n_all) atomicAdd(counts + b, n_all);
   }
   base = __shfl_sync(kFull, base, 0) + inc - cnt;
   u64* dst = cand + (int64_t)b * cand_cap + base;
   for (int i = 0; i < cnt; ++i) dst[i] = mine[i * 32];
+}
+
+// Radius-1 fast path, second generation: FOUR pixels per lane, survivors kept as a bit mask.
+// A warp task covers 128 map columns [S, S+128) (S = 124 * column-warp) and evaluates the 124
+// columns S+1 .. S+124 over kQuadRows centre rows.  Per row and lane: one 128-bit load (kVec) or
+// four clamped scalar loads, two shuffles, four 3-input maxima for the horizontal window, and per
+// pixel   keep <=> c > max3(above, left, thr)  &&  c >= max(right, below)   (scan-order tie rule).
+// The keep bits of an 8-row batch fill one 32-bit register per lane (bit 4k+j = row k, pixel j);
+// after the batch the warp scans the bit counts, takes ONE global atomic, and every lane appends
+// its survivors (score re-read through L1).  No shared memory, no per-row stores.
+// The reflect-101 border of the interior grid is applied when the row / column is fetched:
+// interior column -1 is map column 0 -> map column 2, interior column wi is map column W-1 ->
+// map column W-3, and the same for rows.
+constexpr int kQuadRows = 32;
+constexpr int kQuadBatch = 8;
+constexpr int kQuadCols = 124;
+constexpr int kQuadWarps = 8;
+
+template <bool kVec, bool kPosThr>
+__global__ void __launch_bounds__(kQuadWarps * 32, 4)
+nms_quad_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int64_t sy, int has_thr,
+                   const float* __restrict__ thr_val, int32_t* __restrict__ counts,
+                   int32_t* __restrict__ cand_count, u64* __restrict__ cand, int64_t cand_cap, int ncw,
+                   int ntasks) {
+  constexpr unsigned kFull = 0xffffffffu;
+  // image index varies fastest over the grid: CTAs running at the same time append to different
+  // candidate lists, so their atomics do not queue on one address
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int task = blockIdx.y * kQuadWarps + warp;
+  if (task >= ntasks) return;
+  const int cw = task % ncw, strip = task / ncw;
+  const int hi = H - 2, wi = W - 2;
+  const int x0 = cw * kQuadCols + 4 * lane;              // map column of this lane's pixel 0
+  const int y0 = strip * kQuadRows, y1 = min(hi, y0 + kQuadRows);
+  const float* img = score + b * sb;
+  const float tv = has_thr ? thr_val[b] : -INFINITY;
+
+  // column addressing, fixed for the whole strip
+  const float* colp;                                     // kVec: 16-byte aligned base of the lane's quad
+  int co0 = 0, co1 = 0, co2 = 0, co3 = 0;                // !kVec: per-pixel (reflected, clamped) column offsets
+  bool fix_l = false, fix_r = false;
+  if (kVec) {
+    colp = img + (x0 + 3 < W ? x0 : 0);                  // lanes past the right edge read a harmless quad
+    fix_l = x0 == 0;                                     // map column 0  := map column 2
+    fix_r = x0 + 3 == W - 1;                             // map column W-1 := map column W-3 (W % 4 == 0 here)
+  } else {
+    auto col = [&](int x) { return x <= 0 ? 2 : (x >= W - 1 ? W - 3 : x); };
+    co0 = col(x0); co1 = col(x0 + 1); co2 = col(x0 + 2); co3 = col(x0 + 3);
+    colp = img;
+  }
+  auto load_at = [&](const float* rp) -> float4 {        // rp: lane base + map row offset
+    float4 v;
+    if (kVec) {
+      v = __ldg(reinterpret_cast<const float4*>(rp));
+      if (fix_l) v.x = v.z;
+      if (fix_r) v.w = v.y;
+    } else {
+      v.x = __ldg(rp + co0); v.y = __ldg(rp + co1); v.z = __ldg(rp + co2); v.w = __ldg(rp + co3);
+    }
+    return v;
+  };
+  auto load_row = [&](int yi) -> float4 {                // interior row yi in [-1, hi + 7], reflect-101 / clamped
+    const int yr = yi < 0 ? 1 : (yi < hi ? yi : max(2 * hi - 2 - yi, 0));
+    return load_at(colp + (int64_t)(yr + 1) * sy);
+  };
+  // which of the lane's four pixels are evaluated: map columns S+1 .. S+124, and <= W-2
+  unsigned colmask = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + j, rel = 4 * lane + j;
+    if (rel >= 1 && rel <= kQuadCols && x <= W - 2) colmask |= 1u << j;
+  }
+  const unsigned lanevalid = colmask * 0x11111111u;
+
+  // prologue: row above the strip and the first centre row
+  float a0, a1, a2, a3, c0, c1, c2, c3, cl, cr, h0, h1, h2, h3;
+  {
+    const float4 p = load_row(y0 - 1), q = load_row(y0);
+    float l = __shfl_up_sync(kFull, p.w, 1), r = __shfl_down_sync(kFull, p.x, 1);
+    a0 = fmaxf(fmaxf(l, p.x), p.y); a1 = fmaxf(fmaxf(p.x, p.y), p.z);
+    a2 = fmaxf(fmaxf(p.y, p.z), p.w); a3 = fmaxf(fmaxf(p.z, p.w), r);
+    cl = __shfl_up_sync(kFull, q.w, 1); cr = __shfl_down_sync(kFull, q.x, 1);
+    c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
+    h0 = fmaxf(fmaxf(cl, c0), c1); h1 = fmaxf(fmaxf(c0, c1), c2);
+    h2 = fmaxf(fmaxf(c1, c2), c3); h3 = fmaxf(fmaxf(c2, c3), cr);
+  }
+  // Rows arrive in half batches of four; two half batches fill one 32-bit survivor mask.  Few
+  // registers per thread matter more here than deep per-warp prefetch: the kernel needs ~14
+  // instructions per pixel, so it only keeps up with HBM when many warps interleave their load
+  // and compare phases (measured: 24 warps with register double buffering were slower).
+  constexpr int kHalf = kQuadBatch / 2;
+  auto load_half = [&](float4 (&buf)[kHalf], int yfirst) {       // new rows yfirst .. yfirst+3 (interior index)
+    if (yfirst + kHalf - 1 < hi) {                               // warp uniform: all of them are interior rows
+      const float* rp = colp + (int64_t)(yfirst + 1) * sy;
+#pragma unroll
+      for (int k = 0; k < kHalf; ++k) buf[k] = load_at(rp + k * sy);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kHalf; ++k) buf[k] = load_row(yfirst + k);
+    }
+  };
+  unsigned mask = 0, maskp = 0;
+  auto eval_half = [&](const float4 (&buf)[kHalf], int shift) {
+#pragma unroll
+    for (int k = 0; k < kHalf; ++k) {
+      const float4 n = buf[k];
+      const float l = __shfl_up_sync(kFull, n.w, 1), r = __shfl_down_sync(kFull, n.x, 1);
+      const float n0 = fmaxf(fmaxf(l, n.x), n.y), n1 = fmaxf(fmaxf(n.x, n.y), n.z);
+      const float n2 = fmaxf(fmaxf(n.y, n.z), n.w), n3 = fmaxf(fmaxf(n.z, n.w), r);
+      const bool k0 = c0 > fmaxf(fmaxf(a0, cl), tv) && c0 >= fmaxf(c1, n0);
+      const bool k1 = c1 > fmaxf(fmaxf(a1, c0), tv) && c1 >= fmaxf(c2, n1);
+      const bool k2 = c2 > fmaxf(fmaxf(a2, c1), tv) && c2 >= fmaxf(c3, n2);
+      const bool k3 = c3 > fmaxf(fmaxf(a3, c2), tv) && c3 >= fmaxf(cr, n3);
+      const int sh = shift + 4 * k;
+      if (k0) mask |= 1u << sh;
+      if (k1) mask |= 2u << sh;
+      if (k2) mask |= 4u << sh;
+      if (k3) mask |= 8u << sh;
+      if (!kPosThr) {
+        if (k0 && c0 > 0.f) maskp |= 1u << sh;
+        if (k1 && c1 > 0.f) maskp |= 2u << sh;
+        if (k2 && c2 > 0.f) maskp |= 4u << sh;
+        if (k3 && c3 > 0.f) maskp |= 8u << sh;
+      }
+      a0 = h0; a1 = h1; a2 = h2; a3 = h3;
+      c0 = n.x; c1 = n.y; c2 = n.z; c3 = n.w; cl = l; cr = r;
+      h0 = n0; h1 = n1; h2 = n2; h3 = n3;
+    }
+  };
+  const int sy32 = (int)sy;                                      // host checks the row stride fits
+  int n_all = 0;
+  float4 A[kHalf];
+#pragma unroll 1
+  for (int yb = y0; yb < y1; yb += kQuadBatch) {         // centre rows yb .. yb+7, new rows yb+1 .. yb+8
+    mask = 0; maskp = 0;
+    load_half(A, yb + 1);
+    eval_half(A, 0);
+    load_half(A, yb + 1 + kHalf);
+    eval_half(A, 4 * kHalf);
+    const int vr = y1 - yb;                              // centre rows of this group inside the strip
+    const unsigned valid = lanevalid & (vr >= kQuadBatch ? kFull : ((1u << (4 * vr)) - 1u));
+    mask &= valid;
+    unsigned emit = kPosThr ? mask : (maskp & valid);
+    n_all += __popc(mask);
+    const int cnt = __popc(emit);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(kFull, inc, 31);
+    int base = 0;
+    if (total && lane == 31) base = atomicAdd(cand_count + b * kCntStride, total);
+    if (total) {                                         // warp uniform
+      base = __shfl_sync(kFull, base, 31);
+      u64* dst = cand + (int64_t)b * cand_cap + base + inc - cnt;
+      const float* vbase = img + (int64_t)(yb + 1) * sy + x0;
+      const unsigned ibase = 0xffffffffu - ((unsigned)yb * (unsigned)wi + (unsigned)(x0 - 1));
+      while (emit) {                                     // two survivors per trip: both score reads in flight together
+        const int b0 = __ffs(emit) - 1;
+        emit &= emit - 1;
+        const bool two = emit != 0;
+        const int b1 = two ? __ffs(emit) - 1 : b0;
+        emit &= emit - 1;
+        const float v0 = __ldg(vbase + ((b0 >> 2) * sy32 + (b0 & 3)));   // just streamed through L1 by this warp
+        const float v1 = __ldg(vbase + ((b1 >> 2) * sy32 + (b1 & 3)));
+        dst[0] = ((u64)__float_as_uint(v0) << 32) | (u64)(ibase - (unsigned)((b0 >> 2) * wi + (b0 & 3)));
+        if (two) dst[1] = ((u64)__float_as_uint(v1) << 32) | (u64)(ibase - (unsigned)((b1 >> 2) * wi + (b1 & 3)));
+        dst += 2;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_all += __shfl_xor_sync(kFull, n_all, o);
+  if (lane == 0 && n_all) atomicAdd(counts + b, n_all);
 }
 
 // ---- phase 2: select + sort + centroid ------------------------------------
@@ -558,7 +737,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     if (tid == 0) atomicMax(status, n > cap_pts ? 1 : 2);
     return;
   }
-  const int C = (int)min((int64_t)cand_count[b], cand_cap);
+  const int C = (int)min((int64_t)cand_count[b * kCntStride], cand_cap);
   const int n_real = min(n, C);
   const u64* keys = cand + (int64_t)b * cand_cap;
 
@@ -883,7 +1062,20 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
 #define PF_STRIP(RR)                                                                                              \
   nms_strip_kernel<RR><<<grid, kStripWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, rows, has_thr,     \
                                                                w.thr_val, counts, w.cand_count, w.cand, w.cand_cap)
-    if (r == 1) {
+    if (r == 1 && !getenv("POSFEAT_NMS_STRIP2")) {
+      const int ncw = (W - 2 + kQuadCols - 1) / kQuadCols, nstrips = (H - 2 + kQuadRows - 1) / kQuadRows;
+      const int ntasks = ncw * nstrips;
+      dim3 gq(B, (ntasks + kQuadWarps - 1) / kQuadWarps);
+      PF_CHECK_ARG(stride_y < (1 << 27), "row stride too large");
+      const bool vec = (W % 4 == 0) && (stride_y % 4 == 0) && (stride_b % 4 == 0) && (((uintptr_t)score & 15) == 0);
+      const bool pos = thr_mode == POSFEAT_THR_ABS && thr >= 0.f;
+#define PF_QUAD(V, P)                                                                                             \
+  nms_quad_r1_kernel<V, P><<<gq, kQuadWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, has_thr, w.thr_val, \
+                                                               counts, w.cand_count, w.cand, w.cand_cap, ncw, ntasks)
+      if (vec) { if (pos) PF_QUAD(true, true); else PF_QUAD(true, false); }
+      else { if (pos) PF_QUAD(false, true); else PF_QUAD(false, false); }
+#undef PF_QUAD
+    } else if (r == 1) {
       dim3 g2((W - 2 + kStripWarps * 60 - 1) / (kStripWarps * 60), (H - 2 + kStrip2Rows - 1) / kStrip2Rows, B);
       // a non-negative absolute threshold implies positive survivors (known on the host for THR_ABS)
       if (thr_mode == POSFEAT_THR_ABS && thr >= 0.f)
