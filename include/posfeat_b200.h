@@ -198,10 +198,16 @@ int posfeat_mnn_host_f32(const float* A_host, int N, const float* B_host, int M,
  * Backward: given g_out [B,n,C] produces g_q [B,n,D] and/or g_k [B,m,D] (either
  * may be NULL); the logits are recomputed from (q, k, lse); no atomics.
  * D <= 128, C <= 4.
+ * Forward: problems with m >= 128 and B*n*m >= 2^18 run on the tensor cores (tcgen05
+ * kind::tf32 with hi/lo operand splitting, float32-accurate logits) and need the
+ * workspace posfeat_corr_expect_workspace_bytes reports (256-byte aligned); smaller ones
+ * use a SIMT kernel and the workspace may be NULL (the size query returns 0).
  */
+size_t posfeat_corr_expect_workspace_bytes(int B, int n, int m, int D, int C);
 int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, int v_batched,
                                 int B, int n, int m, int D, int C, float scale,
-                                float* out, float* lse, void* stream);
+                                float* out, float* lse, void* workspace, size_t ws_bytes,
+                                void* stream);
 int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, int v_batched,
                                 int B, int n, int m, int D, int C, float scale,
                                 const float* out, const float* lse, const float* g_out,

@@ -47,7 +47,8 @@ SIGNATURES = {
     "posfeat_ratio_match_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_mnn_host_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_host_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
-    "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "posfeat_corr_expect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_corr_expect_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                          _vp]),
     "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i, _i,

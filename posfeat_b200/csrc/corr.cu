@@ -6,8 +6,8 @@
 //     out[b,i,:] = sum_j softmax_j(scale * <q_i, k_j>) * v[j,:]
 // computed flash-style: 64x64 logit tiles in registers, online softmax, the
 // [B,n,m] probability tensor is never written.  The backward pass recomputes
-// the logits from (q, k, lse) and needs no atomics (one kernel owns rows of q,
-// one owns rows of k).
+// the logits from (q, k, lse); one kernel owns rows of q, one owns rows of k (atomics
+// only when a long sweep over the other side is split across CTAs to fill the chip).
 //
 // Window / line variant (get_expected_correspondence_within_window,
 // losses/preprocess_utils.py:721-758; the sampling half of epipolar_line_search,
@@ -15,9 +15,19 @@
 // between two endpoints) are bilinearly gathered on the fly from the feature
 // map, dotted with the query and soft-maxed; the [B,n,m,D] gathered tensor of
 // the reference (943 MB at B=8, n=1200) is never materialised.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace posfeat {
+
+// tensor-core forward path (corr_tc.cu)
+bool corr_tc_eligible(int B, int n, int m, int D, int C);
+size_t corr_tc_workspace_bytes(int B, int n, int m, int D, int C);
+int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, int B, int n, int m, int D, int C,
+                float scale, float* out, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 constexpr int kCT = 64;          // logit tile edge
 constexpr int kCDmax = 128;      // descriptor length supported by the dense kernels
@@ -136,7 +146,8 @@ template <bool kXisQ>
 __global__ void __launch_bounds__(256)
 corr_expect_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                        int v_batched, int n, int m, int D, int C, float scale, const float* __restrict__ out,
-                       const float* __restrict__ lse, const float* __restrict__ g_out, float* __restrict__ gX) {
+                       const float* __restrict__ lse, const float* __restrict__ g_out, float* __restrict__ gX,
+                       int ytiles_per_split) {
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;                        // [kCDmax][kCT+4]  (k-major)
   float* Ys = Xs + kCDmax * (kCT + 4);     // [kCT][kCDmax+4]  (row-major: second GEMM reads rows)
@@ -187,7 +198,10 @@ corr_expect_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int y0 = 0; y0 < nY; y0 += kCT) {
+  // the Y sweep may be split over blockIdx.z (few X tiles, long Y): partial sums are then added atomically
+  const int ybeg = blockIdx.z * ytiles_per_split * kCT;
+  const int yend = min(nY, ybeg + ytiles_per_split * kCT);
+  for (int y0 = ybeg; y0 < yend; y0 += kCT) {
     __syncthreads();
     // Y tile row-major (for W*Y) ...
     for (int e = tid; e < kCT * kCDmax; e += 256) {
@@ -257,7 +271,10 @@ corr_expect_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = tx * 8 + j;
-        if (c < D) gXb[(size_t)r * D + c] = acc[i][j] * scale;
+        if (c < D) {
+          if (gridDim.z == 1) gXb[(size_t)r * D + c] = acc[i][j] * scale;
+          else atomicAdd(gXb + (size_t)r * D + c, acc[i][j] * scale);
+        }
       }
   }
 }
@@ -489,11 +506,19 @@ static int check_dense(const void* q, const void* k, const void* v, int B, int n
   return 0;
 }
 
+extern "C" size_t posfeat_corr_expect_workspace_bytes(int B, int n, int m, int D, int C) {
+  if (B < 1 || n < 1 || m < 1) return 0;
+  return corr_tc_workspace_bytes(B, n, m, D, C);
+}
+
 extern "C" int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, int v_batched, int B, int n,
-                                           int m, int D, int C, float scale, float* out, float* lse, void* stream_) {
+                                           int m, int D, int C, float scale, float* out, float* lse, void* workspace,
+                                           size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_dense(q, k, v, B, n, m, D, C)) return e;
   PF_CHECK_ARG(out && lse, "NULL output pointer");
+  if (corr_tc_eligible(B, n, m, D, C) && !getenv("POSFEAT_CORR_SIMT"))
+    return corr_tc_fwd(q, k, v, v_batched, B, n, m, D, C, scale, out, lse, workspace, ws_bytes, stream);
   dim3 grid((n + kCT - 1) / kCT, B);
   ProfScope prof(PROF_CORR_FWD, stream);
   corr_expect_fwd_kernel<<<grid, 256, 0, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse);
@@ -511,16 +536,22 @@ extern "C" int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const
   PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_CORR_BWD, stream);
-  if (g_q) {
-    dim3 grid((n + kCT - 1) / kCT, B);
-    corr_expect_bwd_kernel<true><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, g_q);
-    PF_LAUNCH_CHECK("corr_expect_bwd_kernel<q>");
-  }
-  if (g_k) {
-    dim3 grid((m + kCT - 1) / kCT, B);
-    corr_expect_bwd_kernel<false><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, g_k);
-    PF_LAUNCH_CHECK("corr_expect_bwd_kernel<k>");
-  }
+  // rows of X are owned by a CTA; when there are too few X tiles to fill the chip the Y sweep is split as well
+  auto launch = [&](bool x_is_q, float* gX) -> int {
+    const int nX = x_is_q ? n : m, nY = x_is_q ? m : n;
+    const int xt = (nX + kCT - 1) / kCT, yt = (nY + kCT - 1) / kCT;
+    int splits = std::max(1, std::min(yt, (4 * 148 + xt * B - 1) / (xt * B)));
+    const int tps = (yt + splits - 1) / splits;
+    splits = (yt + tps - 1) / tps;
+    if (splits > 1) PF_CUDA(cudaMemsetAsync(gX, 0, sizeof(float) * (size_t)B * nX * D, stream));
+    dim3 grid(xt, B, splits);
+    if (x_is_q) corr_expect_bwd_kernel<true><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, gX, tps);
+    else corr_expect_bwd_kernel<false><<<grid, 256, smem, stream>>>(q, k, v, v_batched, n, m, D, C, scale, out, lse, g_out, gX, tps);
+    PF_LAUNCH_CHECK("corr_expect_bwd_kernel");
+    return POSFEAT_OK;
+  };
+  if (g_q) if (int e = launch(true, g_q)) return e;
+  if (g_k) if (int e = launch(false, g_k)) return e;
   return POSFEAT_OK;
 }
 

@@ -330,112 +330,8 @@ nms_strip_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int6
   for (int i = lane; i < cnt; i += 32) dst[i] = s_list[warp][i];
 }
 
-// Radius-1 specialisation (the HPatches / training configuration): two pixels per lane.
-// Lane l owns interior columns (xs + 2l - 2, xs + 2l - 1); lanes 0 and 31 are halo lanes, so a
-// warp covers 60 columns per row with two loads and two shuffles.  Survivors go to a PRIVATE
-// per-lane stack in shared memory (two horizontally or vertically adjacent pixels cannot both
-// survive, so a lane keeps at most rows/2 of them): no ballots, no atomics in the row loop;
-// one warp scan and one global atomic per strip at the end.
-constexpr int kStrip2Rows = 32;
-constexpr int kStrip2Cap = kStrip2Rows / 2;       // survivors per lane per strip
-template <bool kPosThr>   // kPosThr: a non-negative threshold is active, so every survivor has a positive score
-__global__ void __launch_bounds__(kStripWarps * 32)
-nms_strip2_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int64_t sy, int has_thr,
-                     const float* __restrict__ thr_val, int32_t* __restrict__ counts,
-                     int32_t* __restrict__ cand_count, u64* __restrict__ cand, int64_t cand_cap) {
-  __shared__ u64 s_list[kStripWarps][kStrip2Cap][32];     // [slot][lane]: conflict-free 8-byte stores
-  constexpr unsigned kFull = 0xffffffffu;
-  const int b = blockIdx.z;
-  const int hi = H - 2, wi = W - 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int xs = (blockIdx.x * kStripWarps + warp) * 60;
-  if (xs >= wi) return;
-  const int xa = xs + 2 * lane - 2, xb = xa + 1;
-  const int y0 = blockIdx.y * kStrip2Rows;
-  const int y1 = min(hi, y0 + kStrip2Rows);
-  // per-lane column pointers (always in bounds: loads are unconditional, masking happens afterwards)
-  const char* pla = reinterpret_cast<const char*>(score + b * sb + 1 + reflect_idx(min(max(xa, -1), wi), wi));
-  const char* plb = reinterpret_cast<const char*>(score + b * sb + 1 + reflect_idx(min(max(xb, -1), wi), wi));
-  asm volatile("" : "+l"(pla), "+l"(plb));       // keep the per-lane bases as finished 64-bit values
-  const int64_t syb = sy * 4;
-  const bool ea = lane >= 1 && lane <= 30 && xa < wi, eb = lane >= 1 && lane <= 30 && xb < wi;
-  // threshold folded into the comparison chain
-  const float tv = has_thr ? thr_val[b] : -INFINITY;
-  const unsigned lo_a = 0xffffffffu - (unsigned)xa, lo_b = 0xffffffffu - (unsigned)xb;
-
-  float above_a = -INFINITY, above_b = -INFINITY;       // window max of the row above the centre row
-  float ca = -INFINITY, cb = -INFINITY, cl = -INFINITY, cr = -INFINITY, hma = -INFINITY, hmb = -INFINITY;  // centre row
-  int n_neg = 0;                                        // survivors that are not emitted (score <= 0)
-  u64* mine = &s_list[warp][0][lane];
-  const unsigned wptr0 = (unsigned)__cvta_generic_to_shared(mine);
-  unsigned wptr = wptr0;                                // private stack pointer (slot stride = 32 lanes * 8 B)
-  constexpr int kBatch = 8;
-#pragma unroll 1
-  for (int yb = y0 - 1; yb < y1 + 1; yb += kBatch) {
-    float ina[kBatch], inb[kBatch];
-#pragma unroll
-    for (int k = 0; k < kBatch; ++k) {
-      const int yy = yb + k;
-      const int yr = yy < 0 ? 1 : (yy >= hi ? hi - 2 : yy);        // reflect-101 for radius 1 (warp uniform)
-      const int64_t ro = (int64_t)(yr + 1) * syb;                  // warp-uniform row offset in bytes
-      // No masking: every load is in bounds (clamped row / column), and a value loaded for a
-      // position outside the reflect-padded extent can only reach pixels that are not evaluated
-      // (halo lanes beyond the right edge, centre rows >= y1).
-      ina[k] = __ldg(reinterpret_cast<const float*>(pla + ro));
-      inb[k] = __ldg(reinterpret_cast<const float*>(plb + ro));
-    }
-#pragma unroll
-    for (int k = 0; k < kBatch; ++k) {
-      const int yc = yb + k - 1;                         // centre row evaluated now
-      const float a = ina[k], bq = inb[k];
-      const float l = __shfl_up_sync(kFull, bq, 1), r = __shfl_down_sync(kFull, a, 1);
-      const float na = fmaxf(fmaxf(l, a), bq), nb = fmaxf(fmaxf(a, bq), r);   // window max of the new row
-      const bool row_eval = yc >= y0 && yc < y1;
-      const bool ka = ea && row_eval && ca > above_a && ca > cl && ca >= cb && ca >= na && ca > tv;
-      const bool kb = eb && row_eval && cb > above_b && cb > ca && cb >= cr && cb >= nb && cb > tv;
-      const unsigned rowlo = (unsigned)yc * (unsigned)wi;
-      if (kPosThr) {
-        // branch-free: predicated store + pointer bump
-        if (ka) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wptr), "r"(lo_a - rowlo), "r"(__float_as_uint(ca)) : "memory"); wptr += 256; }
-        if (kb) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wptr), "r"(lo_b - rowlo), "r"(__float_as_uint(cb)) : "memory"); wptr += 256; }
-      } else {
-        if (ka) {
-          if (ca > 0.f) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wptr), "r"(lo_a - rowlo), "r"(__float_as_uint(ca)) : "memory"); wptr += 256; }
-          else ++n_neg;
-        }
-        if (kb) {
-          if (cb > 0.f) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wptr), "r"(lo_b - rowlo), "r"(__float_as_uint(cb)) : "memory"); wptr += 256; }
-          else ++n_neg;
-        }
-      }
-      above_a = hma; above_b = hmb;
-      ca = a; cb = bq; cl = l; cr = r; hma = na; hmb = nb;
-    }
-  }
-  // compact the private stacks: exclusive warp scan of the per-lane counts
-  const int cnt = (int)((wptr - wptr0) >> 8);
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const int total = __shfl_sync(kFull, inc, 31);
-  int n_all = n_neg;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_all += __shfl_xor_sync(kFull, n_all, o);
-  n_all += total;
-  int base = 0;
-  if (lane == 0) {
-    if (total) base = atomicAdd(cand_count + b * kCntStride, total);
-    if (n_all) atomicAdd(counts + b, n_all);
-  }
-  base = __shfl_sync(kFull, base, 0) + inc - cnt;
-  u64* dst = cand + (int64_t)b * cand_cap + base;
-  for (int i = 0; i < cnt; ++i) dst[i] = mine[i * 32];
-}
-
-// Radius-1 fast path, second generation: FOUR pixels per lane, survivors kept as a bit mask.
+// Radius-1 fast path (the HPatches / training configuration): FOUR pixels per lane, survivors kept
+// as a bit mask.
 // A warp task covers 128 map columns [S, S+128) (S = 124 * column-warp) and evaluates the 124
 // columns S+1 .. S+124 over kQuadRows centre rows.  Per row and lane: one 128-bit load (kVec) or
 // four clamped scalar loads, two shuffles, four 3-input maxima for the horizontal window, and per
@@ -1062,7 +958,7 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
 #define PF_STRIP(RR)                                                                                              \
   nms_strip_kernel<RR><<<grid, kStripWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, rows, has_thr,     \
                                                                w.thr_val, counts, w.cand_count, w.cand, w.cand_cap)
-    if (r == 1 && !getenv("POSFEAT_NMS_STRIP2")) {
+    if (r == 1) {
       const int ncw = (W - 2 + kQuadCols - 1) / kQuadCols, nstrips = (H - 2 + kQuadRows - 1) / kQuadRows;
       const int ntasks = ncw * nstrips;
       dim3 gq(B, (ntasks + kQuadWarps - 1) / kQuadWarps);
@@ -1075,15 +971,6 @@ extern "C" int posfeat_detect_candidates_f32(const float* score, int B, int H, i
       if (vec) { if (pos) PF_QUAD(true, true); else PF_QUAD(true, false); }
       else { if (pos) PF_QUAD(false, true); else PF_QUAD(false, false); }
 #undef PF_QUAD
-    } else if (r == 1) {
-      dim3 g2((W - 2 + kStripWarps * 60 - 1) / (kStripWarps * 60), (H - 2 + kStrip2Rows - 1) / kStrip2Rows, B);
-      // a non-negative absolute threshold implies positive survivors (known on the host for THR_ABS)
-      if (thr_mode == POSFEAT_THR_ABS && thr >= 0.f)
-        nms_strip2_r1_kernel<true><<<g2, kStripWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, has_thr, w.thr_val,
-                                                                        counts, w.cand_count, w.cand, w.cand_cap);
-      else
-        nms_strip2_r1_kernel<false><<<g2, kStripWarps * 32, 0, stream>>>(score, H, W, stride_b, stride_y, has_thr, w.thr_val,
-                                                                         counts, w.cand_count, w.cand, w.cand_cap);
     } else if (r == 0) PF_STRIP(0);
     else if (r == 2) PF_STRIP(2);
     else PF_STRIP(3);

@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "mnn_common.cuh"
+#include "tc_common.cuh"
 
 namespace posfeat {
 
@@ -97,74 +98,6 @@ __device__ __forceinline__ float row_delta(const DirParams& d, int pair, int row
 }
 
 // ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hang.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const unsigned long long t0 = globaltimer_ns();
-  unsigned spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      printf("posfeat mnn_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // ---- CTA-pair (cta_group::2) variants
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -202,16 +135,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       ::"r"(bar), "r"(rank) : "memory");
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
-  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
-  return d;
-}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=256 (CTA pair), N=256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kYRows >> 3) << 17) | ((256u >> 4) << 24);
 
@@ -720,6 +643,7 @@ struct ScanArgs {
   int* comp_cnt;          // [pairs][nchunks]
   int* comp;              // [pairs][nchunks][kCompCap]
   int nchunks;
+  int rows_per_block;
 };
 
 // grid (row blocks, pairs); every thread compares 8 table entries (one uint4) with the 8
@@ -739,16 +663,28 @@ tc_scan_kernel(const ScanArgs a) {
     s_thr[c] = __float2half_rd(t);
   }
   __syncthreads();
-  const int rows_per_block = 64;
+  // the block's rows x vectors form one flat index space, four independent loads per thread in flight
+  const int rows_per_block = a.rows_per_block;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(d.NX, row0 + rows_per_block);
+  const int items = (row1 - row0) * nvec;
   const uint4* thr4 = reinterpret_cast<const uint4*>(s_thr);
-  for (int row = row0; row < row1; ++row) {
-    const uint4* trow = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row) * pitch);
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-      const uint4 u = __ldg(trow + v);
-      const uint4 th = thr4[v];
-      const unsigned wu[4] = {u.x, u.y, u.z, u.w}, wt[4] = {th.x, th.y, th.z, th.w};
+  const uint4* tbase = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row0) * pitch);
+  constexpr int kU = 4;
+  for (int base = threadIdx.x; base < items; base += kU * blockDim.x) {
+    uint4 u[kU];
+    int rr[kU], vv[kU];
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      const int it = base + q * blockDim.x;
+      rr[q] = it / nvec;
+      vv[q] = it - rr[q] * nvec;
+      u[q] = it < items ? __ldg(tbase + (size_t)rr[q] * nvec + vv[q]) : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+    }
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      const uint4 th = thr4[vv[q]];
+      const unsigned wu[4] = {u[q].x, u[q].y, u[q].z, u[q].w}, wt[4] = {th.x, th.y, th.z, th.w};
       unsigned mask = 0;
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
@@ -760,10 +696,10 @@ tc_scan_kernel(const ScanArgs a) {
       while (mask) {
         const int h = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int c = v * 8 + h;
+        const int c = vv[q] * 8 + h;
         const size_t slot = (size_t)pair * a.nchunks + c;
         const int pos = atomicAdd(a.comp_cnt + slot, 1);
-        if (pos < kCompCap) a.comp[slot * kCompCap + pos] = row;
+        if (pos < kCompCap) a.comp[slot * kCompCap + pos] = row0 + rr[q];
       }
     }
   }
@@ -1043,22 +979,6 @@ int launch_compact_flags(const int32_t* nn12, const unsigned char* flags, int P,
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 static int make_map(CUtensorMap* map, void* base, int rows_pad) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(POSFEAT_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -1224,9 +1144,12 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     if (nn21 == nullptr) return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher supports M <= %d", kVerMaxChunks * kChunk);
     return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);
   }
-  ScanArgs sa{p.d[0], w.tmin, w.comp_cnt, w.comp, nchunks};
+  // enough CTAs to fill the chip also when a single small pair is matched
+  int scan_rows = 64;
+  while (scan_rows > 4 && (int64_t)((N + scan_rows - 1) / scan_rows) * P < 2 * 148) scan_rows >>= 1;
+  ScanArgs sa{p.d[0], w.tmin, w.comp_cnt, w.comp, nchunks, scan_rows};
   prof_begin(PROF_MNN_SCAN, stream);
-  tc_scan_kernel<<<dim3((N + 63) / 64, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
+  tc_scan_kernel<<<dim3((N + scan_rows - 1) / scan_rows, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
   prof_end(PROF_MNN_SCAN, stream);
   PF_LAUNCH_CHECK("tc_scan_kernel");
   VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.mutual, nchunks};

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ._runtime import check, lib, ptr, require_cuda, stream_ptr
+from ._runtime import check, lib, ptr, require_cuda, stream_ptr, workspace
 from .preprocess_utils import denormalize_coords, normalize_coords, sample_l2norm
 
 
@@ -28,6 +28,20 @@ def gen_grid(h_min, h_max, w_min, w_max, len_h, len_w):
     xs = torch.linspace(w_min, w_max, len_w)
     ys = torch.linspace(h_min, h_max, len_h)
     return torch.stack((xs[None, :].expand(len_h, len_w), ys[:, None].expand(len_h, len_w)), -1).reshape(-1, 2).float()
+
+
+_grid_cache = {}
+
+
+def _device_grid(h, w, device):
+    """[-1, 1] node grid of an h x w map on `device`, built once (the reference rebuilds it on the host
+    and copies it on every call, losses/preprocess_utils.py:58-60)."""
+    key = (h, w, str(device))
+    g = _grid_cache.get(key)
+    if g is None:
+        g = gen_grid(-1, 1, -1, 1, h, w).to(device)
+        g = _grid_cache[key] = (g, torch.cat([g, g ** 2], -1).contiguous())
+    return g
 
 
 def homogenize(coord):
@@ -85,9 +99,11 @@ class CorrExpect(torch.autograd.Function):
         out = torch.empty((B, n, C), dtype=torch.float32, device=qd.device)
         lse = torch.empty((B, n), dtype=torch.float32, device=qd.device)
         with torch.cuda.device(qd.device):
+            nbytes = lib().posfeat_corr_expect_workspace_bytes(B, n, m, D, C)
+            ws = workspace("corr", nbytes, qd.device) if nbytes else None
             check(lib().posfeat_corr_expect_fwd_f32(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), v_batched, B, n, m, D,
-                                                    C, float(scale), out.data_ptr(), lse.data_ptr(),
-                                                    stream_ptr(qd.device)))
+                                                    C, float(scale), out.data_ptr(), lse.data_ptr(), ptr(ws),
+                                                    ws.numel() if ws is not None else 0, stream_ptr(qd.device)))
         ctx.save_for_backward(qd, kd, vd, out, lse)
         ctx.scale = float(scale)
         return out
@@ -117,9 +133,8 @@ def get_expected_correspondence_locs(feat1, featmap2, with_std=False):
     """losses/preprocess_utils.py:55-82.  feat1 [B,n,d], featmap2 [B,d,h,w] ->
     expected normalised xy [B,n,2]; with_std: (xy, std [B,n], kurtosis [B,n], prob [B,n,hw])."""
     B, d, h2, w2 = featmap2.shape
-    grid = gen_grid(-1, 1, -1, 1, h2, w2).to(featmap2.device)            # [hw, 2]
+    grid, table = _device_grid(h2, w2, featmap2.device)                   # [hw, 2]; x, y, x^2, y^2
     keys = featmap2.reshape(B, d, h2 * w2).transpose(1, 2)                # [B, hw, d]
-    table = torch.cat([grid, grid ** 2], -1)                              # x, y, x^2, y^2
     out = corr_expect(feat1, keys, table, 1.0)
     exp_xy = out[..., :2]
     if not with_std:
@@ -142,8 +157,14 @@ class WindowExpect(torch.autograd.Function):
         fd = fmap.detach()
         if fd.dtype != torch.float32:
             fd = fd.float()
-        if not (fd.is_contiguous() or fd.is_contiguous(memory_format=torch.channels_last)):
-            fd = fd.contiguous()          # the backward pass shares one stride set between fmap and its gradient
+        # The gather kernels read one 512-byte descriptor per tap when channels are innermost; an NCHW
+        # map would cost one 32-byte sector per channel.  One layout pass over the map (a no-op when the
+        # backbone already runs channels_last) is far cheaper than that; the gradient comes back in the
+        # same strides.
+        if fd.shape[1] >= 32:
+            fd = fd.contiguous(memory_format=torch.channels_last)
+        elif not fd.is_contiguous():
+            fd = fd.contiguous()
         B, D, h, w = fd.shape
         n, m = qd.shape[1], od.shape[0]
         dev = qd.device
@@ -224,7 +245,11 @@ def epipolar_line_search(coord, Fmat, feat1, featmap2, h, w, line_step=100, use_
     e1, e2, valid = get_endpoints(coord, Fmat, h, w)
     ends = torch.cat([e1, e2], -1).float().contiguous()                   # [B,n,4]
     qd = _f32c(feat1)
-    fd = featmap2.detach()
+    fd = featmap2.detach().float()
+    if d >= 32:
+        fd = fd.contiguous(memory_format=torch.channels_last)     # one 512-byte read per tap (see WindowExpect)
+    elif not fd.is_contiguous():
+        fd = fd.contiguous()
     dev = qd.device
     exp_soft = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
     std_soft = torch.empty((B, n), dtype=torch.float32, device=dev)
@@ -337,8 +362,9 @@ class Preprocess_Line2Window(nn.Module):
         feat1g_std = (o1[..., 2:] - feat1g_corloc_n ** 2).clamp(min=1e-6).sqrt().sum(-1)
         feat2g_std = (o2[..., 2:] - feat2g_corloc_n ** 2).clamp(min=1e-6).sqrt().sum(-1)
 
-        m2 = T * F.normalize(xf2, p=2.0, dim=1)
-        m1 = T * F.normalize(xf1, p=2.0, dim=1)
+        # channels innermost: the line and window kernels then read whole descriptors (converted once here)
+        m2 = (T * F.normalize(xf2, p=2.0, dim=1)).contiguous(memory_format=torch.channels_last)
+        m1 = (T * F.normalize(xf1, p=2.0, dim=1)).contiguous(memory_format=torch.channels_last)
         if self.config["use_line_search"]:
             j1, j2 = jitter if jitter is not None else (None, None)
             ws = self.config["window_size"]
