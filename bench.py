@@ -301,7 +301,7 @@ def main():
         if nms_ms:
             nbytes = 4.0 * 2 * P * H * W
             gbs = nbytes / (nms_ms * 1e-3) / 1e9
-            extra["nms_hbm"] = {"bound": "hbm", "kernel": "nms_candidates_kernel", "achieved": gbs, "peak": pk["hbm"],
+            extra["nms_hbm"] = {"bound": "hbm", "kernel": "nms_quad_r1_kernel", "achieved": gbs, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": gbs / pk["hbm"], "algorithmic_bytes_per_launch": nbytes}
         mnn_ms = sum(kern.get(k, {}).get("ms_per_launch", 0) * kern.get(k, {}).get("launches_per_step", 0)
                      for k in ("mnn_prep", "mnn_tc", "mnn_rescore", "mnn_scan", "mnn_verify", "mnn_compact")) / max(P, 1)

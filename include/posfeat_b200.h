@@ -145,6 +145,8 @@ int posfeat_sample_bwd_f32(const float* g_out, int B, int D, int h, int w,
  * memory.  algo: 0 = auto, 1 = exact SIMT kernel (fp64 accumulation),
  * 2 = tcgen05 tensor-core kernel (bf16 operands, candidate rescoring in fp64;
  * requires D == 128).  Both give the same nn12/nn21.
+ * nn21 may be NULL: only the match list is produced then (the tensor-core path
+ * contracts one direction and verifies mutuality per column chunk; M <= 65536).
  */
 #define POSFEAT_MNN_AUTO 0
 #define POSFEAT_MNN_SIMT 1
