@@ -199,9 +199,16 @@ extern "C" int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* 
 }
 
 // ---- ratio-test matchers (evaluations/aachen/matchers.py:17-75, ETH custom_matcher.py:16-73)
+// Same algorithm choice as the mutual-NN matcher: large D == 128 problems contract on the tensor cores
+// (both directions, top-2 rescoring), everything else on the exact SIMT kernel.
+static size_t ratio_core_bytes(int N, int M, int D) {
+  const bool tc = resolve_algo(N, M, D, POSFEAT_MNN_AUTO) == POSFEAT_MNN_TC;
+  return align_up(tc ? tc_workspace_bytes(1, N, M) : simt_workspace_bytes(N, M), 256);
+}
+
 extern "C" size_t posfeat_ratio_match_workspace_bytes(int N, int M, int D) {
   if (N < 2 || M < 2 || D < 1) return 0;
-  return simt_workspace_bytes(N, M) + align_up(sizeof(int32_t) * (size_t)M, 256) +
+  return ratio_core_bytes(N, M, D) + align_up(sizeof(int32_t) * (size_t)M, 256) +
          align_up(sizeof(float) * 2 * (size_t)N, 256) + align_up(sizeof(float) * 2 * (size_t)M, 256) +
          align_up((size_t)N, 256);
 }
@@ -213,15 +220,22 @@ extern "C" int posfeat_ratio_match_f32(const float* A, int N, int64_t lda, const
   PF_CHECK_ARG(A && Bm && nn12 && matches && n_matches && workspace, "NULL pointer");
   PF_CHECK_ARG(N >= 2 && M >= 2 && D >= 1, "the ratio test needs at least two descriptors on each side (torch.topk(2) raises otherwise)");
   PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
+  PF_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ratio workspace must be 256-byte aligned");
   const size_t need = posfeat_ratio_match_workspace_bytes(N, M, D);
   if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "ratio workspace: need %zu bytes, got %zu", need, ws_bytes);
   char* w = (char*)workspace;
-  void* simt_ws = w; w += simt_workspace_bytes(N, M);
+  const size_t core = ratio_core_bytes(N, M, D);
+  void* core_ws = w; w += core;
   int32_t* nn21 = (int32_t*)w; w += align_up(sizeof(int32_t) * (size_t)M, 256);
   float* top12 = (float*)w; w += align_up(sizeof(float) * 2 * (size_t)N, 256);
   float* top21 = (float*)w; w += align_up(sizeof(float) * 2 * (size_t)M, 256);
   unsigned char* flags = (unsigned char*)w;
-  if (int e = mnn_simt_top2(A, N, lda, Bm, M, ldb, D, nn12, nn21, top12, top21, simt_ws, stream)) return e;
+  if (resolve_algo(N, M, D, POSFEAT_MNN_AUTO) == POSFEAT_MNN_TC && !getenv("POSFEAT_RATIO_SIMT")) {
+    if (int e = mnn_tc(A, 0, N, lda, Bm, 0, M, ldb, D, 1, nn12, nn21, matches, n_matches, core_ws, core, stream, top12, top21))
+      return e;
+  } else {
+    if (int e = mnn_simt_top2(A, N, lda, Bm, M, ldb, D, nn12, nn21, top12, top21, core_ws, stream)) return e;
+  }
   if (int e = launch_ratio_flags(nn12, nn21, top12, top21, N, M, ratio, mutual, flags, stream)) return e;
   return launch_compact_flags(nn12, flags, 1, N, matches, n_matches, stream);
 }

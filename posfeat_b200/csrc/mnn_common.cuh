@@ -27,7 +27,7 @@ size_t tc_workspace_bytes(int P, int N, int M);
 // nn21 may be NULL (matches only); the call also produces matches / n_matches
 int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm, int64_t strideB, int M, int64_t ldb,
            int D, int P, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches, void* ws, size_t ws_bytes,
-           cudaStream_t stream);
+           cudaStream_t stream, float* top12 = nullptr, float* top21 = nullptr);
 int launch_mutual_compact_batched(const int32_t* nn12, const int32_t* nn21, int P, int N, int M, int64_t* matches,
                                   int32_t* n_matches, cudaStream_t stream);
 

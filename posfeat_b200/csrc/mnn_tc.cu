@@ -434,12 +434,19 @@ struct RescoreArgs {
   const float* Y; int64_t ldy, strideY;
   int32_t* nn;                            // [pairs][NX]
   float* best;                            // optional [pairs][NX]: exact best similarity, rounded down
+  float* top2;                            // kTop2 only: [pairs][NX][2] best and second best similarity (float32)
   // matches-only path (may be NULL): per-chunk minimum verification threshold and the mutual flags
   int* tmin;                              // [pairs][nchunks] ordered ints, pre-set to 0x7f7f7f7f
   unsigned char* mutual;                  // [pairs][NX], set to 1 here
   int nchunks;
 };
 
+// kTop2 (ratio-test matchers): the second largest similarity of the row is needed as well.  With T2 the
+// second largest table entry, every chunk whose entry reaches T2 - delta is rescored: the chunk of the true
+// maximum and the chunk holding the best value outside it both satisfy that (two chunks have entries >= T2,
+// one of them is not the maximum's chunk, and entries are within delta/2 of the true chunk maxima), and
+// the runner-up is either in the maximum's chunk or is that other chunk's maximum.
+template <bool kTop2>
 __global__ void __launch_bounds__(256, 3)
 tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   __shared__ __align__(16) float xs[8][kD];
@@ -471,6 +478,7 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     }
   };
   __half2 hm = *reinterpret_cast<const __half2*>(&kNegInf2);
+  __half2 hm2 = hm;                        // kTop2: element-wise second largest of the two half streams
   load_block(0);
   {
     // the x row is fetched while the table loads are in flight
@@ -486,19 +494,45 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   for (int blk = 0; blk < nblk; ++blk) {
     if (blk > 0) load_block(blk);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      hm = __hmax2(hm, __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&tv[r].x), *reinterpret_cast<const __half2*>(&tv[r].y)),
-                               __hmax2(*reinterpret_cast<const __half2*>(&tv[r].z), *reinterpret_cast<const __half2*>(&tv[r].w))));
+    for (int r = 0; r < 4; ++r) {
+      if (kTop2) {
+        const unsigned wds[4] = {tv[r].x, tv[r].y, tv[r].z, tv[r].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2 v = *reinterpret_cast<const __half2*>(&wds[k]);
+          hm2 = __hmax2(hm2, __hmin2(hm, v));
+          hm = __hmax2(hm, v);
+        }
+      } else {
+        hm = __hmax2(hm, __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&tv[r].x), *reinterpret_cast<const __half2*>(&tv[r].y)),
+                                 __hmax2(*reinterpret_cast<const __half2*>(&tv[r].z), *reinterpret_cast<const __half2*>(&tv[r].w))));
+      }
+    }
   }
-  const float F = warp_max(fmaxf(__low2float(hm), __high2float(hm)));
+  float F, T2 = 0.f;
+  if (kTop2) {
+    // top two of the lane's four values, then a warp merge of (first, second) pairs
+    const float l1 = __low2float(hm), h1 = __high2float(hm), l2 = __low2float(hm2), h2 = __high2float(hm2);
+    float m1 = fmaxf(l1, h1), m2 = fmaxf(fminf(l1, h1), fmaxf(l2, h2));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      m2 = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
+      m1 = fmaxf(m1, o1);
+    }
+    F = m1; T2 = m2;
+  } else {
+    F = warp_max(fmaxf(__low2float(hm), __high2float(hm)));
+  }
   const float xn = d.xnorm[(size_t)pair * d.NXpad + row], ymax = __uint_as_float(d.ystats[2 * pair].max_norm);
-  const float thr = F - (row_delta(d, pair, row) * table_scale(d, pair) + kHalfSlack);
+  const float thr = (kTop2 ? T2 : F) - (row_delta(d, pair, row) * table_scale(d, pair) + kHalfSlack);
   const __half2 thr2 = __float2half2_rn(__half2float(__float2half_rd(thr)));   // rounded down: never drops a candidate
   const float band = 2.f * kEps32 * xn * ymax;
   const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
   __syncwarp();
 
   float m32 = -INFINITY;       // running float32 maximum over everything seen
+  float r2 = -INFINITY;        // kTop2: running float32 runner-up (m32 is the running first)
   double bestv = -INFINITY;    // exact best
   int besti = 0x7fffffff;
   const float4* x4 = reinterpret_cast<const float4*>(&xs[w][0]);
@@ -566,8 +600,19 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
     if (col0 + myc >= d.NY) s32 = -INFINITY;
     float cm = s32;
+    if (kTop2) {
+      float c2 = -INFINITY;
 #pragma unroll
-    for (int o = 16; o >= 4; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+      for (int o = 16; o >= 4; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, cm, o), o2 = __shfl_xor_sync(0xffffffffu, c2, o);
+        c2 = fmaxf(fminf(cm, o1), fmaxf(c2, o2));
+        cm = fmaxf(cm, o1);
+      }
+      r2 = fmaxf(fminf(m32, cm), fmaxf(r2, c2));
+    } else {
+#pragma unroll
+      for (int o = 16; o >= 4; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    }
     m32 = fmaxf(m32, cm);
     unsigned need = __ballot_sync(0xffffffffu, (lane & 3) == 0 && s32 >= m32 - band);
     while (need) {
@@ -608,6 +653,11 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     const int bj = besti == 0x7fffffff ? 0 : besti;
     a.nn[(size_t)pair * d.NX + row] = bj;
     if (a.best) a.best[(size_t)pair * d.NX + row] = __double2float_rd(bestv);
+    if (kTop2) {
+      float* t2 = a.top2 + 2 * ((size_t)pair * d.NX + row);
+      t2[0] = (float)bestv;                 // the reference's sim is float32
+      t2[1] = r2;
+    }
     if (a.tmin) {
       // threshold a competitor's table entry must reach to possibly beat this row at column bj
       const MatStats& sx = d.xstats[2 * pair];
@@ -1065,7 +1115,7 @@ static void choose_splits(int P, int rb0, int yt0, int rb1, int yt1, int G, int*
 
 int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm, int64_t strideB, int M, int64_t ldb,
            int D, int P, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches, void* ws, size_t ws_bytes,
-           cudaStream_t stream) {
+           cudaStream_t stream, float* top12, float* top21) {
   if (D != kD) return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
   TcWs w = carve_tc(ws, P, N, M);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
@@ -1092,7 +1142,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   const int yt0 = (M + kYRows - 1) / kYRows, yt1 = (N + kYRows - 1) / kYRows;
   int s0, s1;
   // nn21 == NULL: matches only -> the second direction is replaced by the column verification
-  const bool one_dir = nn21 == nullptr && w.pitch[0] <= kVerMaxChunks;
+  const bool one_dir = nn21 == nullptr && top12 == nullptr && w.pitch[0] <= kVerMaxChunks;
   choose_splits(P, rb0, yt0, one_dir ? 0 : rb1, yt1, G, &s0, &s1);
   auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int NYpad, int yt, int S) {
     d.xnorm = dir ? w.bnorm : w.anorm;
@@ -1131,15 +1181,17 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     PF_CUDA(cudaMemsetAsync(w.tmin, 0x7f, sizeof(int) * (size_t)P * nchunks, stream));
     PF_CUDA(cudaMemsetAsync(w.comp_cnt, 0, sizeof(int) * (size_t)P * nchunks, stream));
   }
-  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr,
+  RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr, top12,
                  one_dir ? w.tmin : nullptr, w.mutual, nchunks};
-  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, nullptr, nullptr, 0};
+  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
   const long long resc_warps = (long long)P * (N + (one_dir ? 0 : M));
   prof_begin(PROF_MNN_RESCORE, stream);
-  tc_rescore_kernel<<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
+  if (top12) tc_rescore_kernel<true><<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
+  else tc_rescore_kernel<false><<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
   prof_end(PROF_MNN_RESCORE, stream);
   PF_LAUNCH_CHECK("tc_rescore_kernel");
+  if (top12) return POSFEAT_OK;      // ratio-test callers apply their own acceptance rule to (nn, top2)
   if (!one_dir) {
     if (nn21 == nullptr) return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher supports M <= %d", kVerMaxChunks * kChunk);
     return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);

@@ -214,3 +214,18 @@ def test_ratio_matchers_errors():
         ratio_matcher(torch.zeros(5, 128, device="cuda"), torch.zeros(1, 128, device="cuda"))
     with pytest.raises(ValueError):
         ratio_matcher(torch.zeros(5, 128, device="cuda"), torch.zeros(5, 64, device="cuda"))
+
+
+def test_ratio_tc_equals_simt(monkeypatch):
+    """Large D=128 problems take the tensor-core route (top-2 rescoring); it must return what
+    the exact SIMT kernel returns, up to rows sitting on the ratio threshold."""
+    from posfeat_b200.matchers import mutual_nn_ratio_matcher, ratio_matcher
+    a, b = ratio_pair(3000, 2500, 128)
+    ac, bc = a.cuda(), b.cuda()
+    for fn, mutual in ((ratio_matcher, False), (mutual_nn_ratio_matcher, True)):
+        tc = fn(ac, bc, ratio=0.8)
+        monkeypatch.setenv("POSFEAT_RATIO_SIMT", "1")
+        simt = fn(ac, bc, ratio=0.8)
+        monkeypatch.delenv("POSFEAT_RATIO_SIMT")
+        assert len(tc) > 100
+        check_ratio_near_tie(a.numpy(), b.numpy(), tc, simt, 0.8, mutual)
