@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
+    ap.add_argument("--streams", type=int, default=1, help="CUDA streams the pair batch is split over (1 = plain path)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 comparison leg")
     ap.add_argument("--fmap-layout", default="channels_last", choices=["channels_last", "nchw"])
@@ -204,7 +205,8 @@ def main():
 
     P = args.pairs
     score, fmap = synth_pairs(P, 1234 + 1000 * rank, dev, args.fmap_layout)   # each rank owns its shard of the pair list
-    pipe = PairPipeline(DET_CFG)
+    pipe = PairPipeline(DET_CFG, streams=args.streams)
+    n_streams = pipe.streams
 
     def barrier():
         if world > 1:
@@ -248,12 +250,14 @@ def main():
     torch.cuda.synchronize()
     ms_e2e = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host is in the loop: take wall clock
     # ---- per-kernel durations (CUDA events on the launching stream) -----
+    pipe.streams = 1                      # per-kernel durations are taken with the kernels running alone
     _lib.profile_enable(True)
     for _ in range(args.steps):
         step()
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    pipe.streams = n_streams
     clocks = sampler.stop() if rank == 0 else None
     # ---- the same pipeline in stock PyTorch ops on this GPU (rank 0, bounded sample; not part of `value`) ----
     eager = None
@@ -328,7 +332,7 @@ def main():
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16 MMA + f64 rescoring (matcher), f32 (detect/sample)",
                "data": "synthetic",
-               "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "keypoints": int(n_kp),
+               "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "streams": n_streams, "keypoints": int(n_kp),
                           "descriptor_dim": D, "fmap_layout": args.fmap_layout, "detector": {k: v for k, v in DET_CFG.items()},
                           "mean_matches_per_pair": mean_matches,
                           "l2": f"inputs {((score.numel() + fmap.numel()) * 4) >> 20} MiB per step > 126 MB L2 (no flush needed)",

@@ -8,7 +8,8 @@ Public surface mirrors the reference's plugin points:
 """
 from ._lib import LIB_PATH, PosfeatError  # noqa: F401
 
-__all__ = ["generate_kpts_single", "sample_feat_by_coord", "mnn_matcher", "mutual_nn_matcher",
+__all__ = ["generate_kpts_single", "generate_kpts_single_noavg", "sample_feat_by_coord", "mnn_matcher",
+           "mutual_nn_matcher", "ratio_matcher", "mutual_nn_ratio_matcher", "AsyncDescWriter",
            "normalize_coords", "denormalize_coords", "install", "LIB_PATH", "PosfeatError"]
 
 _LAZY = {
@@ -21,6 +22,8 @@ _LAZY = {
     "get_expected_correspondence_within_window": "preprocess",
     "Preprocess_Line2Window": "preprocess",
     "process": "extractor", "save_desc": "extractor", "FeatureExtractor": "extractor",
+    "AsyncDescWriter": "extractor", "generate_kpts_single_noavg": "preprocess_utils",
+    "ratio_matcher": "matchers", "mutual_nn_ratio_matcher": "matchers",
 }
 
 
@@ -36,8 +39,9 @@ def install(putils_module, matchers_module=None):
     """Monkey-patch a reference checkout's modules so its own managers and
     evaluation scripts call the B200 kernels."""
     from . import matchers, preprocess_utils as pu
-    for name in ("generate_kpts_single", "sample_feat_by_coord", "mnn_matcher"):
+    for name in ("generate_kpts_single", "generate_kpts_single_noavg", "sample_feat_by_coord", "mnn_matcher"):
         setattr(putils_module, name, getattr(pu, name))
     if matchers_module is not None:
-        matchers_module.mutual_nn_matcher = matchers.mutual_nn_matcher
+        for name in ("mutual_nn_matcher", "ratio_matcher", "mutual_nn_ratio_matcher"):
+            setattr(matchers_module, name, getattr(matchers, name))
     return putils_module

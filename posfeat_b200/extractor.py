@@ -60,8 +60,7 @@ def save_desc(inputs, processed, desc_root, postfix, save_npz=True, save_h5=Fals
     scores = processed["kp_score"].squeeze(0).detach().cpu().numpy()
     message = "\nkpts: {}".format(kpt.shape[0])
     if save_npz:
-        with open(save_path + ".{}".format(postfix), "wb") as f:
-            np.savez(f, keypoints=kpt, scores=scores, descriptors=desc)
+        _write_npz(save_path + ".{}".format(postfix), kpt, scores, desc)
     if save_h5:
         try:
             import h5py
@@ -83,6 +82,82 @@ def save_desc(inputs, processed, desc_root, postfix, save_npz=True, save_h5=Fals
             if image_size is not None:
                 grp.create_dataset("image_size", data=np.asarray(image_size))
     return message
+
+
+def _write_npz(path, kpt, scores, desc):
+    with open(path, "wb") as f:
+        np.savez(f, keypoints=kpt, scores=scores, descriptors=desc)
+
+
+class AsyncDescWriter:
+    """Non-blocking ``save_desc`` for the extraction loop.
+
+    The reference writes every image's ``.npz`` synchronously between two backbone
+    calls (managers/extractor.py:254-316: D2H copy, ``np.savez``, disk).  Here the
+    D2H copies go to pinned staging buffers on a side stream and a small thread pool
+    does the ``np.savez``; the GPU keeps working on the next image.  File contents and
+    names are identical to ``save_desc(save_npz=True)``.  ``close()`` (or leaving the
+    ``with`` block) waits for all pending files and re-raises the first writer error.
+    """
+
+    def __init__(self, desc_root, postfix, workers=4, max_pending=64):
+        from concurrent.futures import ThreadPoolExecutor
+        self.desc_root, self.postfix = desc_root, postfix
+        self.pool = ThreadPoolExecutor(max_workers=workers)
+        self.pending = []
+        self.max_pending = max_pending
+        self.copy_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+    def _stage(self, t):
+        """Device tensor -> (pinned host tensor, event); host tensors pass through."""
+        t = t.detach()
+        if not t.is_cuda:
+            return t.contiguous(), None
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self.copy_stream.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(self.copy_stream):
+            host.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        t.record_stream(self.copy_stream)
+        return host, ev
+
+    def save(self, inputs, processed):
+        name = inputs["name1"][0]
+        path = os.path.join(self.desc_root, name) + ".{}".format(self.postfix)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        kpt = np.array(processed["kpt"], copy=True)
+        desc, e1 = self._stage(processed["desc"].squeeze(0))
+        score, e2 = self._stage(processed["kp_score"].squeeze(0))
+
+        def job():
+            for e in (e1, e2):
+                if e is not None:
+                    e.synchronize()
+            _write_npz(path, kpt, score.numpy(), desc.numpy())
+            return path
+
+        self.pending.append(self.pool.submit(job))
+        if len(self.pending) >= self.max_pending:      # bound the pinned memory held by queued files
+            self.pending.pop(0).result()
+        return "\nkpts: {}".format(kpt.shape[0])
+
+    def flush(self):
+        pending, self.pending = self.pending, []
+        return [f.result() for f in pending]
+
+    def close(self):
+        try:
+            return self.flush()
+        finally:
+            self.pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class FeatureExtractor:

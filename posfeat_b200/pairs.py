@@ -22,7 +22,7 @@ def shard(items, rank: int, world: int):
 
 
 class PairPipeline:
-    def __init__(self, detector_config: dict, normalize: bool = True, mnn_algo: int = _lib.MNN_AUTO):
+    def __init__(self, detector_config: dict, normalize: bool = True, mnn_algo: int = _lib.MNN_AUTO, streams: int = 1):
         cfg = dict(detector_config)
         if not cfg.get("stable", True):
             raise NotImplementedError("stable=False is out of scope")
@@ -31,6 +31,8 @@ class PairPipeline:
                         thr_mod=cfg.get("thr_mod", "mean"))
         self.normalize = normalize
         self.mnn_algo = mnn_algo
+        self.streams = int(streams)          # >1: batches are split over CUDA streams (see run)
+        self._side = None
         self._host = None
 
     # -- per-image stage -------------------------------------------------
@@ -46,7 +48,7 @@ class PairPipeline:
                 "desc": desc, "idx": r["idx"][:, :n], "n": n}
 
     # -- per-pair stage --------------------------------------------------
-    def match(self, desc: torch.Tensor):
+    def match(self, desc: torch.Tensor, ws_key: str = "mnn"):
         """desc [2P,n,D]: images (2i, 2i+1) form pair i.  Returns matches
         [P,n,2] int64 and n_matches [P] int32 (device)."""
         L = lib()
@@ -63,7 +65,7 @@ class PairPipeline:
         da, db = desc[0::2], desc[1::2]          # strided views: pair stride = 2 images
         with torch.cuda.device(dev):
             ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, self.mnn_algo)
-            ws = workspace("mnn", ws_bytes, dev)
+            ws = workspace(ws_key, ws_bytes, dev)
             check(L.posfeat_mnn_batched_f32(da.data_ptr(), da.stride(0), n, da.stride(1), db.data_ptr(),
                                             db.stride(0), n, db.stride(1), D, P, self.mnn_algo,
                                             nn12.data_ptr(), 0 if nn21 is None else nn21.data_ptr(), matches.data_ptr(), nm.data_ptr(),
@@ -71,10 +73,55 @@ class PairPipeline:
         return matches, nm
 
     def run(self, score: torch.Tensor, fmap: torch.Tensor):
-        """Whole path for 2P images -> (features dict, matches, n_matches), on device."""
+        """Whole path for 2P images -> (features dict, matches, n_matches), on device.
+
+        With ``streams > 1`` and a fixed ``num_pts`` the batch is cut into that many groups of pairs,
+        each queued on its own stream with no host round trip in between: the keypoint count n stays on
+        the device and the group is processed at n = num_pts, which is what the detector returns whenever
+        every image has that many survivors.  The latency-bound selection kernel of one group then runs
+        under the sampler / matcher of another.  n is read once after everything is queued; if an image
+        came up short (n < num_pts) the batch is redone on the plain path.  Measured gain on a B200 at
+        64 pairs per step: +1.7 % with two streams, negative with more -- the default stays 1."""
+        P = score.shape[0] // 2
+        num_pts = self.cfg["num_pts"]
+        if self.streams > 1 and num_pts and num_pts >= MIN_PTS and P >= 2 * self.streams:
+            out = self._run_streams(score, fmap)
+            if out is not None:
+                return out
         feats = self.extract(score, fmap)
         matches, nm = self.match(feats["desc"])
         return feats, matches, nm
+
+    def _run_streams(self, score, fmap):
+        dev = score.device
+        G = self.streams
+        if self._side is None or len(self._side) != G:
+            self._side = [torch.cuda.Stream(device=dev) for _ in range(G)]
+        main = torch.cuda.current_stream(dev)
+        P = score.shape[0] // 2
+        cap = int(self.cfg["num_pts"])
+        h, w = score.shape[2:]
+        bounds = [2 * ((P * g) // G) for g in range(G + 1)]          # image index ranges, whole pairs
+        desc_all = torch.empty((2 * P, cap, fmap.shape[1]), dtype=torch.float32, device=dev)
+        parts = []
+        for g, st in enumerate(self._side):
+            lo, hi = bounds[g], bounds[g + 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                r = detect_topk(score[lo:hi], sync=False, ws_key=f"detect{g}", **self.cfg)
+                kps = r["kps"]                                          # [b, cap, 2]; all rows valid iff n == cap
+                desc = sample_l2norm(fmap[lo:hi], kps, self.normalize, out=desc_all[lo:hi])
+                matches, nm = self.match(desc, ws_key=f"mnn{g}")
+                parts.append((r, kps, desc, matches, nm))
+        for st in self._side:
+            main.wait_stream(st)
+        n_all = torch.stack([p[0]["n"].reshape(()) for p in parts]).cpu()      # the one host read of the step
+        if int(n_all.min()) != cap or int(n_all.max()) != cap:
+            return None
+        kps = torch.cat([p[1] for p in parts])
+        feats = {"kps_n": kps, "kpt": denormalize_coords(kps, h, w), "kp_score": torch.cat([p[0]["score"] for p in parts]),
+                 "desc": desc_all, "idx": torch.cat([p[0]["idx"] for p in parts]), "n": cap}
+        return feats, torch.cat([p[3] for p in parts]), torch.cat([p[4] for p in parts])
 
     # -- host-buffer entry (what a caller holding CPU tensors uses) --------
     def run_host(self, score_host: torch.Tensor, fmap_host: torch.Tensor):

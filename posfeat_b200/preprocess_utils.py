@@ -44,7 +44,7 @@ def _thr_mode(thr, thr_mod):
 
 
 def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_mod="mean",
-                sync=True, fullmap=False):
+                sync=True, fullmap=False, ws_key="detect"):
     """Kernel-level detector.  Returns a dict with device tensors
     ``kps [b,cap,2]``, ``score [b,cap]``, ``idx [b,cap]`` (int64 linear index into
     the interior grid), ``counts [b]``, ``n`` (python int when ``sync`` else a
@@ -76,7 +76,7 @@ def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_
         if num_pts:
             cap = max(int(num_pts), MIN_PTS)
             ws_bytes = L.posfeat_detect_workspace_bytes(b, h + pad, w + pad, cap)
-            ws = workspace("detect", ws_bytes, dev)
+            ws = workspace(ws_key, ws_bytes, dev)
             idx = torch.empty((b, cap), dtype=torch.int64, device=dev)
             kps = torch.empty((b, cap, 2), dtype=torch.float32, device=dev)
             sc = torch.empty((b, cap), dtype=torch.float32, device=dev)
@@ -87,7 +87,7 @@ def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_
         else:
             # num_pts=False: n is the smallest survivor count -> read it, then select
             ws_bytes = L.posfeat_detect_workspace_bytes(b, h + pad, w + pad, 1)
-            ws = workspace("detect", ws_bytes, dev)
+            ws = workspace(ws_key, ws_bytes, dev)
             check(L.posfeat_detect_candidates_f32(x.data_ptr(), b, h, w, x.stride(0), x.stride(2), nms_mode,
                                                   int(nms_radius), thr_mode, thr_val, counts.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), st))
@@ -146,14 +146,17 @@ def generate_kpts_single_noavg(kp_map, nms_radius, num_pts=False, scale=4, stabl
 
 
 # -------------------------------------------------------------------- sampler
-def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False):
+def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False, out=None):
     """Kernel-level sampler on device tensors.  x may be NCHW-contiguous or
     channels_last; returns [b,n,c] float32 (and a bf16 copy if asked)."""
     L = lib()
     b, c, h, w = x.shape
     n = coord_n.shape[1]
     dev = x.device
-    out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (b, n, c) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 [b,n,c] tensor")
     obf = torch.empty((b, n, c), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     if n_valid is not None:
         out.zero_()

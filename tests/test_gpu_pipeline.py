@@ -43,6 +43,25 @@ def test_pair_pipeline_vs_oracle(algo):
         assert len(got) > 100
 
 
+@pytest.mark.parametrize("short", [False, True])
+def test_pair_pipeline_streams_equal_plain_path(short):
+    """The multi-stream variant (n kept on the device, groups of pairs on separate streams) returns what the
+    plain path returns; when an image has fewer survivors than num_pts it falls back to the plain path."""
+    from posfeat_b200.pairs import PairPipeline
+    score, fmap = small_pairs(5, seed=3)
+    cfg = dict(CFG)
+    if short:
+        cfg["num_pts"] = 6000                      # more than the 160x208 maps can supply -> n < num_pts
+    plain = PairPipeline(cfg, streams=1)
+    multi = PairPipeline(cfg, streams=2)
+    f1, m1, n1 = plain.run(score.cuda(), fmap.cuda())
+    f2, m2, n2 = multi.run(score.cuda(), fmap.cuda())
+    assert f1["n"] == f2["n"] and (f1["n"] < cfg["num_pts"]) == short
+    assert torch.equal(f1["idx"], f2["idx"]) and torch.equal(f1["desc"], f2["desc"]) and torch.equal(n1, n2)
+    for i in range(5):
+        assert torch.equal(m1[i, :int(n1[i])], m2[i, :int(n2[i])])
+
+
 def test_pipeline_host_entry_matches_device_entry():
     from posfeat_b200.pairs import PairPipeline
     score, fmap = small_pairs(2, seed=9)
@@ -110,6 +129,27 @@ def test_extractor_process_and_npz(tmp_path):
     import posfeat_b200 as Pb
     m = Pb.mnn_matcher(torch.from_numpy(z["descriptors"]), torch.from_numpy(z["descriptors"]))
     np.testing.assert_array_equal(m, np.stack([np.arange(300)] * 2, -1))
+
+
+def test_async_writer_with_device_tensors(tmp_path):
+    """AsyncDescWriter: D2H through pinned staging on a side stream while the GPU keeps working."""
+    from posfeat_b200.extractor import AsyncDescWriter
+    root = str(tmp_path / "desc")
+    want = {}
+    with AsyncDescWriter(root, "PoSFeat_t", workers=2) as wr:
+        for i in range(8):
+            desc = torch.randn(1, 500, 128, device="cuda")
+            sc = torch.rand(1, 500, 1, device="cuda")
+            kpt = np.random.rand(500, 2).astype(np.float32)
+            wr.save({"name1": [f"s/{i}.ppm"]}, {"kpt": kpt, "desc": desc, "kp_score": sc})
+            want[i] = (kpt.copy(), sc[0].cpu().numpy(), desc[0].cpu().numpy())
+            desc.zero_()                        # later work on the same stream must not leak into the file
+            sc.zero_()
+    for i, (k, s_, d) in want.items():
+        z = np.load(os.path.join(root, "s", f"{i}.ppm.PoSFeat_t"))
+        np.testing.assert_array_equal(z["keypoints"], k)
+        np.testing.assert_array_equal(z["scores"], s_)
+        np.testing.assert_array_equal(z["descriptors"], d)
 
 
 def test_install_patches_reference_style_module():
