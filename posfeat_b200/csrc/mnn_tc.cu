@@ -627,15 +627,15 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
     if (nblk > 1) load_block(blk);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const unsigned wds[4] = {tv[r].x, tv[r].y, tv[r].z, tv[r].w};
+      // candidates are rare: test the lane's 8 entries as a whole first, expand bit positions only on a hit
+      const unsigned m0 = __hge2_mask(*reinterpret_cast<const __half2*>(&tv[r].x), thr2);   // 0xffff per half
+      const unsigned m1 = __hge2_mask(*reinterpret_cast<const __half2*>(&tv[r].y), thr2);
+      const unsigned m2 = __hge2_mask(*reinterpret_cast<const __half2*>(&tv[r].z), thr2);
+      const unsigned m3 = __hge2_mask(*reinterpret_cast<const __half2*>(&tv[r].w), thr2);
       unsigned mask = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wds[k]), thr2);   // 1.0 / 0.0 per half
-        const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
-        mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * k);
-        mask |= ((bits >> 16) ? 1u : 0u) << (2 * k + 1);
-      }
+      if (m0 | m1 | m2 | m3)
+        mask = ((m0 & 1u) | ((m0 >> 16) & 1u) << 1) | ((m1 & 1u) | ((m1 >> 16) & 1u) << 1) << 2 |
+               ((m2 & 1u) | ((m2 >> 16) & 1u) << 1) << 4 | ((m3 & 1u) | ((m3 >> 16) & 1u) << 1) << 6;
       unsigned any = __ballot_sync(0xffffffffu, mask != 0);
       while (any) {
         const int l = __ffs(any) - 1;
@@ -713,43 +713,41 @@ tc_scan_kernel(const ScanArgs a) {
     s_thr[c] = __float2half_rd(t);
   }
   __syncthreads();
-  // the block's rows x vectors form one flat index space, four independent loads per thread in flight
+  // a warp walks rows, its lanes the vectors of a row (no index division); four rows in flight per lane.
+  // Hits are rare (about one table entry in a thousand), so a vector is first tested as a whole.
   const int rows_per_block = a.rows_per_block;
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(d.NX, row0 + rows_per_block);
-  const int items = (row1 - row0) * nvec;
   const uint4* thr4 = reinterpret_cast<const uint4*>(s_thr);
-  const uint4* tbase = reinterpret_cast<const uint4*>(d.table + ((size_t)pair * d.NXpad + row0) * pitch);
+  const uint4* tbase = reinterpret_cast<const uint4*>(d.table + (size_t)pair * d.NXpad * pitch);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   constexpr int kU = 4;
-  for (int base = threadIdx.x; base < items; base += kU * blockDim.x) {
-    uint4 u[kU];
-    int rr[kU], vv[kU];
+  const uint4 kNever = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 th = thr4[v];
+    const __half2 t0 = *reinterpret_cast<const __half2*>(&th.x), t1 = *reinterpret_cast<const __half2*>(&th.y);
+    const __half2 t2 = *reinterpret_cast<const __half2*>(&th.z), t3 = *reinterpret_cast<const __half2*>(&th.w);
+    for (int rb = row0 + warp * kU; rb < row1; rb += nwarps * kU) {
+      uint4 u[kU];
 #pragma unroll
-    for (int q = 0; q < kU; ++q) {
-      const int it = base + q * blockDim.x;
-      rr[q] = it / nvec;
-      vv[q] = it - rr[q] * nvec;
-      u[q] = it < items ? __ldg(tbase + (size_t)rr[q] * nvec + vv[q]) : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
-    }
+      for (int q = 0; q < kU; ++q) u[q] = rb + q < row1 ? __ldg(tbase + (size_t)(rb + q) * nvec + v) : kNever;
 #pragma unroll
-    for (int q = 0; q < kU; ++q) {
-      const uint4 th = thr4[vv[q]];
-      const unsigned wu[4] = {u[q].x, u[q].y, u[q].z, u[q].w}, wt[4] = {th.x, th.y, th.z, th.w};
-      unsigned mask = 0;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const __half2 ge = __hge2(*reinterpret_cast<const __half2*>(&wu[h]), *reinterpret_cast<const __half2*>(&wt[h]));
-        const unsigned bits = *reinterpret_cast<const unsigned*>(&ge);
-        mask |= ((bits & 0xffffu) ? 1u : 0u) << (2 * h);
-        mask |= ((bits >> 16) ? 1u : 0u) << (2 * h + 1);
-      }
-      while (mask) {
-        const int h = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int c = vv[q] * 8 + h;
-        const size_t slot = (size_t)pair * a.nchunks + c;
-        const int pos = atomicAdd(a.comp_cnt + slot, 1);
-        if (pos < kCompCap) a.comp[slot * kCompCap + pos] = row0 + rr[q];
+      for (int q = 0; q < kU; ++q) {
+        const unsigned m0 = __hge2_mask(*reinterpret_cast<const __half2*>(&u[q].x), t0);
+        const unsigned m1 = __hge2_mask(*reinterpret_cast<const __half2*>(&u[q].y), t1);
+        const unsigned m2 = __hge2_mask(*reinterpret_cast<const __half2*>(&u[q].z), t2);
+        const unsigned m3 = __hge2_mask(*reinterpret_cast<const __half2*>(&u[q].w), t3);
+        if ((m0 | m1 | m2 | m3) == 0) continue;
+        unsigned mask = ((m0 & 1u) | ((m0 >> 16) & 1u) << 1) | ((m1 & 1u) | ((m1 >> 16) & 1u) << 1) << 2 |
+                        ((m2 & 1u) | ((m2 >> 16) & 1u) << 1) << 4 | ((m3 & 1u) | ((m3 >> 16) & 1u) << 1) << 6;
+        while (mask) {
+          const int h = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int c = v * 8 + h;
+          const size_t slot = (size_t)pair * a.nchunks + c;
+          const int pos = atomicAdd(a.comp_cnt + slot, 1);
+          if (pos < kCompCap) a.comp[slot * kCompCap + pos] = rb + q;
+        }
       }
     }
   }
