@@ -126,6 +126,14 @@ int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h, int w,
                               const float* coord_n, int n, const int32_t* n_valid,
                               int do_norm, float* out, void* out_bf16, void* stream);
 
+/* Pair pipeline: sampling as above for 2P images (pair p = images 2p, 2p+1; D == 128, channels-last
+ * map) that also leaves the tensor-core matcher's bf16 operands, row norms and maxima in the workspace
+ * of posfeat_mnn_batched_f32(P, N = M = n): one pass over the descriptors instead of two. */
+int posfeat_sample_pairs_f32(const float* fmap, int B, int D, int h, int w,
+                             int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                             const float* coord_n, int n, int do_norm, float* out,
+                             void* mnn_workspace, size_t mnn_ws_bytes, void* stream);
+
 /* Backward of the gather (training path, losses/preprocess.py:56-57): accumulates
  * w_tap * g_out [B,n,D] into g_fmap (same strides as fmap, zero-initialised by
  * the caller; float atomics).  The L2 normalisation is differentiated on the
@@ -151,6 +159,9 @@ int posfeat_sample_bwd_f32(const float* g_out, int B, int D, int h, int w,
 #define POSFEAT_MNN_AUTO 0
 #define POSFEAT_MNN_SIMT 1
 #define POSFEAT_MNN_TC 2
+/* or-ed into algo of posfeat_mnn_batched_f32: the workspace already holds the operands
+ * posfeat_sample_pairs_f32 prepared for the same (P, N = M) */
+#define POSFEAT_MNN_PREPARED 0x100
 size_t posfeat_mnn_workspace_bytes(int N, int M, int D, int algo);
 
 int posfeat_mnn_f32(const float* A, int N, int64_t lda, const float* Bm, int M, int64_t ldb,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "posfeat_detect_status": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "posfeat_sample_l2norm_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _i, _vp,
                                        _vp, _vp]),
+    "posfeat_sample_pairs_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "posfeat_sample_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "posfeat_mnn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -59,6 +60,7 @@ SIGNATURES = {
 
 NMS_NONE, NMS_HARD, NMS_SOFT = 0, 1, 2
 DETECT_FULLMAP = 0x10
+MNN_PREPARED = 0x100
 THR_NONE, THR_ABS, THR_MAX, THR_MEAN = 0, 1, 2, 3
 MNN_AUTO, MNN_SIMT, MNN_TC = 0, 1, 2
 

@@ -172,7 +172,10 @@ extern "C" int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, 
   PF_CHECK_ARG(P >= 1 && P <= 65535, "pairs=%d outside [1, 65535]", P);
   PF_CHECK_ARG(N >= 1 && M >= 1 && D >= 1, "empty operand (N=%d M=%d D=%d): the reference's torch.max raises on an empty reduction too", N, M, D);
   PF_CHECK_ARG(lda >= D && ldb >= D, "row stride smaller than D");
+  const bool prepared = (algo & POSFEAT_MNN_PREPARED) != 0;
+  algo &= ~POSFEAT_MNN_PREPARED;
   PF_CHECK_ARG(algo >= POSFEAT_MNN_AUTO && algo <= POSFEAT_MNN_TC, "unknown algo %d", algo);
+  PF_CHECK_ARG(!prepared || (algo == POSFEAT_MNN_TC && N == M), "POSFEAT_MNN_PREPARED goes with POSFEAT_MNN_TC and N == M");
   const int a = resolve_algo(N, M, D, algo);
   const size_t need = posfeat_mnn_batched_workspace_bytes(P, N, M, D, a);
   if (ws_bytes < need) return set_error(POSFEAT_EWORKSPACE, "mnn workspace: need %zu bytes, got %zu", need, ws_bytes);
@@ -180,7 +183,7 @@ extern "C" int posfeat_mnn_batched_f32(const float* A, int64_t stride_a, int N, 
     if (!tc_supported(N, M, D))
       return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
     return mnn_tc(A, stride_a, N, lda, Bm, stride_b, M, ldb, D, P, nn12, nn21, matches, n_matches, workspace, ws_bytes,
-                  stream);
+                  stream, nullptr, nullptr, prepared);
   } else {
     PF_CHECK_ARG(nn21 != nullptr, "the exact SIMT matcher needs an nn21 buffer");
     for (int p = 0; p < P; ++p)

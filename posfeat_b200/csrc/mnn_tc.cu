@@ -55,12 +55,6 @@ constexpr int kSmemTotal = kSmemBar + 256;
 constexpr int kSmemAlloc = kSmemTotal + 1024;
 
 // per-matrix scalars produced by the prep kernel (float bits, combined with atomicMax)
-struct MatStats {
-  unsigned max_norm;      // max_j |y_j|
-  unsigned max_norm_bf;   // max_j |y~_j|
-  unsigned max_err;       // max_j |y~_j - y_j|
-  unsigned pad;
-};
 
 struct DirParams {            // all arrays are batched over pairs: index = pair * stride + ...
   const float* xnorm;          // [pairs][NXpad] |x_i|
@@ -814,7 +808,7 @@ constexpr int kVerWarps = 4;
 // the chunk's 8 columns are evaluated in float32; a member loses its match if another
 // competitor is larger in the member's column.  Comparisons inside the float32 error band are
 // settled exactly (float64), ties by the lower row index.
-__global__ void __launch_bounds__(kVerWarps * 32, 6)
+__global__ void __launch_bounds__(kVerWarps * 32, 8)
 tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
   __shared__ float s_e[kVerWarps][32][kChunk];                    // competitor matrix of short lists
@@ -1088,6 +1082,19 @@ static TcWs carve_tc(void* base, int P, int N, int M) {
   return w;
 }
 
+int tc_prep_sink(void* ws, size_t ws_bytes, int P, int N, int M, PrepSink* sink, cudaStream_t stream) {
+  TcWs w = carve_tc(ws, P, N, M);
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  if (((uintptr_t)ws & 255) != 0) return set_error(POSFEAT_EINVAL, "mnn workspace must be 256-byte aligned");
+  const int Np = pad_rows(N), Mp = pad_rows(M);
+  PF_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(MatStats) * 2 * P, stream));
+  if (Np != N || Mp != M) {   // padding rows must read as zero operands
+    PF_CUDA(cudaMemsetAsync(w.Ab, 0, (size_t)((char*)w.stats - (char*)w.Ab), stream));
+  }
+  *sink = PrepSink{w.Ab, w.Bb, w.anorm, w.aerr, w.bnorm, w.berr, w.stats, Np, Mp};
+  return POSFEAT_OK;
+}
+
 bool tc_supported(int N, int M, int D) { return D == kD && N >= 1 && M >= 1; }
 size_t tc_workspace_bytes(int P, int N, int M) { return carve_tc(nullptr, P, N, M).total; }
 
@@ -1113,7 +1120,7 @@ static void choose_splits(int P, int rb0, int yt0, int rb1, int yt1, int G, int*
 
 int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm, int64_t strideB, int M, int64_t ldb,
            int D, int P, int32_t* nn12, int32_t* nn21, int64_t* matches, int32_t* n_matches, void* ws, size_t ws_bytes,
-           cudaStream_t stream, float* top12, float* top21) {
+           cudaStream_t stream, float* top12, float* top21, bool prepared) {
   if (D != kD) return set_error(POSFEAT_EUNSUPPORTED, "tensor-core matcher needs D == 128 (got D=%d)", D);
   TcWs w = carve_tc(ws, P, N, M);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "mnn tc workspace: need %zu bytes, got %zu", w.total, ws_bytes);
@@ -1122,13 +1129,15 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   if ((long long)P * Np >= (1ll << 31) || (long long)P * Mp >= (1ll << 31))
     return set_error(POSFEAT_EINVAL, "batched matcher: pairs * rows exceeds 2^31");
 
-  PF_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(MatStats) * 2 * P, stream));
-  PrepArgs pa{A, lda, strideA, N, Np, Bm, ldb, strideB, M, Mp, w.Ab, w.Bb, w.anorm, w.aerr, w.bnorm, w.berr, w.stats, P};
-  const long long prep_warps = (long long)P * (Np + Mp);
-  prof_begin(PROF_MNN_PREP, stream);
-  tc_prep_kernel<<<(unsigned)(prep_warps / 64), 256, 0, stream>>>(pa);
-  prof_end(PROF_MNN_PREP, stream);
-  PF_LAUNCH_CHECK("tc_prep_kernel");
+  if (!prepared) {   // otherwise the sampler already left bf16 rows, norms and maxima in the workspace (tc_prep_sink)
+    PF_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(MatStats) * 2 * P, stream));
+    PrepArgs pa{A, lda, strideA, N, Np, Bm, ldb, strideB, M, Mp, w.Ab, w.Bb, w.anorm, w.aerr, w.bnorm, w.berr, w.stats, P};
+    const long long prep_warps = (long long)P * (Np + Mp);
+    prof_begin(PROF_MNN_PREP, stream);
+    tc_prep_kernel<<<(unsigned)(prep_warps / 64), 256, 0, stream>>>(pa);
+    prof_end(PROF_MNN_PREP, stream);
+    PF_LAUNCH_CHECK("tc_prep_kernel");
+  }
 
   CUtensorMap mapA, mapB;
   if (int e = make_map(&mapA, w.Ab, P * Np)) return e;

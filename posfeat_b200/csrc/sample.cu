@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "mnn_common.cuh"
 
 namespace posfeat {
 
@@ -89,12 +90,12 @@ sample_strided_kernel(const float* __restrict__ fmap, int D, int h, int w, int64
 }
 
 // unit channel stride (NHWC), D % 4 == 0, 16-byte aligned pixels: float4 taps
-template <int VPL>  // float4 per lane (D <= 128*VPL)
+template <int VPL, bool kSink>  // float4 per lane (D <= 128*VPL)
 __global__ void __launch_bounds__(256)
 sample_nhwc_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sy,
                    int64_t sx, const float* __restrict__ coord, int n,
                    const int32_t* __restrict__ n_valid, int do_norm, float* __restrict__ out,
-                   __nv_bfloat16* __restrict__ out_bf16) {
+                   __nv_bfloat16* __restrict__ out_bf16, const PrepSink sink) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -138,6 +139,7 @@ sample_nhwc_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t 
       float4 r = v[j];
       if (do_norm) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
       *reinterpret_cast<float4*>(o + c) = r;
+      if (kSink) prep_sink_row(sink, b >> 1, b & 1, p, lane, r);     // D == 128: every lane holds one float4
       if (out_bf16) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
         uint2 pk;
@@ -196,11 +198,11 @@ extern "C" int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h,
                    (!ob || (uintptr_t)ob % 8 == 0);
   if (vec) {
     if (D <= 128)
-      sample_nhwc_kernel<1><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+      sample_nhwc_kernel<1, false><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob, PrepSink{});
     else if (D <= 256)
-      sample_nhwc_kernel<2><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+      sample_nhwc_kernel<2, false><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob, PrepSink{});
     else
-      sample_nhwc_kernel<4><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
+      sample_nhwc_kernel<4, false><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, n_valid, do_norm, out, ob, PrepSink{});
   } else {
     if (D <= 32)
       sample_strided_kernel<1><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
@@ -214,6 +216,31 @@ extern "C" int posfeat_sample_l2norm_f32(const float* fmap, int B, int D, int h,
       sample_strided_kernel<16><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, coord_n, n, n_valid, do_norm, out, ob);
   }
   PF_LAUNCH_CHECK("sample kernel");
+  return POSFEAT_OK;
+}
+
+// Sampler + matcher operand preparation in one pass (pair pipeline): images (2p, 2p+1) are the two sides of
+// pair p; besides `out` the kernel leaves the tensor-core matcher's bf16 operand rows, row norms, rounding
+// error norms and their maxima in the matcher workspace, so posfeat_mnn_batched_f32 can be called with
+// POSFEAT_MNN_TC | POSFEAT_MNN_PREPARED and skips its own pass over the descriptors.
+extern "C" int posfeat_sample_pairs_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc,
+                                        int64_t sy, int64_t sx, const float* coord_n, int n, int do_norm, float* out,
+                                        void* mnn_workspace, size_t mnn_ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(fmap && coord_n && out && mnn_workspace, "NULL pointer");
+  PF_CHECK_ARG(B >= 2 && B % 2 == 0 && B <= 65534, "B=%d: need an even number of images (pairs)", B);
+  PF_CHECK_ARG(D == 128 && n >= 1 && h >= 1 && w >= 1, "fused sampling needs D == 128 (got D=%d) and n >= 1", D);
+  PF_CHECK_ARG(sc == 1 && sx % 4 == 0 && sy % 4 == 0 && sb % 4 == 0 && ((uintptr_t)fmap % 16 == 0) &&
+                   ((uintptr_t)out % 16 == 0),
+               "fused sampling needs a channels-last, 16-byte aligned descriptor map");
+  PrepSink sink;
+  if (int e = tc_prep_sink(mnn_workspace, mnn_ws_bytes, B / 2, n, n, &sink, stream)) return e;
+  const int warps = 8;
+  dim3 grid((n + warps - 1) / warps, B), block(32 * warps);
+  ProfScope prof(PROF_SAMPLE, stream);
+  sample_nhwc_kernel<1, true><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, nullptr, do_norm, out,
+                                                           nullptr, sink);
+  PF_LAUNCH_CHECK("sample_nhwc_kernel<sink>");
   return POSFEAT_OK;
 }
 

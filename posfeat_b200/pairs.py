@@ -48,9 +48,35 @@ class PairPipeline:
                 "desc": desc, "idx": r["idx"][:, :n], "n": n}
 
     # -- per-pair stage --------------------------------------------------
-    def match(self, desc: torch.Tensor, ws_key: str = "mnn"):
+    def _tc_applies(self, n, D):
+        return D == 128 and self.mnn_algo in (_lib.MNN_AUTO, _lib.MNN_TC) and (self.mnn_algo == _lib.MNN_TC or n * n >= 1024 * 1024)
+
+    def sample_for_pairs(self, fmap, kps, ws_key: str = "mnn", out=None):
+        """Sampler for the pair path: when the tensor-core matcher will run, one kernel writes the
+        descriptors AND the matcher's bf16 operands / norms into its workspace (posfeat_sample_pairs_f32),
+        so the matcher skips its own pass over the descriptors.  Returns (desc, prepared)."""
+        b, D, h, w = fmap.shape
+        n = kps.shape[1]
+        fused = (b % 2 == 0 and n >= 1 and self._tc_applies(n, D) and fmap.dtype == torch.float32 and
+                 fmap.is_contiguous(memory_format=torch.channels_last) and fmap.data_ptr() % 16 == 0)
+        if not fused:
+            return sample_l2norm(fmap, kps, self.normalize, out=out), False
+        L = lib()
+        dev = fmap.device
+        kps = kps.contiguous()
+        if out is None:
+            out = torch.empty((b, n, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = workspace(ws_key, L.posfeat_mnn_batched_workspace_bytes(b // 2, n, n, D, _lib.MNN_TC), dev)
+            check(L.posfeat_sample_pairs_f32(fmap.data_ptr(), b, D, h, w, fmap.stride(0), fmap.stride(1), fmap.stride(2),
+                                             fmap.stride(3), kps.data_ptr(), n, int(bool(self.normalize)), out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        return out, True
+
+    def match(self, desc: torch.Tensor, ws_key: str = "mnn", prepared: bool = False):
         """desc [2P,n,D]: images (2i, 2i+1) form pair i.  Returns matches
-        [P,n,2] int64 and n_matches [P] int32 (device)."""
+        [P,n,2] int64 and n_matches [P] int32 (device).  ``prepared``: the workspace ``ws_key`` already
+        holds the operands written by sample_for_pairs."""
         L = lib()
         b, n, D = desc.shape
         P = b // 2
@@ -60,14 +86,15 @@ class PairPipeline:
         nn12 = torch.empty((P, n), dtype=torch.int32, device=dev)
         # nn21 is not requested: the tensor-core matcher then computes one direction and verifies
         # mutuality by a column scan; the exact SIMT matcher (small sizes / algo=1) needs the buffer
-        use_simt = self.mnn_algo == _lib.MNN_SIMT or D != 128 or (self.mnn_algo == _lib.MNN_AUTO and n * n < 1024 * 1024)
+        use_simt = not self._tc_applies(n, D)
+        algo = (_lib.MNN_TC | _lib.MNN_PREPARED) if prepared else self.mnn_algo
         nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if use_simt else None
         da, db = desc[0::2], desc[1::2]          # strided views: pair stride = 2 images
         with torch.cuda.device(dev):
-            ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, self.mnn_algo)
+            ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, _lib.MNN_TC if prepared else self.mnn_algo)
             ws = workspace(ws_key, ws_bytes, dev)
             check(L.posfeat_mnn_batched_f32(da.data_ptr(), da.stride(0), n, da.stride(1), db.data_ptr(),
-                                            db.stride(0), n, db.stride(1), D, P, self.mnn_algo,
+                                            db.stride(0), n, db.stride(1), D, P, algo,
                                             nn12.data_ptr(), 0 if nn21 is None else nn21.data_ptr(), matches.data_ptr(), nm.data_ptr(),
                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return matches, nm
@@ -88,8 +115,14 @@ class PairPipeline:
             out = self._run_streams(score, fmap)
             if out is not None:
                 return out
-        feats = self.extract(score, fmap)
-        matches, nm = self.match(feats["desc"])
+        r = detect_topk(score, sync=True, **self.cfg)
+        n = r["n"]
+        kps = r["kps"][:, :n]
+        desc, prepared = self.sample_for_pairs(fmap, kps)
+        h, w = score.shape[2:]
+        feats = {"kps_n": kps, "kpt": denormalize_coords(kps, h, w), "kp_score": r["score"][:, :n],
+                 "desc": desc, "idx": r["idx"][:, :n], "n": n}
+        matches, nm = self.match(desc, prepared=prepared)
         return feats, matches, nm
 
     def _run_streams(self, score, fmap):
@@ -110,8 +143,8 @@ class PairPipeline:
             with torch.cuda.stream(st):
                 r = detect_topk(score[lo:hi], sync=False, ws_key=f"detect{g}", **self.cfg)
                 kps = r["kps"]                                          # [b, cap, 2]; all rows valid iff n == cap
-                desc = sample_l2norm(fmap[lo:hi], kps, self.normalize, out=desc_all[lo:hi])
-                matches, nm = self.match(desc, ws_key=f"mnn{g}")
+                desc, prepared = self.sample_for_pairs(fmap[lo:hi], kps, ws_key=f"mnn{g}", out=desc_all[lo:hi])
+                matches, nm = self.match(desc, ws_key=f"mnn{g}", prepared=prepared)
                 parts.append((r, kps, desc, matches, nm))
         for st in self._side:
             main.wait_stream(st)

@@ -62,6 +62,32 @@ def test_pair_pipeline_streams_equal_plain_path(short):
         assert torch.equal(m1[i, :int(n1[i])], m2[i, :int(n2[i])])
 
 
+def test_fused_sampler_operands_equal_separate_pass():
+    """channels-last maps + tensor-core matcher: the sampler writes the matcher's bf16 operands and norms
+    itself (posfeat_sample_pairs_f32).  Results must equal the path where the matcher rounds the
+    descriptors in its own pass (NCHW map -> plain sampler)."""
+    from posfeat_b200 import _lib
+    from posfeat_b200.pairs import PairPipeline
+    score, fmap = small_pairs(3, seed=11, H=320, W=416)
+    cfg = dict(CFG, num_pts=1500)
+    pipe = PairPipeline(cfg, mnn_algo=_lib.MNN_TC)
+    f_cl = fmap.cuda().contiguous(memory_format=torch.channels_last)
+    kps = pipe.extract(score.cuda(), f_cl)["kps_n"].contiguous()
+    _, prepared = pipe.sample_for_pairs(f_cl, kps)
+    assert prepared
+    _, prepared = pipe.sample_for_pairs(fmap.cuda(), kps)
+    assert not prepared
+    fa, ma, na = pipe.run(score.cuda(), f_cl)
+    fb, mb, nb = pipe.run(score.cuda(), fmap.cuda())
+    assert torch.equal(fa["idx"], fb["idx"]) and torch.equal(na, nb)
+    np.testing.assert_allclose(fa["desc"].cpu().numpy(), fb["desc"].cpu().numpy(), rtol=0, atol=1e-6)
+    for i in range(3):
+        a_, b_ = fa["desc"][2 * i].cpu().numpy(), fa["desc"][2 * i + 1].cpu().numpy()
+        want = O.mnn_matcher(a_, b_, exact=True)
+        check_mnn_near_tie(a_, b_, ma[i, :int(na[i])].cpu().numpy(), want)
+        assert int(na[i]) > 300
+
+
 def test_pipeline_host_entry_matches_device_entry():
     from posfeat_b200.pairs import PairPipeline
     score, fmap = small_pairs(2, seed=9)
