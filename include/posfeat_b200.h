@@ -221,10 +221,13 @@ int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const float* v, 
                                 int B, int n, int m, int D, int C, float scale,
                                 float* out, float* lse, void* workspace, size_t ws_bytes,
                                 void* stream);
+/* Backward on the same size rule: tensor cores (W = P o (g.v - g.out) materialised as tf32 hi/lo, then two
+ * split-K 3xTF32 GEMMs) with the workspace posfeat_corr_expect_bwd_workspace_bytes reports, else SIMT. */
+size_t posfeat_corr_expect_bwd_workspace_bytes(int B, int n, int m, int D, int C);
 int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, int v_batched,
                                 int B, int n, int m, int D, int C, float scale,
                                 const float* out, const float* lse, const float* g_out,
-                                float* g_q, float* g_k, void* stream);
+                                float* g_q, float* g_k, void* workspace, size_t ws_bytes, void* stream);
 
 /* Window / line variant.  mode 0: get_expected_correspondence_within_window,
  * losses/preprocess_utils.py:721-758 -- positions = centre [B,n,2] + offsets [m,2]

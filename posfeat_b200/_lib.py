@@ -50,8 +50,9 @@ SIGNATURES = {
     "posfeat_mnn_host_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "posfeat_corr_expect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "posfeat_corr_expect_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "posfeat_corr_expect_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "posfeat_corr_expect_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                         _vp]),
+                                         _vp, _sz, _vp]),
     "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i, _i,
                                            _vp, _vp, _vp, _vp, _vp]),
     "posfeat_window_expect_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i,

@@ -28,6 +28,11 @@ bool corr_tc_eligible(int B, int n, int m, int D, int C);
 size_t corr_tc_workspace_bytes(int B, int n, int m, int D, int C);
 int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, int B, int n, int m, int D, int C,
                 float scale, float* out, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t corr_tc_bwd_workspace_bytes(int B, int n, int m, int D, int C);
+bool corr_tc_bwd_eligible(int B, int n, int m, int D, int C);
+int corr_tc_bwd(const float* q, const float* k, const float* v, int v_batched, int B, int n, int m, int D, int C,
+                float scale, const float* out, const float* lse, const float* g_out, float* g_q, float* g_k, void* ws,
+                size_t ws_bytes, cudaStream_t stream);
 
 constexpr int kCT = 64;          // logit tile edge
 constexpr int kCDmax = 128;      // descriptor length supported by the dense kernels
@@ -526,12 +531,20 @@ extern "C" int posfeat_corr_expect_fwd_f32(const float* q, const float* k, const
   return POSFEAT_OK;
 }
 
+extern "C" size_t posfeat_corr_expect_bwd_workspace_bytes(int B, int n, int m, int D, int C) {
+  if (B < 1 || n < 1 || m < 1) return 0;
+  return corr_tc_bwd_workspace_bytes(B, n, m, D, C);
+}
+
 extern "C" int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, int v_batched, int B, int n,
                                            int m, int D, int C, float scale, const float* out, const float* lse,
-                                           const float* g_out, float* g_q, float* g_k, void* stream_) {
+                                           const float* g_out, float* g_q, float* g_k, void* workspace, size_t ws_bytes,
+                                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_dense(q, k, v, B, n, m, D, C)) return e;
   PF_CHECK_ARG(out && lse && g_out && (g_q || g_k), "NULL pointer");
+  if (corr_tc_bwd_eligible(B, n, m, D, C) && !getenv("POSFEAT_CORR_SIMT"))
+    return corr_tc_bwd(q, k, v, v_batched, B, n, m, D, C, scale, out, lse, g_out, g_q, g_k, workspace, ws_bytes, stream);
   const size_t smem = sizeof(float) * (kCDmax * (kCT + 4) + kCT * (kCDmax + 4) + kCT * (kCT + 1) + 32 * (kCT + 4));
   PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PF_CUDA(cudaFuncSetAttribute(corr_expect_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -71,6 +71,12 @@ struct CorrTcParams {
   const float4* v4;          // [v_batched ? B : 1][m_pad] value rows padded to 4 columns
   int v_batched;
   float* part;               // [B][q_tiles][splits][128][8]: m, l, acc0..3
+  // kMode 1 (backward, W materialisation): W = P o (g.v - g.out), written as tf32 hi/lo, plain and transposed
+  const float* g;            // [B][n][C]
+  const float* o;            // [B][n][C] forward output
+  const float* lse;          // [B][n]
+  float *w_hi, *w_lo;        // [B][n_pad][m_pad]
+  float *wt_hi, *wt_lo;      // [B][m_pad][n_pad]
 };
 
 // ---- split: x -> hi = tf32(x), lo = x - hi, zero padded to [rows_pad][Dp] per batch (Dp = 32 * slices).
@@ -120,6 +126,10 @@ __global__ void corr_padv_kernel(const float* __restrict__ v, int vb, int m, int
   }
 }
 
+// kMode 0: forward (online softmax expectation).  kMode 1: backward, first step -- the same contraction, but
+// the epilogue turns every logit into W_ij = exp(scale s_ij - lse_i) (g_i . v_j - g_i . out_i) and stores it
+// (tf32 hi/lo, row-major and transposed) as the operand of the two gradient GEMMs.
+template <int kMode>
 __global__ void __launch_bounds__(kCtThreads, 1)
 corr_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_constant__ CUtensorMap mapQl,
                    const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl,
@@ -221,6 +231,65 @@ corr_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_const
       const float4* vb = p.v4 + (p.v_batched ? (size_t)b * p.m_pad : 0);
       const float sl2 = p.sl2;
       const int m = p.m;
+      if (kMode == 1) {
+        // ---- backward: W tiles ----
+        const int qi = qt * kCtM + row;                      // query index inside the batch
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, go = 0.f, lse2 = INFINITY;   // padding rows: W = 0
+        if (qi < p.n) {
+          const float* gp = p.g + ((size_t)b * p.n + qi) * p.C;
+          const float* op = p.o + ((size_t)b * p.n + qi) * p.C;
+          float gg[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int c = 0; c < p.C; ++c) { gg[c] = __ldg(gp + c); go = fmaf(gg[c], __ldg(op + c), go); }
+          g0 = gg[0]; g1 = gg[1]; g2 = gg[2]; g3 = gg[3];
+          lse2 = __ldg(p.lse + (size_t)b * p.n + qi) * 1.4426950408889634f;
+        }
+        float* wrow_hi = p.w_hi + ((size_t)b * p.n_pad + qi) * p.m_pad;
+        float* wrow_lo = p.w_lo + ((size_t)b * p.n_pad + qi) * p.m_pad;
+        int as = 0, aph = 0;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(bar_acc_full + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t)(as * kCtN + half * 64) + ((uint32_t)(quarter * 32) << 16);
+          const int c0 = t * kCtN + half * 64;
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t v[32];
+            tc_ld32(taddr + ch * 32, v);
+            tc_wait_ld();
+            if (ch == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+            }
+            const int cb = c0 + ch * 32;
+            const float4* vp = vb + cb;
+            float* th = p.wt_hi + ((size_t)b * p.m_pad + cb) * p.n_pad + qi;
+            float* tl = p.wt_lo + ((size_t)b * p.m_pad + cb) * p.n_pad + qi;
+            float hi[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pj = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -lse2));
+              const float4 vv = __ldg(vp + j);
+              const float dp = fmaf(g3, vv.w, fmaf(g2, vv.z, fmaf(g1, vv.y, g0 * vv.x))) - go;
+              const float wv = pj * dp;
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(wv));
+              hi[j] = __uint_as_float(hb);
+              const float lo = wv - hi[j];
+              v[j] = __float_as_uint(lo);
+              th[(size_t)j * p.n_pad] = hi[j];           // transposed copy: the 32 lanes (rows) write 128 contiguous bytes
+              tl[(size_t)j * p.n_pad] = lo;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              *reinterpret_cast<float4*>(wrow_hi + cb + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+              *reinterpret_cast<float4*>(wrow_lo + cb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                         __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          }
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      } else {
       float mrun = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int as = 0, aph = 0;
       for (int t = t0; t < t1; ++t) {
@@ -283,8 +352,9 @@ corr_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_const
         reinterpret_cast<float4*>(out)[0] = make_float4(mm, l * ca + d[1] * cbb, a0 * ca + d[2] * cbb, a1 * ca + d[3] * cbb);
         reinterpret_cast<float4*>(out)[1] = make_float4(a2 * ca + d[4] * cbb, a3 * ca + d[5] * cbb, 0.f, 0.f);
       }
+      }   // kMode == 0
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (kMode == 0 && warp >= 4 && warp < 8) {
     // a split without tiles (cannot happen with the host's split choice, kept for safety): neutral partial
     const int row = (warp & 3) * 32 + lane;
     float* out = p.part + ((((size_t)b * p.q_tiles + qt) * p.splits + split) * kCtM + row) * 8;
@@ -322,13 +392,190 @@ __global__ void corr_tc_merge_kernel(const CorrTcParams p, float* __restrict__ o
   lse[i] = (M + log2f(L)) * 0.6931471805599453f;
 }
 
+// ---- transposed split: src [B][rows][D] -> hiT / loT [B][Dp][rows_pad] (rows contiguous), zero padded.
+// 32 x 32 tiles through shared memory so that both the reads (along D) and the writes (along rows) coalesce.
+__global__ void corr_split_t_kernel(const float* __restrict__ src, int rows, int D, int rows_pad, int Dp,
+                                    float* __restrict__ hiT, float* __restrict__ loT) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 256 threads: 8 rows per pass
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < rows && c < D) ? __ldg(src + ((size_t)b * rows + r) * D + c) : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;                              // output row c (a channel), column r
+    if (c < Dp && r < rows_pad) {
+      const float x = tile[tx][k];
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+      const float h = __uint_as_float(hb);
+      const size_t o = ((size_t)b * Dp + c) * rows_pad + r;
+      hiT[o] = h;
+      loT[o] = x - h;
+    }
+  }
+}
+
+// ---- split-K 3xTF32 GEMM for the gradients:  C[b][M][N] (+)= scale * A[b][M][K] * Bt[b][N][K]^T
+// A, Bt are pre-split into tf32 hi/lo and K-major (K contiguous); N = Dp <= 128.  One CTA = one 128-row tile of C
+// and a contiguous range of 32-wide K slices; the accumulator lives in TMEM for the whole range and is written
+// once (to the output, or to a per-split partial that corr_tc_reduce_kernel sums).
+constexpr int kGmStages = 3;
+constexpr int kGmStageBytes = 4 * kCtAtomBytes;                    // A hi, A lo, B hi, B lo
+constexpr int kGmSmemBar = kGmStages * kGmStageBytes;
+constexpr int kGmSmemAlloc = kGmSmemBar + 128 + 1024;
+constexpr int kGmThreads = 8 * 32;                                 // warps 0,1,2: TMA, MMA, TMEM; warps 4-7: epilogue
+
+struct GemmParams {
+  int M_pad;             // rows of A (and C) per batch, multiple of 128
+  int N;                 // Dp
+  int m_valid;           // rows of C that exist
+  int n_valid;           // columns of C that exist (D)
+  int slices;            // K / 32
+  int splits, slices_per_split;
+  float scale;
+  float* out;            // splits == 1: [B][m_valid][n_valid];  else partials [splits][B][M_pad][N]
+  int B;
+};
+
+__global__ void __launch_bounds__(kGmThreads, 1)
+corr_tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                    const GemmParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + kGmSmemBar;
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kGmStages, bar_acc = bar_empty + 8 * kGmStages;
+  const uint32_t tmem_slot = bar_acc + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - sbase));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
+  const int s0 = split * p.slices_per_split, s1 = min(p.slices, s0 + p.slices_per_split);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGmStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t b_bytes = (uint32_t)p.N * 128u;                  // one B slice: N rows x 128 bytes
+
+  if (warp == 0 && lane == 0) {
+    int st = 0, ph = 0;
+    const int arow = b * p.M_pad + mt * 128, brow = b * p.N;
+    for (int sl = s0; sl < s1; ++sl) {
+      mbar_wait(bar_empty + 8 * st, ph ^ 1);
+      mbar_expect_tx(bar_full + 8 * st, 2 * kCtAtomBytes + 2 * b_bytes);
+      const uint32_t base = sbase + st * kGmStageBytes;
+      tma_load_2d(base, &mapAh, sl * 32, arow, bar_full + 8 * st);
+      tma_load_2d(base + kCtAtomBytes, &mapAl, sl * 32, arow, bar_full + 8 * st);
+      tma_load_2d(base + 2 * kCtAtomBytes, &mapBh, sl * 32, brow, bar_full + 8 * st);
+      tma_load_2d(base + 3 * kCtAtomBytes, &mapBl, sl * 32, brow, bar_full + 8 * st);
+      if (++st == kGmStages) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    int st = 0, ph = 0;
+    for (int sl = s0; sl < s1; ++sl) {
+      mbar_wait(bar_full + 8 * st, ph);
+      tc_fence_after();
+      const uint32_t base = sbase + st * kGmStageBytes;
+      const uint64_t ah = make_sw128_desc(base), al = make_sw128_desc(base + kCtAtomBytes);
+      const uint64_t bh = make_sw128_desc(base + 2 * kCtAtomBytes), bl = make_sw128_desc(base + 3 * kCtAtomBytes);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t o = (uint64_t)(k * 2);
+        tc_mma_tf32(tmem_base, al + o, bh + o, idesc, (sl > s0 || k) ? 1u : 0u);
+        tc_mma_tf32(tmem_base, ah + o, bl + o, idesc, 1u);
+        tc_mma_tf32(tmem_base, ah + o, bh + o, idesc, 1u);
+      }
+      tc_commit(bar_empty + 8 * st);
+      if (++st == kGmStages) { st = 0; ph ^= 1; }
+    }
+    tc_commit(bar_acc);
+  } else if (warp >= 4) {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const int r = mt * 128 + row;
+    if (s0 < s1) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+      uint32_t v[32];
+      if (s0 < s1) {
+        tc_ld32(tmem_base + (uint32_t)c0 + ((uint32_t)(quarter * 32) << 16), v);
+        tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (p.splits == 1) {
+        if (r < p.m_valid) {
+          float* dst = p.out + ((size_t)b * p.m_valid + r) * p.n_valid + c0;
+          if ((p.n_valid & 3) == 0 && c0 + 32 <= p.n_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * p.scale, __uint_as_float(v[j + 1]) * p.scale,
+                                                                __uint_as_float(v[j + 2]) * p.scale, __uint_as_float(v[j + 3]) * p.scale);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.n_valid) dst[j] = __uint_as_float(v[j]) * p.scale;
+          }
+        }
+      } else {
+        float* dst = p.out + ((((size_t)split * p.B + b) * p.M_pad + r) * p.N) + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
+// out[b][r][c] = scale * sum_s part[s][b][r][c]
+__global__ void corr_tc_reduce_kernel(const float* __restrict__ part, int splits, int B, int M_pad, int N, int m_valid,
+                                      int n_valid, float scale, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * m_valid * n_valid) return;
+  const int c = (int)(i % n_valid);
+  const int64_t rr = i / n_valid;
+  const int r = (int)(rr % m_valid), b = (int)(rr / m_valid);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[(((size_t)s * B + b) * M_pad + r) * N + c];
+  out[i] = acc * scale;
+}
+
 // ------------------------------------------------------------------ host side
-static int make_map_f32(CUtensorMap* map, void* base, int Dp, int64_t rows) {
+static int make_map_f32(CUtensorMap* map, void* base, int64_t Dp, int64_t rows, int box_rows = 128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(POSFEAT_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)Dp * 4};
-  cuuint32_t box[2] = {32, 128};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -414,14 +661,145 @@ int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, i
   if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
   static bool attr_set = false;
   if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
+    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
     attr_set = true;
   }
   dim3 grid(p.splits, p.q_tiles, B);
-  corr_tc_fwd_kernel<<<grid, kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
+  corr_tc_fwd_kernel<0><<<grid, kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
   PF_LAUNCH_CHECK("corr_tc_fwd_kernel");
   corr_tc_merge_kernel<<<(int)(((int64_t)B * n + 255) / 256), 256, 0, stream>>>(p, out, lse);
   PF_LAUNCH_CHECK("corr_tc_merge_kernel");
+  return POSFEAT_OK;
+}
+
+// ---------------------------------------------------------------- backward on the tensor cores
+struct CorrTcBwdWs {
+  float *qh, *ql, *kh, *kl;          // [B][n_pad|m_pad][Dp]
+  float *qth, *qtl, *kth, *ktl;      // [B][Dp][n_pad|m_pad]
+  float4* v4;
+  float *wh, *wl, *wth, *wtl;        // [B][n_pad][m_pad], [B][m_pad][n_pad]
+  float* part;                       // split-K partials of the larger of the two GEMMs
+  size_t total;
+};
+
+static void gemm_shape(int B, int m_tiles, int slices, int* splits, int* sps) {
+  const int units = B * m_tiles;
+  int s = std::max(1, std::min((2 * 148) / std::max(units, 1), slices));
+  *sps = (slices + s - 1) / s;
+  *splits = (slices + *sps - 1) / *sps;
+}
+
+static CorrTcBwdWs carve_corr_tc_bwd(void* base, int B, int n, int m, int D, int vb) {
+  CorrTcBwdWs w{};
+  const size_t Dp = (D + 31) / 32 * 32, np = pad128(n), mp = pad128(m);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  w.qh = (float*)take(4 * B * np * Dp); w.ql = (float*)take(4 * B * np * Dp);
+  w.kh = (float*)take(4 * B * mp * Dp); w.kl = (float*)take(4 * B * mp * Dp);
+  w.qth = (float*)take(4 * B * np * Dp); w.qtl = (float*)take(4 * B * np * Dp);
+  w.kth = (float*)take(4 * B * mp * Dp); w.ktl = (float*)take(4 * B * mp * Dp);
+  w.v4 = (float4*)take(sizeof(float4) * (size_t)vb * mp);
+  w.wh = (float*)take(4 * B * np * mp); w.wl = (float*)take(4 * B * np * mp);
+  w.wth = (float*)take(4 * B * np * mp); w.wtl = (float*)take(4 * B * np * mp);
+  int sq, spq, sk, spk;
+  gemm_shape(B, (int)(np / 128), (int)(mp / 32), &sq, &spq);      // g_q: K dimension = m
+  gemm_shape(B, (int)(mp / 128), (int)(np / 32), &sk, &spk);      // g_k: K dimension = n
+  const size_t pq = sq > 1 ? (size_t)sq * B * np * Dp : 0, pk = sk > 1 ? (size_t)sk * B * mp * Dp : 0;
+  w.part = (float*)take(4 * std::max(pq, pk));
+  w.total = off;
+  return w;
+}
+
+// The backward path launches ten kernels; below ~8M logits the SIMT kernels finish sooner (measured).
+bool corr_tc_bwd_eligible(int B, int n, int m, int D, int C) {
+  return corr_tc_eligible(B, n, m, D, C) && (int64_t)B * n * m >= (1 << 23);
+}
+
+size_t corr_tc_bwd_workspace_bytes(int B, int n, int m, int D, int C) {
+  if (!corr_tc_bwd_eligible(B, n, m, D, C)) return 0;
+  return carve_corr_tc_bwd(nullptr, B, n, m, D, B).total;
+}
+
+static int run_gemm(float* Ah, float* Al, float* Bh, float* Bl, int B, int M_pad, int Kdim, int Dp, int m_valid, int n_valid,
+                    float scale, float* out, float* part, cudaStream_t stream) {
+  GemmParams g{};
+  g.M_pad = M_pad; g.N = Dp; g.m_valid = m_valid; g.n_valid = n_valid; g.slices = Kdim / 32; g.B = B;
+  gemm_shape(B, M_pad / 128, g.slices, &g.splits, &g.slices_per_split);
+  g.scale = g.splits == 1 ? scale : 1.f;
+  g.out = g.splits == 1 ? out : part;
+  CUtensorMap mah, mal, mbh, mbl;
+  if (int e = make_map_f32(&mah, Ah, Kdim, (int64_t)B * M_pad)) return e;
+  if (int e = make_map_f32(&mal, Al, Kdim, (int64_t)B * M_pad)) return e;
+  if (int e = make_map_f32(&mbh, Bh, Kdim, (int64_t)B * Dp, Dp)) return e;
+  if (int e = make_map_f32(&mbl, Bl, Kdim, (int64_t)B * Dp, Dp)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PF_CUDA(cudaFuncSetAttribute(corr_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGmSmemAlloc));
+    attr_set = true;
+  }
+  corr_tc_gemm_kernel<<<dim3(g.splits, M_pad / 128, B), kGmThreads, kGmSmemAlloc, stream>>>(mah, mal, mbh, mbl, g);
+  PF_LAUNCH_CHECK("corr_tc_gemm_kernel");
+  if (g.splits > 1) {
+    const int64_t total = (int64_t)B * m_valid * n_valid;
+    corr_tc_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(part, g.splits, B, M_pad, Dp, m_valid, n_valid, scale, out);
+    PF_LAUNCH_CHECK("corr_tc_reduce_kernel");
+  }
+  return POSFEAT_OK;
+}
+
+// g_q = scale * W K,  g_k = scale * W^T Q  with  W = P o (g.v - g.out)  (see corr_tc_fwd_kernel<1>)
+int corr_tc_bwd(const float* q, const float* k, const float* v, int v_batched, int B, int n, int m, int D, int C,
+                float scale, const float* out, const float* lse, const float* g_out, float* g_q, float* g_k, void* ws,
+                size_t ws_bytes, cudaStream_t stream) {
+  const int vb = v_batched ? B : 1;
+  CorrTcBwdWs w = carve_corr_tc_bwd(ws, B, n, m, D, vb);
+  PF_CHECK_ARG(ws && ((uintptr_t)ws & 255) == 0, "corr workspace must be 256-byte aligned");
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "corr backward workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  CorrTcParams p{};
+  p.B = B; p.n = n; p.m = m; p.D = D; p.C = C;
+  p.n_pad = pad128(n); p.m_pad = pad128(m);
+  p.atoms = (D + 31) / 32;
+  corr_tc_shape(B, n, m, &p.q_tiles, &p.k_tiles, &p.splits, &p.tiles_per_split);
+  p.sl2 = scale * 1.4426950408889634f;
+  p.v4 = w.v4; p.v_batched = v_batched;
+  p.g = g_out; p.o = out; p.lse = lse;
+  p.w_hi = w.wh; p.w_lo = w.wl; p.wt_hi = w.wth; p.wt_lo = w.wtl;
+  const int Dp = p.atoms * 32;
+  ProfScope prof(PROF_CORR_BWD, stream);
+  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.n_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(q, B, n, D, p.n_pad, Dp, w.qh, w.ql);
+  PF_LAUNCH_CHECK("corr_split_kernel(q)");
+  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.m_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(k, B, m, D, p.m_pad, Dp, w.kh, w.kl);
+  PF_LAUNCH_CHECK("corr_split_kernel(k)");
+  if (g_k) {
+    corr_split_t_kernel<<<dim3(p.n_pad / 32, Dp / 32, B), 256, 0, stream>>>(q, n, D, p.n_pad, Dp, w.qth, w.qtl);
+    PF_LAUNCH_CHECK("corr_split_t_kernel(q)");
+  }
+  if (g_q) {
+    corr_split_t_kernel<<<dim3(p.m_pad / 32, Dp / 32, B), 256, 0, stream>>>(k, m, D, p.m_pad, Dp, w.kth, w.ktl);
+    PF_LAUNCH_CHECK("corr_split_t_kernel(k)");
+  }
+  corr_padv_kernel<<<(int)std::min<int64_t>(((int64_t)vb * p.m_pad + 255) / 256, 148 * 8), 256, 0, stream>>>(v, vb, m, C, p.m_pad, w.v4);
+  PF_LAUNCH_CHECK("corr_padv_kernel");
+  CUtensorMap mqh, mql, mkh, mkl;
+  if (int e = make_map_f32(&mqh, w.qh, Dp, (int64_t)B * p.n_pad)) return e;
+  if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;
+  if (int e = make_map_f32(&mkh, w.kh, Dp, (int64_t)B * p.m_pad)) return e;
+  if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
+    attr_set = true;
+  }
+  corr_tc_fwd_kernel<1><<<dim3(p.splits, p.q_tiles, B), kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
+  PF_LAUNCH_CHECK("corr_tc_fwd_kernel<W>");
+  if (g_q)
+    if (int e = run_gemm(w.wh, w.wl, w.kth, w.ktl, B, p.n_pad, p.m_pad, Dp, n, D, scale, g_q, w.part, stream)) return e;
+  if (g_k)
+    if (int e = run_gemm(w.wth, w.wtl, w.qth, w.qtl, B, p.m_pad, p.n_pad, Dp, m, D, scale, g_k, w.part, stream)) return e;
   return POSFEAT_OK;
 }
 

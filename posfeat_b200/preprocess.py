@@ -119,9 +119,12 @@ class CorrExpect(torch.autograd.Function):
         gk = torch.empty_like(kd) if ctx.needs_input_grad[1] else None
         if gq is not None or gk is not None:
             with torch.cuda.device(qd.device):
+                nbytes = lib().posfeat_corr_expect_bwd_workspace_bytes(B, n, m, D, C)
+                ws = workspace("corr_bwd", nbytes, qd.device) if nbytes else None
                 check(lib().posfeat_corr_expect_bwd_f32(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), int(vd.dim() == 3),
                                                         B, n, m, D, C, ctx.scale, out.data_ptr(), lse.data_ptr(),
-                                                        g.data_ptr(), ptr(gq), ptr(gk), stream_ptr(qd.device)))
+                                                        g.data_ptr(), ptr(gq), ptr(gk), ptr(ws),
+                                                        ws.numel() if ws is not None else 0, stream_ptr(qd.device)))
         return gq, gk, None, None
 
 
