@@ -42,7 +42,9 @@ def test_window_expectation_golden(golden):
 
 
 @pytest.mark.parametrize("B,n,m,D,C,scale", [(2, 150, 170, 128, 4, 60.0), (1, 64, 64, 32, 2, 1.0),
-                                              (3, 33, 257, 100, 3, 10.0), (8, 512, 1200, 128, 4, 60.0)])
+                                              (3, 33, 257, 100, 3, 10.0), (8, 512, 1200, 128, 4, 60.0),
+                                              # >= 2^23 logits: backward on the tensor cores as well
+                                              (2, 300, 15000, 128, 4, 30.0), (1, 700, 13000, 96, 3, 10.0)])
 def test_dense_forward_backward_vs_torch(B, n, m, D, C, scale):
     import posfeat_b200.preprocess as PP
     g = torch.Generator().manual_seed(n + m)
