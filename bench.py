@@ -201,6 +201,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")             # at these levels NCCL prints a version banner to stdout;
+                                                     # this script's stdout is exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs
