@@ -62,7 +62,6 @@ struct DirParams {            // all arrays are batched over pairs: index = pair
   const MatStats* xstats;      // [pairs][2] -> element pair*2 + which (set up per direction)
   const MatStats* ystats;
   __half* table;               // [pairs][NXpad][pitch] chunk maxima, scaled by 1/(max|x| max|y|)
-  __half* tableT;              // optional transposed copy [pairs][pitch][NXpad] (matches-only path)
   int pitch;                   // y_tiles * 32 chunks per row
   int NX, NY, NXpad, NYpad;
   int splits, tiles_per_split, y_tiles;
@@ -289,11 +288,8 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int NY = d.NY;
       const size_t nxpad = (size_t)d.NXpad;
       __half* trow = d.table + ((size_t)q.pair * nxpad + row) * d.pitch + j * 8 + (size_t)q.t0 * 32;
-      unsigned short* tcol = d.tableT ? reinterpret_cast<unsigned short*>(d.tableT) +
-                                            ((size_t)q.pair * d.pitch + (size_t)q.t0 * 32 + j * 8) * nxpad + row
-                                      : nullptr;
-      const bool skipT = p.debug & 32, skipR = p.debug & 64;
-      for (int t = q.t0; t < q.t1; ++t, trow += 32, tcol += (tcol ? 32 * nxpad : 0)) {
+      const bool skipR = p.debug & 64;
+      for (int t = q.t0; t < q.t1; ++t, trow += 32) {
         mbar_wait(bar_acc_full + 8 * as, aph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + j * 64) + ((uint32_t)(quarter * 32) << 16);
@@ -314,14 +310,6 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (++as == 2) { as = 0; aph ^= 1; }
         hi = full ? reduce32<false>(v, c0 + 32, NY, scale) : reduce32<true>(v, c0 + 32, NY, scale);
         if (!skipR) *reinterpret_cast<uint4*>(trow) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        if (tcol && !skipT) {
-          // chunk-major copy: for a fixed chunk the 32 lanes (rows) write 64 contiguous bytes
-          unsigned short* tc = tcol;
-          const unsigned wv[4] = {lo.x, lo.y, hi.x, hi.y};
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8, tc += nxpad)
-            *tc = (unsigned short)((c8 & 1) ? (wv[c8 >> 1] >> 16) : (wv[c8 >> 1] & 0xffffu));
-        }
       }
     }
   }
@@ -431,6 +419,7 @@ struct RescoreArgs {
   float* top2;                            // kTop2 only: [pairs][NX][2] best and second best similarity (float32)
   // matches-only path (may be NULL): per-chunk minimum verification threshold and the mutual flags
   int* tmin;                              // [pairs][nchunks] ordered ints, pre-set to 0x7f7f7f7f
+  float* best8;                           // [pairs][NX][8] float32 similarities to the 8 columns of the winner's chunk
   unsigned char* mutual;                  // [pairs][NX], set to 1 here
   int nchunks;
 };
@@ -527,6 +516,7 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
 
   float m32 = -INFINITY;       // running float32 maximum over everything seen
   float r2 = -INFINITY;        // kTop2: running float32 runner-up (m32 is the running first)
+  float best_s32 = 0.f;        // this lane's column of the float32 similarities of the winner's chunk
   double bestv = -INFINITY;    // exact best
   int besti = 0x7fffffff;
   const float4* x4 = reinterpret_cast<const float4*>(&xs[w][0]);
@@ -614,6 +604,7 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
       need &= need - 1;
       exact_col(col0 + ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1));
     }
+    if ((besti >> 3) == (col0 >> 3)) best_s32 = s32;     // the winner moved into this chunk (a chunk is visited once)
   };
 
   // ---- pass 2: candidate chunks = table entries >= thr
@@ -643,6 +634,7 @@ tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
       }
     }
   }
+  if (a.best8 && (lane & 3) == 0) a.best8[((size_t)pair * d.NX + row) * kChunk + myc] = best_s32;
   if (lane == 0) {
     const int bj = besti == 0x7fffffff ? 0 : besti;
     a.nn[(size_t)pair * d.NX + row] = bj;
@@ -754,6 +746,7 @@ struct VerifyArgs {
   const int32_t* nn12;       // [pairs][NX]
   const int* comp_cnt;       // [pairs][nchunks]
   const int* comp;           // [pairs][nchunks][kCompCap]
+  const float* best8;        // [pairs][NX][8] from the rescoring kernel (valid for the row's own chunk)
   unsigned char* mutual;     // [pairs][NX]
   int nchunks;
 };
@@ -824,14 +817,16 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   const float* Yp = a.Y + pair * a.strideY;
   const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
   const float4* yv = &s_y[warp][0];
+  auto stage_y = [&]() {                 // the chunk's 8 columns -> shared memory (only needed to evaluate rows here)
 #pragma unroll
-  for (int r = 0; r < kChunk; ++r) {
-    const int jj = c * kChunk + r;
-    const float* yr = Yp + (int64_t)jj * a.ldy + lane * 4;
-    s_y[warp][r * 32 + lane] =
-        jj < d.NY ? make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncwarp();
+    for (int r = 0; r < kChunk; ++r) {
+      const int jj = c * kChunk + r;
+      const float* yr = Yp + (int64_t)jj * a.ldy + lane * 4;
+      s_y[warp][r * 32 + lane] =
+          jj < d.NY ? make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+  };
   auto load_row = [&](int row) {
     const float* xr = Xp + (int64_t)row * a.ldx + lane * 4;
     return make_float4(__ldg(xr), __ldg(xr + 1), __ldg(xr + 2), __ldg(xr + 3));
@@ -859,17 +854,31 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     const int* rows = a.comp + slot * kCompCap;
     const int iq = lane < total ? __ldg(rows + lane) : -1;
     const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
-    for (int r0 = 0; r0 < total; r0 += 4) {
-      float4 xr[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xr[k] = load_row(__shfl_sync(0xffffffffu, iq, min(r0 + k, total - 1)));
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (r0 + k < total) warp_chunk_dots_f32(xr[k], yv, lane, &s_e[warp][r0 + k][0]);
-    }
-    __syncwarp();
     const bool member = iq >= 0 && (jq >> 3) == c;
     if (!__any_sync(0xffffffffu, member)) return;
+    // rows matched into this chunk were already evaluated against its 8 columns by the rescoring kernel
+    if (member) {
+      const float4* b8 = reinterpret_cast<const float4*>(a.best8 + ((size_t)pair * d.NX + iq) * kChunk);
+      *reinterpret_cast<float4*>(&s_e[warp][lane][0]) = __ldg(b8);
+      *reinterpret_cast<float4*>(&s_e[warp][lane][4]) = __ldg(b8 + 1);
+    }
+    // the few other rows whose table entry reached the threshold are evaluated here
+    unsigned others = __ballot_sync(0xffffffffu, iq >= 0 && !member);
+    if (others) stage_y();
+    while (others) {
+      float4 xr[4];
+      int lk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lk[k] = others ? __ffs(others) - 1 : -1;
+        if (others) others &= others - 1;
+        if (lk[k] >= 0) xr[k] = load_row(__shfl_sync(0xffffffffu, iq, lk[k]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lk[k] >= 0) warp_chunk_dots_f32(xr[k], yv, lane, &s_e[warp][lk[k]][0]);
+    }
+    __syncwarp();
     const int cc = member ? jq - c * kChunk : 0;
     const float mine = s_e[warp][lane & 31][cc];
     bool lost = false;
@@ -880,6 +889,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     if (member && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
     return;
   }
+  stage_y();
   if (total <= kCompCap) {
     const int* rows = a.comp + slot * kCompCap;
     // long list: members in batches of 32 (one per lane), competitors streamed
@@ -1044,6 +1054,7 @@ struct TcWs {
   int pitch[2];
   // matches-only path
   float* best;
+  float* best8;
   int *tmin, *comp_cnt, *comp;
   unsigned char* mutual;
   size_t total;
@@ -1073,6 +1084,7 @@ static TcWs carve_tc(void* base, int P, int N, int M) {
   w.table[1] = (__half*)take(sizeof(__half) * P * Mp * w.pitch[1]);
   // matches-only path
   w.best = (float*)take(sizeof(float) * P * (size_t)N);
+  w.best8 = (float*)take(sizeof(float) * P * (size_t)N * kChunk);
   const size_t nch = (size_t)(M + kChunk - 1) / kChunk;
   w.tmin = (int*)take(sizeof(int) * P * nch * 2);            // tmin followed by comp_cnt
   w.comp_cnt = w.tmin + P * nch;
@@ -1157,7 +1169,6 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     d.xstats = w.stats + (dir ? 1 : 0);
     d.ystats = w.stats + (dir ? 0 : 1);
     d.table = w.table[dir];
-    d.tableT = nullptr;
     d.pitch = w.pitch[dir];
     d.NX = NX; d.NY = NY; d.NXpad = NXpad; d.NYpad = NYpad;
     d.y_tiles = yt;
@@ -1189,8 +1200,8 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     PF_CUDA(cudaMemsetAsync(w.comp_cnt, 0, sizeof(int) * (size_t)P * nchunks, stream));
   }
   RescoreArgs r0{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, one_dir ? w.best : nullptr, top12,
-                 one_dir ? w.tmin : nullptr, w.mutual, nchunks};
-  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, 0};
+                 one_dir ? w.tmin : nullptr, one_dir ? w.best8 : nullptr, w.mutual, nchunks};
+  RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
   const long long resc_warps = (long long)P * (N + (one_dir ? 0 : M));
   prof_begin(PROF_MNN_RESCORE, stream);
@@ -1211,7 +1222,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   tc_scan_kernel<<<dim3((N + scan_rows - 1) / scan_rows, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
   prof_end(PROF_MNN_SCAN, stream);
   PF_LAUNCH_CHECK("tc_scan_kernel");
-  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.mutual, nchunks};
+  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.best8, w.mutual, nchunks};
   prof_begin(PROF_MNN_VERIFY, stream);
   tc_verify_kernel<<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
   prof_end(PROF_MNN_VERIFY, stream);
