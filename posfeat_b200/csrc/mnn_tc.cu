@@ -429,17 +429,18 @@ struct RescoreArgs {
 // maximum and the chunk holding the best value outside it both satisfy that (two chunks have entries >= T2,
 // one of them is not the maximum's chunk, and entries are within delta/2 of the true chunk maxima), and
 // the runner-up is either in the maximum's chunk or is that other chunk's maximum.
-template <bool kTop2>
+// kTwoDir = false: only a0's rows exist (matches-only path); the argument block is then addressed statically
+// instead of through indexed constant-bank loads.
+template <bool kTop2, bool kTwoDir>
 __global__ void __launch_bounds__(256, 3)
 tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
   __shared__ __align__(16) float xs[8][kD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_pair = a0.d.NX + a1.d.NX;
-  const long long g = (long long)blockIdx.x * 8 + w;
-  const int pair = (int)(g / rows_pair);
-  if (pair >= pairs) return;
-  int row = (int)(g - (long long)pair * rows_pair);
-  const bool second = row >= a0.d.NX;
+  const int rows_pair = a0.d.NX + (kTwoDir ? a1.d.NX : 0);
+  const int pair = blockIdx.y;                     // grid: (row blocks of a pair, pairs)
+  int row = blockIdx.x * 8 + w;
+  if (row >= rows_pair) return;
+  const bool second = kTwoDir && row >= a0.d.NX;
   if (second) row -= a0.d.NX;
   const RescoreArgs& a = second ? a1 : a0;
   const DirParams& d = a.d;
@@ -1203,10 +1204,12 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
                  one_dir ? w.tmin : nullptr, one_dir ? w.best8 : nullptr, w.mutual, nchunks};
   RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
-  const long long resc_warps = (long long)P * (N + (one_dir ? 0 : M));
+  const dim3 resc_grid((unsigned)((N + (one_dir ? 0 : M) + 7) / 8), (unsigned)P);
+  if (P > 65535) return set_error(POSFEAT_EINVAL, "batched matcher: at most 65535 pairs per call");
   prof_begin(PROF_MNN_RESCORE, stream);
-  if (top12) tc_rescore_kernel<true><<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
-  else tc_rescore_kernel<false><<<(unsigned)((resc_warps + 7) / 8), 256, 0, stream>>>(r0, r1, P);
+  if (top12) tc_rescore_kernel<true, true><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
+  else if (one_dir) tc_rescore_kernel<false, false><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
+  else tc_rescore_kernel<false, true><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
   prof_end(PROF_MNN_RESCORE, stream);
   PF_LAUNCH_CHECK("tc_rescore_kernel");
   if (top12) return POSFEAT_OK;      // ratio-test callers apply their own acceptance rule to (nn, top2)
