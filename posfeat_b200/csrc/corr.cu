@@ -352,6 +352,75 @@ __device__ __forceinline__ float gather_dot(const float* __restrict__ fb, const 
   return warp_sum(dot);
 }
 
+
+// ---- window variant, "box" formulation (mode 0, channels-last map) -------------------------------------
+// The m window positions of a query are a dense little grid (12 x 16 taps about one pixel apart), so their
+// 4 m bilinear corners fall on only ~(w_x + 2)(w_y + 2) distinct pixels.  Because the dot product is linear,
+//   <q, sum_k w_k f_k> = sum_k w_k <q, f_k>,
+// the CTA first evaluates <q, f> once per pixel of the taps' bounding box (one coalesced 512-byte read each,
+// pixels outside the map count as zero = zeros padding) and then blends those scalars per tap: 3x fewer
+// descriptor reads than gathering every corner of every tap; the backward pass likewise accumulates one
+// scalar per pixel in shared memory before it touches g_fmap (3x fewer atomics).
+constexpr int kBoxMax = 1024;      // pixels in the bounding box handled this way (else: per-tap gather)
+
+struct BoxInfo { int xmin, ymin, bw, bh; };
+
+// bounding box of the corner pixels of all m taps (block-wide); returns false when it exceeds kBoxMax
+__device__ __forceinline__ bool window_box(const float* __restrict__ centre, const float* __restrict__ offsets, size_t qi,
+                                           int m, int h, int w, int (*red)[kWinThreads / 32], BoxInfo& box) {
+  int x0 = 1 << 30, x1 = -(1 << 30), y0 = 1 << 30, y1 = -(1 << 30);
+  for (int p = threadIdx.x; p < m; p += kWinThreads) {
+    const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+    const TapSet t = taps_of(pos.x, pos.y, h, w, 0);
+    x0 = min(x0, t.x0); x1 = max(x1, t.x0 + 1); y0 = min(y0, t.y0); y1 = max(y1, t.y0 + 1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = x0; red[1][warp] = x1; red[2][warp] = y0; red[3][warp] = y1; }
+  __syncthreads();
+  x0 = min(min(red[0][0], red[0][1]), min(red[0][2], red[0][3]));
+  x1 = max(max(red[1][0], red[1][1]), max(red[1][2], red[1][3]));
+  y0 = min(min(red[2][0], red[2][1]), min(red[2][2], red[2][3]));
+  y1 = max(max(red[3][0], red[3][1]), max(red[3][2], red[3][3]));
+  box.xmin = x0; box.ymin = y0; box.bw = x1 - x0 + 1; box.bh = y1 - y0 + 1;
+  return (int64_t)box.bw * box.bh <= kBoxMax;
+}
+
+// sd[e] = <q, f[pixel e]> for every pixel of the box (0 outside the map); D % 4 == 0, channels innermost
+__device__ __forceinline__ void box_dots(const float* __restrict__ fb, int D, int h, int w, int64_t sy, int64_t sx,
+                                         const BoxInfo& box, const float4 q4, float* __restrict__ sd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npix = box.bw * box.bh;
+  const bool act = lane * 4 < D;
+  for (int e0 = warp * 4; e0 < npix; e0 += (kWinThreads / 32) * 4) {
+    float d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k;
+      const int by = e / box.bw, bx = e - by * box.bw;
+      const int x = box.xmin + bx, y = box.ymin + by;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < npix && act && x >= 0 && x < w && y >= 0 && y < h)
+        f = __ldg(reinterpret_cast<const float4*>(fb + (int64_t)y * sy + (int64_t)x * sx) + lane);
+      d[k] = fmaf(f.w, q4.w, fmaf(f.z, q4.z, fmaf(f.y, q4.y, f.x * q4.x)));
+    }
+    // four warp sums with six shuffles: halve the value set while halving the lane set
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float k0 = (h16 ? d[2] : d[0]) + __shfl_xor_sync(0xffffffffu, h16 ? d[0] : d[2], 16);
+    float k1 = (h16 ? d[3] : d[1]) + __shfl_xor_sync(0xffffffffu, h16 ? d[1] : d[3], 16);
+    float r = (h8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    const int idx = (h16 ? 2 : 0) + (h8 ? 1 : 0);
+    if ((lane & 7) == 0 && e0 + idx < npix) sd[e0 + idx] = r;
+  }
+}
+
 // one CTA (4 warps) per query
 __global__ void __launch_bounds__(kWinThreads)
 window_expect_fwd_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
@@ -370,12 +439,32 @@ window_expect_fwd_kernel(const float* __restrict__ fmap, int D, int h, int w, in
     const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
     qv[j] = c < D ? __ldg(q + qi * D + c) : 0.f;
   }
-  for (int p = warp; p < m; p += kWinThreads / 32) {
-    const float2 pos = win_pos(mode, centre, offsets, qi, p, m);
-    const TapSet t = taps_of(pos.x, pos.y, h, w, mode);
-    float sv[kWinCPL];
-    const float d = gather_dot(fb, t, D, sc, sy, sx, qv, lane, sv);
-    if (lane == 0) { z[p] = d; px[p] = pos.x; py[p] = pos.y; }
+  __shared__ float sd[kBoxMax];
+  __shared__ int ired[4][kWinThreads / 32];
+  BoxInfo box;
+  bool boxed = false;
+  if (mode == 0 && sc == 1 && (D & 3) == 0 && D <= 128 && (sx & 3) == 0 && (sy & 3) == 0 && (sb & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(fmap) & 15) == 0)
+    boxed = window_box(centre, offsets, qi, m, h, w, ired, box);          // block uniform
+  if (boxed) {
+    const float4 q4 = make_float4(qv[0], qv[1], qv[2], qv[3]);            // sc == 1: lane holds channels 4*lane .. +3
+    box_dots(fb, D, h, w, sy, sx, box, q4, sd);
+    __syncthreads();
+    for (int p = threadIdx.x; p < m; p += kWinThreads) {
+      const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+      const TapSet t = taps_of(pos.x, pos.y, h, w, 0);
+      const float* s0 = sd + (t.y0 - box.ymin) * box.bw + (t.x0 - box.xmin);
+      z[p] = s0[0] * t.w00 + s0[1] * t.w01 + s0[box.bw] * t.w10 + s0[box.bw + 1] * t.w11;
+      px[p] = pos.x; py[p] = pos.y;
+    }
+  } else {
+    for (int p = warp; p < m; p += kWinThreads / 32) {
+      const float2 pos = win_pos(mode, centre, offsets, qi, p, m);
+      const TapSet t = taps_of(pos.x, pos.y, h, w, mode);
+      float sv[kWinCPL];
+      const float d = gather_dot(fb, t, D, sc, sy, sx, qv, lane, sv);
+      if (lane == 0) { z[p] = d; px[p] = pos.x; py[p] = pos.y; }
+    }
   }
   __syncthreads();
   // softmax statistics over the m positions (block reduction)
@@ -468,6 +557,46 @@ window_expect_bwd_kernel(const float* __restrict__ fmap, int D, int h, int w, in
     qv[j] = c < D ? __ldg(q + qi * D + c) : 0.f;
     gq[j] = 0.f;
   }
+  __shared__ float gpix[kBoxMax];
+  __shared__ int ired[4][kWinThreads / 32];
+  BoxInfo box;
+  bool boxed = false;
+  if (sc == 1 && (D & 3) == 0 && D <= 128 && (sx & 3) == 0 && (sy & 3) == 0 && (sb & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(fmap) & 15) == 0 && (reinterpret_cast<uintptr_t>(g_fmap) & 15) == 0)
+    boxed = window_box(centre, offsets, qi, m, h, w, ired, box);          // block uniform
+  if (boxed) {
+    // one scalar per pixel of the box: gpix = sum over taps of dz * bilinear weight
+    const int npix = box.bw * box.bh;
+    for (int e = threadIdx.x; e < npix; e += kWinThreads) gpix[e] = 0.f;
+    __syncthreads();
+    for (int p = threadIdx.x; p < m; p += kWinThreads) {
+      const float d = dz[p];
+      if (d == 0.f) continue;
+      const float2 pos = win_pos(0, centre, offsets, qi, p, m);
+      const TapSet t = taps_of(pos.x, pos.y, h, w, 0);
+      float* g0 = gpix + (t.y0 - box.ymin) * box.bw + (t.x0 - box.xmin);
+      if (t.in00) atomicAdd(g0, d * t.w00);
+      if (t.in01) atomicAdd(g0 + 1, d * t.w01);
+      if (t.in10) atomicAdd(g0 + box.bw, d * t.w10);
+      if (t.in11) atomicAdd(g0 + box.bw + 1, d * t.w11);
+    }
+    __syncthreads();
+    const float4 q4 = make_float4(qv[0], qv[1], qv[2], qv[3]);
+    const bool act = lane * 4 < D;
+    for (int e = warp; e < npix; e += kWinThreads / 32) {
+      const float gcoef = gpix[e];
+      if (gcoef == 0.f) continue;                                          // warp uniform (also every pixel outside the map)
+      const int by = e / box.bw, bx = e - by * box.bw;
+      const int64_t off = (int64_t)(box.ymin + by) * sy + (int64_t)(box.xmin + bx) * sx;
+      if (act) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(fb + off) + lane);
+        gq[0] = fmaf(gcoef, f.x, gq[0]); gq[1] = fmaf(gcoef, f.y, gq[1]);
+        gq[2] = fmaf(gcoef, f.z, gq[2]); gq[3] = fmaf(gcoef, f.w, gq[3]);
+        atomicAdd(reinterpret_cast<float4*>(gfb + off) + lane,
+                  make_float4(gcoef * q4.x, gcoef * q4.y, gcoef * q4.z, gcoef * q4.w));
+      }
+    }
+  } else
   for (int p = warp; p < m; p += kWinThreads / 32) {
     const float d = dz[p];
     if (d == 0.f) continue;
