@@ -229,6 +229,19 @@ int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, 
                                 const float* out, const float* lse, const float* g_out,
                                 float* g_q, float* g_k, void* workspace, size_t ws_bytes, void* stream);
 
+/* Epipolar line search in one launch: epipolar_line_search, losses/preprocess_utils.py:662-694, with
+ * get_endpoints (:697-719) folded in.  coord_px [B,n,2] pixel coordinates in an img_h x img_w image,
+ * Fmat [B,3,3].  Per query: the epipolar line is clipped to the image rectangle (ends [B,n,4] =
+ * normalised x1,y1,x2,y2; valid [B,n] = exactly two border intersections inside), line_step positions
+ * between the endpoints are sampled from fmap (bilinear, border padding), dotted with q and soft-maxed.
+ * exp_soft [B,n,2] soft expectation; nn_xy [B,n,2] sum of the positions attaining the largest
+ * probability; m2 [B,n,2] = sum_p prob_p * pos_p^2; prob [B,n,line_step] optional (may be NULL). */
+int posfeat_line_search_f32(const float* fmap, int B, int D, int h, int w,
+                            int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                            const float* q, const float* coord_px, const float* Fmat, int n,
+                            int img_h, int img_w, int line_step, float* ends, unsigned char* valid,
+                            float* exp_soft, float* nn_xy, float* m2, float* prob, void* stream);
+
 /* Window / line variant.  mode 0: get_expected_correspondence_within_window,
  * losses/preprocess_utils.py:721-758 -- positions = centre [B,n,2] + offsets [m,2]
  * (the gen_grid(-ws,ws,...) table), grid_sample padding 'zeros'.  mode 1: the

@@ -499,6 +499,125 @@ window_expect_fwd_kernel(const float* __restrict__ fmap, int D, int h, int w, in
     for (int p = threadIdx.x; p < m; p += kWinThreads) prob[qi * m + p] = expf(z[p] - mx) * inv;
 }
 
+// ---- epipolar line search in one kernel (epipolar_line_search, losses/preprocess_utils.py:662-694, with
+// get_endpoints :697-719 folded in).  Per query: the epipolar line F x~ is clipped to the image rectangle
+// (two of the four border intersections must lie inside, else the left/right intersections are used and the
+// query is flagged invalid), m positions between the two endpoints are sampled (bilinear, border padding),
+// dotted with the query and soft-maxed.  Outputs per query: the endpoints, the validity flag, the soft
+// expectation, the sum of the positions that attain the largest probability (the reference's
+// `(prob == prob.max) * grids` sum) and sum_p prob_p * g_p^2 for the variance; the [B,n,m,D] gathered tensor
+// and, unless asked for, the probabilities are never written.
+__global__ void __launch_bounds__(kWinThreads)
+line_search_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                   const float* __restrict__ q, const float* __restrict__ coord_px, const float* __restrict__ Fmat,
+                   int n, int imh, int imw, int m, float* __restrict__ ends_out, unsigned char* __restrict__ valid_out,
+                   float* __restrict__ exp_soft, float* __restrict__ nn_xy, float* __restrict__ m2_out,
+                   float* __restrict__ prob) {
+  __shared__ float z[kWinMaxPts], px[kWinMaxPts], py[kWinMaxPts];
+  __shared__ float red[8][kWinThreads / 32];
+  __shared__ float s_ends[4];
+  const int b = blockIdx.y, i = blockIdx.x;
+  const size_t qi = (size_t)b * n + i;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    // line = F [x, y, 1]^T accumulated like a K = 3 SGEMM: fma(F2, 1, fma(F1, y, F0 * x))
+    const float* F = Fmat + (size_t)b * 9;
+    const float x = coord_px[qi * 2], y = coord_px[qi * 2 + 1];
+    const float la = __fadd_rn(__fmaf_rn(F[1], y, __fmul_rn(F[0], x)), F[2]);
+    const float lb = __fadd_rn(__fmaf_rn(F[4], y, __fmul_rn(F[3], x)), F[5]);
+    const float lc = __fadd_rn(__fmaf_rn(F[7], y, __fmul_rn(F[6], x)), F[8]);
+    const float wm = (float)(imw - 1), hm = (float)(imh - 1);
+    float ptx[4], pty[4];
+    ptx[0] = 0.f;  pty[0] = __fdiv_rn(-lc, lb);                                             // left border
+    ptx[1] = wm;   pty[1] = __fdiv_rn(-__fadd_rn(__fmul_rn(la, wm), lc), lb);               // right border
+    ptx[2] = __fdiv_rn(-__fadd_rn(__fmul_rn(lb, hm), lc), la); pty[2] = hm;                 // y = h - 1
+    ptx[3] = __fdiv_rn(-lc, la); pty[3] = 0.f;                                              // y = 0
+    bool in[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      in[k] = ptx[k] >= 0.f && ptx[k] <= wm && pty[k] >= 0.f && pty[k] <= hm;
+      cnt += in[k];
+    }
+    const bool valid = cnt == 2;
+    if (!valid) { in[0] = in[1] = true; in[2] = in[3] = false; }
+    float e[4];
+    int o = 0;
+    const float cx = __fmul_rn(wm, 0.5f), cy = __fmul_rn(hm, 0.5f);     // (w-1)/2, (h-1)/2
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (in[k] && o < 4) {
+        e[o++] = __fdiv_rn(__fsub_rn(ptx[k], cx), cx);
+        e[o++] = __fdiv_rn(__fsub_rn(pty[k], cy), cy);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_ends[k] = e[k]; ends_out[qi * 4 + k] = e[k]; }
+    valid_out[qi] = valid ? 1 : 0;
+  }
+  __syncthreads();
+  const float e0 = s_ends[0], e1 = s_ends[1], e2 = s_ends[2], e3 = s_ends[3];
+  const float* fb = fmap + b * sb;
+  float qv[kWinCPL];
+#pragma unroll
+  for (int j = 0; j < kWinCPL; ++j) {
+    const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
+    qv[j] = c < D ? __ldg(q + qi * D + c) : 0.f;
+  }
+  const float step = 1.0f / (float)(m - 1);
+  for (int p = warp; p < m; p += kWinThreads / 32) {
+    const float t = (p < m / 2) ? step * (float)p : 1.0f - step * (float)(m - 1 - p);     // torch.linspace(0, 1, m)
+    const float gx = __fadd_rn(__fmul_rn(e2 - e0, t), e0), gy = __fadd_rn(__fmul_rn(e3 - e1, t), e1);
+    const TapSet ts = taps_of(gx, gy, h, w, 1);
+    float sv[kWinCPL];
+    const float d = gather_dot(fb, ts, D, sc, sy, sx, qv, lane, sv);
+    if (lane == 0) { z[p] = d; px[p] = gx; py[p] = gy; }
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) mx = fmaxf(mx, z[p]);
+  mx = warp_max(mx);
+  if (lane == 0) red[0][warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0][0], red[0][1]), fmaxf(red[0][2], red[0][3]));
+  float se = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) se += expf(z[p] - mx);
+  se = warp_sum(se);
+  if (lane == 0) red[1][warp] = se;
+  __syncthreads();
+  const float inv = 1.f / (red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+  // probabilities as they would be stored; their maximum decides the nearest-neighbour position(s)
+  float pm = 0.f, sxv = 0.f, syv = 0.f, sxx = 0.f, syy = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads) {
+    const float pr = expf(z[p] - mx) * inv;
+    z[p] = pr;
+    pm = fmaxf(pm, pr);
+    sxv = fmaf(pr, px[p], sxv); syv = fmaf(pr, py[p], syv);
+    sxx = __fadd_rn(sxx, __fmul_rn(__fmul_rn(px[p], px[p]), pr));
+    syy = __fadd_rn(syy, __fmul_rn(__fmul_rn(py[p], py[p]), pr));
+  }
+  pm = warp_max(pm); sxv = warp_sum(sxv); syv = warp_sum(syv); sxx = warp_sum(sxx); syy = warp_sum(syy);
+  if (lane == 0) { red[2][warp] = pm; red[3][warp] = sxv; red[4][warp] = syv; red[5][warp] = sxx; red[6][warp] = syy; }
+  __syncthreads();
+  pm = fmaxf(fmaxf(red[2][0], red[2][1]), fmaxf(red[2][2], red[2][3]));
+  float nx = 0.f, ny = 0.f;
+  for (int p = threadIdx.x; p < m; p += kWinThreads)
+    if (z[p] == pm) { nx += px[p]; ny += py[p]; }
+  nx = warp_sum(nx); ny = warp_sum(ny);
+  __syncthreads();
+  if (lane == 0) { red[0][warp] = nx; red[1][warp] = ny; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    exp_soft[qi * 2 + 0] = red[3][0] + red[3][1] + red[3][2] + red[3][3];
+    exp_soft[qi * 2 + 1] = red[4][0] + red[4][1] + red[4][2] + red[4][3];
+    nn_xy[qi * 2 + 0] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    nn_xy[qi * 2 + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    m2_out[qi * 2 + 0] = red[5][0] + red[5][1] + red[5][2] + red[5][3];
+    m2_out[qi * 2 + 1] = red[6][0] + red[6][1] + red[6][2] + red[6][3];
+  }
+  if (prob)
+    for (int p = threadIdx.x; p < m; p += kWinThreads) prob[qi * m + p] = z[p];
+}
+
 // backward of the window variant (mode 0): g_q and g_fmap from (g_exp, g_std)
 __global__ void __launch_bounds__(kWinThreads)
 window_expect_bwd_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
@@ -721,6 +840,23 @@ extern "C" int posfeat_window_expect_fwd_f32(const float* fmap, int B, int D, in
   window_expect_fwd_kernel<<<grid, kWinThreads, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, q, centre, n, offsets, m, mode,
                                                               exp_xy, std_out, prob, lse);
   PF_LAUNCH_CHECK("window_expect_fwd_kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_line_search_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,
+                                       int64_t sx, const float* q, const float* coord_px, const float* Fmat, int n,
+                                       int img_h, int img_w, int line_step, float* ends, unsigned char* valid,
+                                       float* exp_soft, float* nn_xy, float* m2, float* prob, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_window(fmap, B, D, h, w, q, coord_px, n, line_step)) return e;
+  PF_CHECK_ARG(Fmat && ends && valid && exp_soft && nn_xy && m2, "NULL pointer");
+  PF_CHECK_ARG(line_step >= 2 && img_h >= 2 && img_w >= 2, "line search needs at least 2 samples and a 2x2 image");
+  PF_CHECK_ARG(sc == 1 ? (D % kWinCPL == 0 || D <= 32 * kWinCPL) : true, "bad D");
+  dim3 grid(n, B);
+  ProfScope prof(PROF_WIN_FWD, stream);
+  line_search_kernel<<<grid, kWinThreads, 0, stream>>>(fmap, D, h, w, sb, sc, sy, sx, q, coord_px, Fmat, n, img_h, img_w,
+                                                       line_step, ends, valid, exp_soft, nn_xy, m2, prob);
+  PF_LAUNCH_CHECK("line_search_kernel");
   return POSFEAT_OK;
 }
 

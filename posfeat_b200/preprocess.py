@@ -245,38 +245,37 @@ def epipolar_line_search(coord, Fmat, feat1, featmap2, h, w, line_step=100, use_
     torch.rand draw so runs can be reproduced."""
     B, d, h2, w2 = featmap2.shape
     n = coord.shape[1]
-    e1, e2, valid = get_endpoints(coord, Fmat, h, w)
-    ends = torch.cat([e1, e2], -1).float().contiguous()                   # [B,n,4]
     qd = _f32c(feat1)
+    cd = _f32c(coord)
+    Fd = _f32c(Fmat).reshape(B, 9)
     fd = featmap2.detach().float()
     if d >= 32:
         fd = fd.contiguous(memory_format=torch.channels_last)     # one 512-byte read per tap (see WindowExpect)
     elif not fd.is_contiguous():
         fd = fd.contiguous()
     dev = qd.device
+    ends = torch.empty((B, n, 4), dtype=torch.float32, device=dev)
+    valid_u8 = torch.empty((B, n), dtype=torch.uint8, device=dev)
     exp_soft = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
-    std_soft = torch.empty((B, n), dtype=torch.float32, device=dev)
-    prob = torch.empty((B, n, line_step), dtype=torch.float32, device=dev)
-    lse = torch.empty((B, n), dtype=torch.float32, device=dev)
+    nn_xy = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
+    m2 = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
+    prob = torch.empty((B, n, line_step), dtype=torch.float32, device=dev) if visualize else None
+    # one launch: endpoints (get_endpoints), the line_step samples, softmax, and the reductions the
+    # reference takes over the [B,n,line_step] tensors afterwards
     with torch.cuda.device(dev):
-        check(lib().posfeat_window_expect_fwd_f32(fd.data_ptr(), B, d, h2, w2, fd.stride(0), fd.stride(1), fd.stride(2),
-                                                  fd.stride(3), qd.data_ptr(), ends.data_ptr(), n, 0, line_step, 1,
-                                                  exp_soft.data_ptr(), std_soft.data_ptr(), prob.data_ptr(),
-                                                  lse.data_ptr(), stream_ptr(dev)))
-    t = torch.linspace(0., 1., line_step, device=dev)
-    grids = (e2 - e1)[:, :, None, :] * t[None, None, :, None] + e1[:, :, None, :]          # B,n,step,2
-    if use_nn:
-        mask = prob == prob.max(-1, True)[0]
-        expected = (mask.unsqueeze(-1) * grids).sum(2)
-    else:
-        expected = exp_soft
+        check(lib().posfeat_line_search_f32(fd.data_ptr(), B, d, h2, w2, fd.stride(0), fd.stride(1), fd.stride(2),
+                                            fd.stride(3), qd.data_ptr(), cd.data_ptr(), Fd.data_ptr(), n, int(h), int(w),
+                                            int(line_step), ends.data_ptr(), valid_u8.data_ptr(), exp_soft.data_ptr(),
+                                            nn_xy.data_ptr(), m2.data_ptr(), ptr(prob), stream_ptr(dev)))
+    valid = valid_u8.bool()
+    expected = nn_xy if use_nn else exp_soft          # nn: sum of the positions whose probability is the maximum
     expected_org = expected
     if loc_rand:
         u = jitter if jitter is not None else torch.rand(expected.shape)
         expected = expected + 0.707 * window_size * (2 * u.type_as(expected) - 1)
     border = (expected[:, :, 0] >= -1) & (expected[:, :, 0] <= 1) & (expected[:, :, 1] >= -1) & (expected[:, :, 1] <= 1)
     valid = valid & border
-    var = torch.sum(grids ** 2 * prob.unsqueeze(-1), dim=2) - expected ** 2
+    var = m2 - expected ** 2                            # m2 = sum_p prob_p * grid_p^2 (from the kernel)
     std = torch.sum(torch.sqrt(torch.clamp(var, min=1e-10)), -1)
     if visualize:
         return expected, expected_org, valid, std, prob

@@ -165,3 +165,42 @@ def test_preprocess_line2window_golden(golden):
     loss.backward()
     assert rel_err(xf1.grad.cpu(), g["gxf1"]) < 2e-3
     assert rel_err(xf2.grad.cpu(), g["gxf2"]) < 2e-3
+
+
+def test_epipolar_line_search_vs_torch():
+    """The fused kernel (endpoints + line samples + softmax + reductions) against the reference's sequence of
+    tensor ops (losses/preprocess_utils.py:662-719) written with torch: get_endpoints, grid_sample with border
+    padding, softmax, nearest-neighbour position, variance."""
+    import torch.nn.functional as F
+    import posfeat_b200.preprocess as PP
+    g = torch.Generator().manual_seed(23)
+    B, n, D, h2, w2, H, W, steps, ws = 2, 300, 128, 60, 80, 240, 320, 100, 0.125
+    q = F.normalize(torch.randn(B, n, D, generator=g), dim=-1).cuda()
+    fm = (20 * F.normalize(torch.randn(B, D, h2, w2, generator=g), dim=1)).cuda()
+    coord = torch.stack([torch.rand(B, n, generator=g) * (W - 1), torch.rand(B, n, generator=g) * (H - 1)], -1).cuda()
+    Fm = torch.randn(B, 3, 3, generator=g).cuda()
+    Fm[:, 2, 2] *= 100                      # lines that cross the image for most points
+    jit = torch.rand(B, n, 2, generator=g).cuda()
+    exp_, org_, valid_, std_, prob_ = PP.epipolar_line_search(coord, Fm, q, fm, H, W, line_step=steps, window_size=ws,
+                                                                jitter=jit, visualize=True)
+    # torch restatement
+    e1, e2, valid = PP.get_endpoints(coord, Fm, H, W)
+    t = torch.linspace(0., 1., steps, device="cuda")
+    grids = (e2 - e1)[:, :, None, :] * t[None, None, :, None] + e1[:, :, None, :]
+    samp = F.grid_sample(fm, grids, padding_mode="border", align_corners=False).permute(0, 2, 3, 1)
+    prob = torch.softmax((q.unsqueeze(-2) * samp).sum(-1), -1)
+    mask = prob == prob.max(-1, True)[0]
+    org = (mask.unsqueeze(-1) * grids).sum(2)
+    exp = org + 0.707 * ws * (2 * jit - 1)
+    border = (exp[..., 0] >= -1) & (exp[..., 0] <= 1) & (exp[..., 1] >= -1) & (exp[..., 1] <= 1)
+    var = torch.sum(grids ** 2 * prob.unsqueeze(-1), dim=2) - exp ** 2
+    std = torch.sum(torch.sqrt(torch.clamp(var, min=1e-10)), -1)
+    assert int(valid.sum()) > 0.5 * B * n
+    same_valid = (valid_ == (valid & border))
+    assert float(same_valid.float().mean()) > 0.995          # a border intersection may sit exactly on the rectangle
+    ok = same_valid & valid
+    assert rel_err(prob_[ok].cpu(), prob[ok].cpu()) < 2e-4    # logits of magnitude 20: exp amplifies 1e-6
+    agree = ok & ((org_ - org).abs().max(-1)[0] < 1e-5)       # near-tied maxima may pick the neighbouring sample
+    assert float(agree.float().sum() / ok.float().sum()) > 0.99
+    np.testing.assert_allclose(exp_[agree].cpu().numpy(), exp[agree].cpu().numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(std_[agree].cpu().numpy(), std[agree].cpu().numpy(), rtol=1e-3, atol=2e-3)
