@@ -335,6 +335,25 @@ __device__ __forceinline__ float gather_dot(const float* __restrict__ fb, const 
                                             float (&sv)[kWinCPL]) {
   const float* base = fb + (int64_t)t.y0 * sy + (int64_t)t.x0 * sx;
   float dot = 0.f;
+  if (sc == 1 && ((sx | sy) & 3) == 0 && (reinterpret_cast<uintptr_t>(fb) & 15) == 0 && (D & 3) == 0) {
+    // channels innermost: one 128-bit load per corner and lane
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a00 = z4, a01 = z4, a10 = z4, a11 = z4;
+    if (lane * 4 < D) {
+      const float4* pc = reinterpret_cast<const float4*>(base) + lane;
+      if (t.in00) a00 = __ldg(pc);
+      if (t.in01) a01 = __ldg(reinterpret_cast<const float4*>(base + sx) + lane);
+      if (t.in10) a10 = __ldg(reinterpret_cast<const float4*>(base + sy) + lane);
+      if (t.in11) a11 = __ldg(reinterpret_cast<const float4*>(base + sy + sx) + lane);
+    }
+    sv[0] = a00.x * t.w00 + a01.x * t.w01 + a10.x * t.w10 + a11.x * t.w11;
+    sv[1] = a00.y * t.w00 + a01.y * t.w01 + a10.y * t.w10 + a11.y * t.w11;
+    sv[2] = a00.z * t.w00 + a01.z * t.w01 + a10.z * t.w10 + a11.z * t.w11;
+    sv[3] = a00.w * t.w00 + a01.w * t.w01 + a10.w * t.w10 + a11.w * t.w11;
+#pragma unroll
+    for (int j = 0; j < kWinCPL; ++j) dot = fmaf(sv[j], qv[j], dot);
+    return warp_sum(dot);
+  }
 #pragma unroll
   for (int j = 0; j < kWinCPL; ++j) {
     const int c = (sc == 1) ? lane * kWinCPL + j : lane + 32 * j;
