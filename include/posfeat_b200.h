@@ -229,6 +229,20 @@ int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, 
                                 const float* out, const float* lse, const float* g_out,
                                 float* g_q, float* g_k, void* workspace, size_t ws_bytes, void* stream);
 
+/* DiskLoss dense affinity, losses/kploss.py:158-182 (second training stage): with A = T*<q_i,k_j> - T,
+ * p_ij = softmax_j(A)_ij * softmax_i(A)_ij and log p_ij the sum of the two log-softmaxes, computes per row i
+ *   rows_out[b,i] = { sum_j acc r p (log p + logp_i + logp_j),  sum_j acc r p,  sum_j p,  max_j p }
+ * without materialising any [B,n,m] tensor (tcgen05 kind::tf32, hi/lo operand split).  rowtab [B,n,8] /
+ * coltab [B,m,8] hold per point {lse, la, lb, lc, x, y, logp, accept}: lse = logsumexp of the point's row
+ * (column) of T*<q,k> (from posfeat_corr_expect_fwd_f32 with scale T), (la,lb,lc) its normalised epipolar
+ * line in the other image, (x,y) its pixel coordinates, logp / accept from the keypoint sampler.
+ * reward r: constant (good/bad by |line.point| < thr on both sides, kploss.py:52-88) or dynamic (:90-129). */
+size_t posfeat_dual_softmax_reward_workspace_bytes(int B, int n, int m, int D);
+int posfeat_dual_softmax_reward_f32(const float* q, const float* k, const float* rowtab, const float* coltab,
+                                    int B, int n, int m, int D, float temperature, float thr_own,
+                                    float thr_other, float good_reward, float bad_reward, int dynamic_reward,
+                                    float* rows_out, void* workspace, size_t ws_bytes, void* stream);
+
 /* Epipolar line search in one launch: epipolar_line_search, losses/preprocess_utils.py:662-694, with
  * get_endpoints (:697-719) folded in.  coord_px [B,n,2] pixel coordinates in an img_h x img_w image,
  * Fmat [B,3,3].  Per query: the epipolar line is clipped to the image rectangle (ends [B,n,4] =

@@ -292,9 +292,49 @@ def golden_preprocess():
     print("preprocess ok; loss", float(loss), "valid", processed["valid_epi1"].float().mean().item())
 
 
+def golden_disk():
+    """DiskLoss (losses/kploss.py) on small maps: the random point samples are drawn once with the
+    reference's own point_sample and replayed, so that every implementation sees the same points."""
+    from losses.kploss import DiskLoss
+    g = gen(707)
+    torch.manual_seed(707)
+    b, h, w, d = 2, 64, 96, 32
+    cfg = dict(grid_size=8, loss_distance="cos", temperature_base=60, temperature_max=60,
+               epipolar_reward="constant_reward", reward_config=dict(reward_thr=2, rescale_thr=False),
+               cor_detach=True, good_reward=1, bad_reward=-0.25, kp_penalty=-0.001, match_grad=False)
+    out = {}
+    for tag, reward in (("const", "constant_reward"), ("dyn", "dynamic_reward")):
+        cfg["epipolar_reward"] = reward
+        loss_mod = DiskLoss(cfg)
+        kp1 = torch.randn(b, 1, h, w, generator=g).requires_grad_(True)
+        kp2 = torch.randn(b, 1, h, w, generator=g).requires_grad_(True)
+        xf1 = torch.randn(b, d, h // 4, w // 4, generator=g)
+        xf2 = xf1 + 0.3 * torch.randn(b, d, h // 4, w // 4, generator=g)
+        # a fundamental matrix of a pure horizontal shift: x2 = x1 + 3  (F = [t]_x), so matches are plentiful
+        F1 = torch.tensor([[0., 0., 0.], [0., 0., -1.], [0., 1., 0.]]).repeat(b, 1, 1)
+        F2 = F1.transpose(1, 2).contiguous()
+        s1 = loss_mod.point_sample(kp1)
+        s2 = loss_mod.point_sample(kp2)
+        draws = iter([s1, s2])
+        loss_mod.point_sample = lambda kp_map: next(draws)
+        inputs = {"F1": F1, "F2": F2}
+        outputs = {"epoch": 0, "preds1": {"local_point": kp1, "local_map": xf1}, "preds2": {"local_point": kp2, "local_map": xf2}}
+        loss, comp = loss_mod(inputs, outputs, None)
+        loss.backward()
+        out.update({f"{tag}/kp1": kp1.detach().numpy(), f"{tag}/kp2": kp2.detach().numpy(), f"{tag}/xf1": xf1.numpy(),
+                    f"{tag}/xf2": xf2.numpy(), f"{tag}/F1": F1.numpy(), f"{tag}/F2": F2.numpy(),
+                    f"{tag}/coord1": s1[0].detach().numpy(), f"{tag}/logp1": s1[1].detach().numpy(), f"{tag}/acc1": s1[2].numpy(),
+                    f"{tag}/coord2": s2[0].detach().numpy(), f"{tag}/logp2": s2[1].detach().numpy(), f"{tag}/acc2": s2[2].numpy(),
+                    f"{tag}/loss": loss.detach().numpy(), f"{tag}/g_kp1": kp1.grad.numpy(), f"{tag}/g_kp2": kp2.grad.numpy()})
+        for k, v in comp.items():
+            out[f"{tag}/comp/{k}"] = np.asarray(v.detach().numpy() if torch.is_tensor(v) else v)
+    np.savez_compressed(os.path.join(OUT, "disk.npz"), **out)
+    print("disk ok", float(out["const/loss"]), float(out["dyn/loss"]))
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])                      # e.g. `python oracle/make_golden.py detect_ext`
-    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_preprocess):
+    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_preprocess, golden_disk):
         if not only or fn.__name__[len("golden_"):] in only:
             fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

@@ -470,3 +470,50 @@ def grid_softmax_expectation(feat1, feat2, coord1, coord2, coord1_n, coord2_n,
     std2 = np.sqrt(np.clip(p21.transpose(0, 2, 1) @ (c1n ** 2) - loc2_n ** 2,
                            1e-6, None)).sum(-1)
     return loc1, loc2, std1, std2
+
+
+# --------------------------------------------------------------------------
+# DiskLoss dense affinity (losses/kploss.py:52-88, :158-196), everything after the random point sampling
+# --------------------------------------------------------------------------
+def disk_loss_dense(feat1, feat2, coord1, coord2, F1, F2, logp1, logp2, acc1, acc2, T, reward_thr=2.0,
+                    good_reward=1.0, bad_reward=-0.25, kp_penalty=-0.001, dynamic=False):
+    """feat [b,m,d] / [b,n,d] float32 (already normalised), coord pixel xy, F [b,3,3], logp / acc [b,m] / [b,n].
+    Returns (loss, dict of the reference's components, dloss/dlogp1, dloss/dlogp2) in float64."""
+    f1, f2 = np.asarray(feat1, np.float64), np.asarray(feat2, np.float64)
+    b, m, _ = f1.shape
+    n = f2.shape[1]
+    aff = -T * (1.0 - f1 @ f2.transpose(0, 2, 1))                      # kploss.py:161-166
+
+    def logsoftmax(z, axis):
+        z = z - z.max(axis, keepdims=True)
+        return z - np.log(np.exp(z).sum(axis, keepdims=True))
+    lr, lc = logsoftmax(aff, 2), logsoftmax(aff, 1)                     # cat_I.logits, cat_T.logits^T
+    p, logp = np.exp(lr + lc), lr + lc                                   # dense_p, dense_logp
+
+    def lines(F, c):
+        ch = np.concatenate([c, np.ones_like(c[..., :1])], -1).astype(np.float64)       # b,k,3
+        l = np.einsum("bij,bkj->bki", np.asarray(F, np.float64), ch)
+        return l / np.maximum(np.linalg.norm(l[..., :2], axis=-1, keepdims=True), 1e-8), ch
+    l1, c1h = lines(F1, np.asarray(coord1))
+    l2, c2h = lines(F2, np.asarray(coord2))
+    d1 = np.abs(np.einsum("bmi,bni->bmn", l1, c2h))                      # epipolar_dist
+    d2 = np.abs(np.einsum("bni,bmi->bmn", l2, c1h))                      # epipolar_dist2^T
+    if dynamic:
+        reward = np.maximum(np.exp(-d1 / reward_thr) + np.exp(-d2 / reward_thr) - 2 / np.e, bad_reward)
+    else:
+        good = (d1 < reward_thr) & (d2 < reward_thr)
+        reward = good_reward * good + bad_reward * (~good)
+    a1, a2 = np.asarray(acc1, bool), np.asarray(acc2, bool)
+    acc = a1[:, :, None] & a2[:, None, :]
+    lp1, lp2 = np.asarray(logp1, np.float64), np.asarray(logp2, np.float64)
+    wgt = acc * reward * p
+    reinforce = (wgt * (logp + lp1[:, :, None] + lp2[:, None, :])).sum()
+    pen = kp_penalty * (lp1[a1].sum() + lp2[a2].sum())
+    loss = -reinforce - pen
+    comp = {"reinforce": reinforce, "kp_penalty": pen, "cor minmax": p.reshape(b, -1).max(-1).min(),
+            "cor minmean": p.reshape(b, -1).mean(-1).min(), "cor max": p.max(), "cor mean": p.mean(),
+            "cor summin": min(p.sum(1).min(), p.sum(2).min()), "cor summax": max(p.sum(1).max(), p.sum(2).max()),
+            "n_kps": (a1.sum(-1) + a2.sum(-1)).astype(np.float64).mean(), "n_pairs": p.sum((1, 2)).mean()}
+    g1 = -wgt.sum(2) - kp_penalty * a1                                   # d loss / d logp1
+    g2 = -wgt.sum(1) - kp_penalty * a2
+    return loss, comp, g1, g2

@@ -55,6 +55,8 @@ SIGNATURES = {
                                          _vp, _sz, _vp]),
     "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i, _i,
                                            _vp, _vp, _vp, _vp, _vp]),
+    "posfeat_dual_softmax_reward_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "posfeat_dual_softmax_reward_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp, _vp, _sz, _vp]),
     "posfeat_line_search_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp]),
     "posfeat_window_expect_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i,

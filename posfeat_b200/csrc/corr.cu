@@ -30,6 +30,10 @@ int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, i
                 float scale, float* out, float* lse, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t corr_tc_bwd_workspace_bytes(int B, int n, int m, int D, int C);
 bool corr_tc_bwd_eligible(int B, int n, int m, int D, int C);
+size_t corr_disk_workspace_bytes(int B, int n, int m, int D);
+int corr_disk_rows(const float* q, const float* k, const float* rowtab, const float* coltab, int B, int n, int m, int D,
+                   float temp, float thr_own, float thr_other, float good_reward, float bad_reward, int dynamic_reward,
+                   float* rows_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 int corr_tc_bwd(const float* q, const float* k, const float* v, int v_batched, int B, int n, int m, int D, int C,
                 float scale, const float* out, const float* lse, const float* g_out, float* g_q, float* g_k, void* ws,
                 size_t ws_bytes, cudaStream_t stream);
@@ -860,6 +864,23 @@ extern "C" int posfeat_window_expect_fwd_f32(const float* fmap, int B, int D, in
                                                               exp_xy, std_out, prob, lse);
   PF_LAUNCH_CHECK("window_expect_fwd_kernel");
   return POSFEAT_OK;
+}
+
+// ---- DiskLoss dense affinity (losses/kploss.py:158-182): row-side sums of the dual-softmax match distribution
+extern "C" size_t posfeat_dual_softmax_reward_workspace_bytes(int B, int n, int m, int D) {
+  if (B < 1 || n < 1 || m < 1 || D < 1 || D > 128) return 0;
+  return corr_disk_workspace_bytes(B, n, m, D);
+}
+
+extern "C" int posfeat_dual_softmax_reward_f32(const float* q, const float* k, const float* rowtab, const float* coltab,
+                                               int B, int n, int m, int D, float temperature, float thr_own,
+                                               float thr_other, float good_reward, float bad_reward, int dynamic_reward,
+                                               float* rows_out, void* workspace, size_t ws_bytes, void* stream) {
+  PF_CHECK_ARG(q && k && rowtab && coltab && rows_out && workspace, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && B <= 65535 && n >= 1 && m >= 1 && D >= 1 && D <= 128, "bad shape B=%d n=%d m=%d D=%d", B, n, m, D);
+  PF_CHECK_ARG(thr_own > 0.f && thr_other > 0.f, "reward thresholds must be positive");
+  return corr_disk_rows(q, k, rowtab, coltab, B, n, m, D, temperature, thr_own, thr_other, good_reward, bad_reward,
+                        dynamic_reward, rows_out, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int posfeat_line_search_f32(const float* fmap, int B, int D, int h, int w, int64_t sb, int64_t sc, int64_t sy,

@@ -77,6 +77,14 @@ struct CorrTcParams {
   const float* lse;          // [B][n]
   float *w_hi, *w_lo;        // [B][n_pad][m_pad]
   float *wt_hi, *wt_lo;      // [B][m_pad][n_pad]
+  // kMode 2 (DiskLoss dual-softmax reward sums, losses/kploss.py:158-182)
+  const float4* rowtab;      // [B][n_pad][2]: {lse, la, lb, lc}, {x, y, logp, accept} of the row side
+  const float4* coltab;      // [B][m_pad][2]: the same for the column side
+  float temp;                // affinity = temp * s - temp
+  float thr_own, thr_other;  // reward thresholds on |own line . other point| and |other line . own point|
+  float good_reward, bad_reward;
+  int dynamic_reward;        // 0: constant_reward, 1: dynamic_reward
+  float4* part4;             // [B][q_tiles][splits][128]: {reinforce, reward-weighted p, sum p, max p}
 };
 
 // ---- split: x -> hi = tf32(x), lo = x - hi, zero padded to [rows_pad][Dp] per batch (Dp = 32 * slices).
@@ -231,7 +239,67 @@ corr_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_const
       const float4* vb = p.v4 + (p.v_batched ? (size_t)b * p.m_pad : 0);
       const float sl2 = p.sl2;
       const int m = p.m;
-      if (kMode == 1) {
+      if (kMode == 2) {
+        // ---- DiskLoss: p = softmax_row(A) * softmax_col(A), A = temp * s - temp; per row the sums
+        //      sum_j acc_ij r_ij p_ij (log p_ij + logp_i + logp_j),  sum_j acc_ij r_ij p_ij,  sum_j p_ij,  max_j p_ij
+        const int qi = qt * kCtM + row;
+        const float4* rt = p.rowtab + ((size_t)b * p.n_pad + qi) * 2;
+        const float4 r0 = __ldg(rt), r1 = __ldg(rt + 1);       // padding rows carry lse = +inf -> p = 0
+        const float4* ct = p.coltab + (size_t)b * p.m_pad * 2;
+        const float temp = p.temp;
+        float reinf = 0.f, rsum = 0.f, psum = 0.f, pmax = 0.f;
+        int as = 0, aph = 0;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(bar_acc_full + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t)(as * kCtN + half * 64) + ((uint32_t)(quarter * 32) << 16);
+          const int c0 = t * kCtN + half * 64;
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t v[32];
+            tc_ld32(taddr + ch * 32, v);
+            tc_wait_ld();
+            if (ch == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+            }
+            const float4* cp = ct + (size_t)(c0 + ch * 32) * 2;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+              const float4 q0 = __ldg(cp + 2 * j), q1 = __ldg(cp + 2 * j + 1);   // broadcast loads
+              const float a = fmaf(__uint_as_float(v[j]), temp, -temp);
+              const float lp = (a - r0.x) + (a - q0.x);                          // log p_ij
+              const float pj = ex2_approx(lp * 1.4426950408889634f);
+              const float d1 = fabsf(__fadd_rn(__fmaf_rn(r0.z, q1.y, __fmul_rn(r0.y, q1.x)), r0.w));   // own line . other point
+              const float d2 = fabsf(__fadd_rn(__fmaf_rn(q0.z, r1.y, __fmul_rn(q0.y, r1.x)), q0.w));   // other line . own point
+              float rw;
+              if (p.dynamic_reward)
+                rw = fmaxf(__expf(-d1 / p.thr_own) + __expf(-d2 / p.thr_other) - 0.7357588823428847f, p.bad_reward);
+              else
+                rw = (d1 < p.thr_own && d2 < p.thr_other) ? p.good_reward : p.bad_reward;
+              if (r1.w != 0.f && q1.w != 0.f) {          // accepted pair (padding columns carry accept = 0, lp = -inf)
+                const float wv = rw * pj;
+                reinf = fmaf(wv, lp + r1.z + q1.z, reinf);
+                rsum += wv;
+              }
+              psum += pj;
+              pmax = fmaxf(pmax, pj);
+            }
+          }
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (half == 1) {
+          float* d = merge + row * 8;
+          d[0] = reinf; d[1] = rsum; d[2] = psum; d[3] = pmax;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kCtEpiWarps * 32) : "memory");
+        if (half == 0) {
+          const float* d = merge + row * 8;
+          p.part4[(((size_t)b * p.q_tiles + qt) * p.splits + split) * kCtM + row] =
+              make_float4(reinf + d[0], rsum + d[1], psum + d[2], fmaxf(pmax, d[3]));
+        }
+      } else if (kMode == 1) {
         // ---- backward: W tiles ----
         const int qi = qt * kCtM + row;                      // query index inside the batch
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, go = 0.f, lse2 = INFINITY;   // padding rows: W = 0
@@ -800,6 +868,107 @@ int corr_tc_bwd(const float* q, const float* k, const float* v, int v_batched, i
     if (int e = run_gemm(w.wh, w.wl, w.kth, w.ktl, B, p.n_pad, p.m_pad, Dp, n, D, scale, g_q, w.part, stream)) return e;
   if (g_k)
     if (int e = run_gemm(w.wth, w.wtl, w.qth, w.qtl, B, p.m_pad, p.n_pad, Dp, m, D, scale, g_k, w.part, stream)) return e;
+  return POSFEAT_OK;
+}
+
+// ---------------------------------------------------------------- DiskLoss dual-softmax reward sums
+__global__ void corr_padtab_kernel(const float* __restrict__ tab, int B, int rows, int rows_pad, float4* __restrict__ out) {
+  const int64_t total = (int64_t)B * rows_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % rows_pad), b = (int)(i / rows_pad);
+    float4 a = make_float4(INFINITY, 0.f, 0.f, 0.f), c = make_float4(0.f, 0.f, 0.f, 0.f);   // padding: lse = +inf -> p = 0
+    if (r < rows) {
+      const float* t = tab + ((int64_t)b * rows + r) * 8;
+      a = make_float4(t[0], t[1], t[2], t[3]);
+      c = make_float4(t[4], t[5], t[6], t[7]);
+    }
+    out[2 * i] = a;
+    out[2 * i + 1] = c;
+  }
+}
+
+__global__ void corr_disk_merge_kernel(const float4* __restrict__ part, int B, int n, int q_tiles, int splits,
+                                       float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * n) return;
+  const int b = (int)(i / n), r = (int)(i % n);
+  const float4* base = part + (((size_t)b * q_tiles + r / kCtM) * splits) * kCtM + r % kCtM;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = base[(size_t)s * kCtM];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w = fmaxf(acc.w, v.w);
+  }
+  out[i] = acc;
+}
+
+struct CorrDiskWs {
+  float *qh, *ql, *kh, *kl;
+  float4 *rowtab, *coltab, *part4;
+  size_t total;
+};
+
+static CorrDiskWs carve_corr_disk(void* base, int B, int n, int m, int D) {
+  CorrDiskWs w{};
+  const size_t Dp = (D + 31) / 32 * 32, np = pad128(n), mp = pad128(m);
+  int qt, kt, sp, tps;
+  corr_tc_shape(B, n, m, &qt, &kt, &sp, &tps);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  w.qh = (float*)take(4 * B * np * Dp); w.ql = (float*)take(4 * B * np * Dp);
+  w.kh = (float*)take(4 * B * mp * Dp); w.kl = (float*)take(4 * B * mp * Dp);
+  w.rowtab = (float4*)take(sizeof(float4) * 2 * B * np);
+  w.coltab = (float4*)take(sizeof(float4) * 2 * B * mp);
+  w.part4 = (float4*)take(sizeof(float4) * (size_t)B * qt * sp * kCtM);
+  w.total = off;
+  return w;
+}
+
+size_t corr_disk_workspace_bytes(int B, int n, int m, int D) { return carve_corr_disk(nullptr, B, n, m, D).total; }
+
+// rows_out [B][n] float4 = {sum_j acc r p (log p + logp_i + logp_j), sum_j acc r p, sum_j p, max_j p}
+int corr_disk_rows(const float* q, const float* k, const float* rowtab, const float* coltab, int B, int n, int m, int D,
+                   float temp, float thr_own, float thr_other, float good_reward, float bad_reward, int dynamic_reward,
+                   float* rows_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  CorrDiskWs w = carve_corr_disk(ws, B, n, m, D);
+  PF_CHECK_ARG(ws && ((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "dual softmax workspace: need %zu bytes, got %zu", w.total, ws_bytes);
+  CorrTcParams p{};
+  p.B = B; p.n = n; p.m = m; p.D = D; p.C = 1;
+  p.n_pad = pad128(n); p.m_pad = pad128(m);
+  p.atoms = (D + 31) / 32;
+  corr_tc_shape(B, n, m, &p.q_tiles, &p.k_tiles, &p.splits, &p.tiles_per_split);
+  p.rowtab = w.rowtab; p.coltab = w.coltab; p.part4 = w.part4;
+  p.temp = temp; p.thr_own = thr_own; p.thr_other = thr_other;
+  p.good_reward = good_reward; p.bad_reward = bad_reward; p.dynamic_reward = dynamic_reward;
+  const int Dp = p.atoms * 32;
+  ProfScope prof(PROF_CORR_FWD, stream);
+  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.n_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(q, B, n, D, p.n_pad, Dp, w.qh, w.ql);
+  PF_LAUNCH_CHECK("corr_split_kernel(q)");
+  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.m_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(k, B, m, D, p.m_pad, Dp, w.kh, w.kl);
+  PF_LAUNCH_CHECK("corr_split_kernel(k)");
+  corr_padtab_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.n_pad + 255) / 256, 148 * 8), 256, 0, stream>>>(rowtab, B, n, p.n_pad, w.rowtab);
+  PF_LAUNCH_CHECK("corr_padtab_kernel(rows)");
+  corr_padtab_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.m_pad + 255) / 256, 148 * 8), 256, 0, stream>>>(coltab, B, m, p.m_pad, w.coltab);
+  PF_LAUNCH_CHECK("corr_padtab_kernel(cols)");
+  CUtensorMap mqh, mql, mkh, mkl;
+  if (int e = make_map_f32(&mqh, w.qh, Dp, (int64_t)B * p.n_pad)) return e;
+  if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;
+  if (int e = make_map_f32(&mkh, w.kh, Dp, (int64_t)B * p.m_pad)) return e;
+  if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
+    attr_set = true;
+  }
+  corr_tc_fwd_kernel<2><<<dim3(p.splits, p.q_tiles, B), kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
+  PF_LAUNCH_CHECK("corr_tc_fwd_kernel<disk>");
+  corr_disk_merge_kernel<<<(int)(((int64_t)B * n + 255) / 256), 256, 0, stream>>>(w.part4, B, n, p.q_tiles, p.splits,
+                                                                                 reinterpret_cast<float4*>(rows_out));
+  PF_LAUNCH_CHECK("corr_disk_merge_kernel");
   return POSFEAT_OK;
 }
 

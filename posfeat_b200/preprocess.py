@@ -128,8 +128,25 @@ class CorrExpect(torch.autograd.Function):
         return gq, gk, None, None
 
 
-def corr_expect(q, k, v, scale=1.0):
-    return CorrExpect.apply(q, k, v, scale)
+def corr_expect(q, k, v, scale=1.0, want_lse=False):
+    """out[b,i,:] = sum_j softmax_j(scale <q_i,k_j>) v_j.  ``want_lse`` (no autograd): also the per-row
+    log-sum-exp of the scaled logits, returned as (out, lse)."""
+    if not want_lse:
+        return CorrExpect.apply(q, k, v, scale)
+    require_cuda()
+    qd, kd, vd = _f32c(q), _f32c(k), _f32c(v)
+    B, n, D = qd.shape
+    m = kd.shape[1]
+    C = vd.shape[-1]
+    out = torch.empty((B, n, C), dtype=torch.float32, device=qd.device)
+    lse = torch.empty((B, n), dtype=torch.float32, device=qd.device)
+    with torch.cuda.device(qd.device):
+        nbytes = lib().posfeat_corr_expect_workspace_bytes(B, n, m, D, C)
+        ws = workspace("corr", nbytes, qd.device) if nbytes else None
+        check(lib().posfeat_corr_expect_fwd_f32(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), int(vd.dim() == 3), B, n, m, D,
+                                                C, float(scale), out.data_ptr(), lse.data_ptr(), ptr(ws),
+                                                ws.numel() if ws is not None else 0, stream_ptr(qd.device)))
+    return out, lse
 
 
 def get_expected_correspondence_locs(feat1, featmap2, with_std=False):
