@@ -265,8 +265,8 @@ corr_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQh, const __grid_const
               if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
             }
             const float4* cp = ct + (size_t)(c0 + ch * 32) * 2;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {       // fully unrolled: v[] must stay in registers
               const float4 q0 = __ldg(cp + 2 * j), q1 = __ldg(cp + 2 * j + 1);   // broadcast loads
               const float a = fmaf(__uint_as_float(v[j]), temp, -temp);
               const float lp = (a - r0.x) + (a - q0.x);                          // log p_ij
@@ -664,8 +664,15 @@ static void corr_tc_shape(int B, int n, int m, int* q_tiles, int* k_tiles, int* 
   *q_tiles = pad128(n) / 128;
   *k_tiles = pad128(m) / 128;
   const int units = B * *q_tiles;
-  int s = (2 * 148) / units;                      // at most two full waves of one-CTA-per-SM work
-  s = std::max(1, std::min(s, *k_tiles));
+  // one CTA per SM: choose the number of key splits that wastes the least of the last wave
+  // (cost ~ ceil(units * s / 148) / s), preferring fewer splits on ties, at least 4 key tiles per CTA
+  int s = 1;
+  double best = 1e30;
+  for (int c = 1; c <= std::min(*k_tiles, 16); ++c) {
+    if (c > 1 && *k_tiles / c < 4) break;
+    const double cost = (double)((units * c + 147) / 148) / c;
+    if (cost < best - 1e-9) { best = cost; s = c; }
+  }
   *tps = (*k_tiles + s - 1) / s;
   *splits = (*k_tiles + *tps - 1) / *tps;          // no empty split
 }
