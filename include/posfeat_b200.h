@@ -110,6 +110,10 @@ int posfeat_detect_topk_f32(const float* score, int B, int H, int W,
  * (synchronises `stream`): POSFEAT_OK, or POSFEAT_EINVAL when n exceeded
  * cap_pts / the number of interior pixels (torch.topk would raise there). */
 int posfeat_detect_status(void* workspace, int B, int H, int W, int cap_pts, void* stream);
+/* Same, and also copies the device-side n (n_out of the select call) to *n_host in the same
+ * host round trip (n_dev / n_host may be NULL). */
+int posfeat_detect_finish(void* workspace, int B, int H, int W, int cap_pts,
+                          const int32_t* n_dev, int32_t* n_host, void* stream);
 
 /* ---- (2) bilinear descriptor sampling + L2 normalisation -------------------
  * Replaces sample_feat_by_coord, losses/preprocess_utils.py:40-53

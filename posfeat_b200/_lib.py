@@ -35,6 +35,7 @@ SIGNATURES = {
     "posfeat_detect_topk_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _sz, _vp]),
     "posfeat_detect_status": (_i, [_vp, _i, _i, _i, _i, _vp]),
+    "posfeat_detect_finish": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "posfeat_sample_l2norm_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _i, _vp,
                                        _vp, _vp]),
     "posfeat_sample_pairs_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _i, _vp, _vp, _sz, _vp]),

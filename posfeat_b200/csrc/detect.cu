@@ -1030,9 +1030,17 @@ extern "C" int posfeat_detect_topk_f32(const float* score, int B, int H, int W, 
 
 // Reads the device status flag of the last select (host sync on `stream`).
 extern "C" int posfeat_detect_status(void* workspace, int B, int H, int W, int cap_pts, void* stream_) {
+  return posfeat_detect_finish(workspace, B, H, W, cap_pts, nullptr, nullptr, stream_);
+}
+
+// Status and, optionally, the keypoint count n (device int32 written by the select kernel) in ONE host
+// round trip: both copies are queued before the single stream synchronisation.
+extern "C" int posfeat_detect_finish(void* workspace, int B, int H, int W, int cap_pts, const int32_t* n_dev,
+                                     int32_t* n_host, void* stream_) {
   DetectWs w = carve(workspace, B, H, W, cap_pts);
   int32_t st = 0;
   PF_CUDA(cudaMemcpyAsync(&st, w.status, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  if (n_dev && n_host) PF_CUDA(cudaMemcpyAsync(n_host, n_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
   PF_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   if (st == 0) return POSFEAT_OK;
   const char* why = st == 1 ? "n exceeds cap_pts" : st == 2 ? "n exceeds the number of interior pixels (topk k out of range)"

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._runtime import check, lib, stream_ptr, workspace
-from .preprocess_utils import MIN_PTS, denormalize_coords, detect_topk, sample_l2norm
+from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
 def shard(items, rank: int, world: int):
@@ -115,10 +115,17 @@ class PairPipeline:
             out = self._run_streams(score, fmap)
             if out is not None:
                 return out
-        r = detect_topk(score, sync=True, **self.cfg)
-        n = r["n"]
+        r = detect_topk(score, sync=False, **self.cfg)
+        # while the selection kernel runs: everything that only needs the capacity, not n itself
+        cap, D = r["cap"], fmap.shape[1]
+        desc_buf = torch.empty((score.shape[0], cap, D), dtype=torch.float32, device=score.device)
+        if P >= 1 and self._tc_applies(cap, D):
+            with torch.cuda.device(score.device):
+                workspace("mnn", lib().posfeat_mnn_batched_workspace_bytes(P, cap, cap, D, _lib.MNN_TC), score.device)
+        n = detect_finish(r)                      # the one host round trip of the step
         kps = r["kps"][:, :n]
-        desc, prepared = self.sample_for_pairs(fmap, kps)
+        out = desc_buf if n == cap else desc_buf.view(-1)[:score.shape[0] * n * D].view(score.shape[0], n, D)
+        desc, prepared = self.sample_for_pairs(fmap, kps, out=out)
         h, w = score.shape[2:]
         feats = {"kps_n": kps, "kpt": denormalize_coords(kps, h, w), "kp_score": r["score"][:, :n],
                  "desc": desc, "idx": r["idx"][:, :n], "n": n}

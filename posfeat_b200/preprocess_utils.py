@@ -102,11 +102,25 @@ def detect_topk(kp_map, nms_radius, num_pts=False, use_nms=True, thr=False, thr_
                                               cap,
                                               cap, counts.data_ptr(), n_out.data_ptr(), idx.data_ptr(),
                                               kps.data_ptr(), sc.data_ptr(), ws.data_ptr(), ws.numel(), st))
-        n = n_out
-        if sync:
-            check(L.posfeat_detect_status(ws.data_ptr(), b, h, w, cap, st))
-            n = int(n_out.item())
-    return {"kps": kps, "score": sc, "idx": idx, "counts": counts, "n": n, "cap": cap}
+    r = {"kps": kps, "score": sc, "idx": idx, "counts": counts, "n": n_out, "cap": cap,
+         "_finish": (ws, b, h, w, cap, n_out, dev)}
+    if sync:
+        detect_finish(r)
+    return r
+
+
+def detect_finish(r):
+    """Waits for a ``detect_topk(sync=False)`` call: device status and the keypoint count n come back in one
+    host round trip; ``r["n"]`` becomes a python int.  Work that does not depend on n (allocations, size
+    queries) can be done between the two calls while the selection kernel runs."""
+    import ctypes
+    ws, b, h, w, cap, n_out, dev = r["_finish"]
+    n_host = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        check(lib().posfeat_detect_finish(ws.data_ptr(), b, h, w, cap, n_out.data_ptr(), ctypes.byref(n_host),
+                                          stream_ptr(dev)))
+    r["n"] = int(n_host.value)
+    return r["n"]
 
 
 def generate_kpts_single(kp_map, nms_radius, num_pts=False, scale=4, stable=True, temperature=1, stride=1,
