@@ -796,13 +796,13 @@ __device__ __forceinline__ double warp_exact_dot(const float* __restrict__ xr, c
   return acc;
 }
 
-constexpr int kVerWarps = 4;
+constexpr int kVerWarps = 1;
 // One WARP per (chunk c of Y columns, pair).  R = competitor rows of the chunk (a superset of
 // the members, the rows whose nearest neighbour lies in c).  The competitors' similarities to
 // the chunk's 8 columns are evaluated in float32; a member loses its match if another
 // competitor is larger in the member's column.  Comparisons inside the float32 error band are
 // settled exactly (float64), ties by the lower row index.
-__global__ void __launch_bounds__(kVerWarps * 32, 8)
+__global__ void __launch_bounds__(kVerWarps * 32, 32)
 tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
   __shared__ float s_e[kVerWarps][32][kChunk];                    // competitor matrix of short lists
@@ -818,18 +818,22 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   const float* Yp = a.Y + pair * a.strideY;
   const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
   const float4* yv = &s_y[warp][0];
+  const bool vec_x = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(Xp) & 15) == 0;   // 128-bit row loads
+  const bool vec_y = (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Yp) & 15) == 0;
   auto stage_y = [&]() {                 // the chunk's 8 columns -> shared memory (only needed to evaluate rows here)
 #pragma unroll
     for (int r = 0; r < kChunk; ++r) {
       const int jj = c * kChunk + r;
       const float* yr = Yp + (int64_t)jj * a.ldy + lane * 4;
-      s_y[warp][r * 32 + lane] =
-          jj < d.NY ? make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 yv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jj < d.NY) yv4 = vec_y ? __ldg(reinterpret_cast<const float4*>(yr)) : make_float4(__ldg(yr), __ldg(yr + 1), __ldg(yr + 2), __ldg(yr + 3));
+      s_y[warp][r * 32 + lane] = yv4;
     }
     __syncwarp();
   };
   auto load_row = [&](int row) {
     const float* xr = Xp + (int64_t)row * a.ldx + lane * 4;
+    if (vec_x) return __ldg(reinterpret_cast<const float4*>(xr));
     return make_float4(__ldg(xr), __ldg(xr + 1), __ldg(xr + 2), __ldg(xr + 3));
   };
   // two float32 similarities whose difference is below this band are compared exactly
