@@ -431,14 +431,16 @@ struct RescoreArgs {
 // the runner-up is either in the maximum's chunk or is that other chunk's maximum.
 // kTwoDir = false: only a0's rows exist (matches-only path); the argument block is then addressed statically
 // instead of through indexed constant-bank loads.
+// rows differ in cost (number of candidate chunks): small CTAs keep SM slots from idling behind a slow row
+constexpr int kResWarps = 2;
 template <bool kTop2, bool kTwoDir>
-__global__ void __launch_bounds__(256, 4)   // 64 registers: 32 warps per SM hide the dependent table / Y-row loads (measured: 3 -> 543 us, 4 -> 490 us, 5 -> 497 us)
+__global__ void __launch_bounds__(kResWarps * 32, 32 / kResWarps)   // 64 registers, 32 warps per SM: they hide the dependent table / Y-row loads
 tc_rescore_kernel(const RescoreArgs a0, const RescoreArgs a1, const int pairs) {
-  __shared__ __align__(16) float xs[8][kD];
+  __shared__ __align__(16) float xs[kResWarps][kD];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_pair = a0.d.NX + (kTwoDir ? a1.d.NX : 0);
   const int pair = blockIdx.y;                     // grid: (row blocks of a pair, pairs)
-  int row = blockIdx.x * 8 + w;
+  int row = blockIdx.x * kResWarps + w;
   if (row >= rows_pair) return;
   const bool second = kTwoDir && row >= a0.d.NX;
   if (second) row -= a0.d.NX;
@@ -1208,12 +1210,12 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
                  one_dir ? w.tmin : nullptr, one_dir ? w.best8 : nullptr, w.mutual, nchunks};
   RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
-  const dim3 resc_grid((unsigned)((N + (one_dir ? 0 : M) + 7) / 8), (unsigned)P);
+  const dim3 resc_grid((unsigned)((N + (one_dir ? 0 : M) + kResWarps - 1) / kResWarps), (unsigned)P);
   if (P > 65535) return set_error(POSFEAT_EINVAL, "batched matcher: at most 65535 pairs per call");
   prof_begin(PROF_MNN_RESCORE, stream);
-  if (top12) tc_rescore_kernel<true, true><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
-  else if (one_dir) tc_rescore_kernel<false, false><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
-  else tc_rescore_kernel<false, true><<<resc_grid, 256, 0, stream>>>(r0, r1, P);
+  if (top12) tc_rescore_kernel<true, true><<<resc_grid, kResWarps * 32, 0, stream>>>(r0, r1, P);
+  else if (one_dir) tc_rescore_kernel<false, false><<<resc_grid, kResWarps * 32, 0, stream>>>(r0, r1, P);
+  else tc_rescore_kernel<false, true><<<resc_grid, kResWarps * 32, 0, stream>>>(r0, r1, P);
   prof_end(PROF_MNN_RESCORE, stream);
   PF_LAUNCH_CHECK("tc_rescore_kernel");
   if (top12) return POSFEAT_OK;      // ratio-test callers apply their own acceptance rule to (nn, top2)
