@@ -170,6 +170,15 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+E2E_PATHS = {
+    "stage": "score maps copied whole; descriptor-map pixels under the keypoints' taps fetched once each from pinned host "
+             "memory (posfeat_fetch_taps_f32; bytes = pixels moved, counted by the kernel, x 512 B)",
+    "direct": "score maps copied whole; the sampler reads its taps from pinned host memory (bytes requested = 4 taps x 512 B "
+              "per keypoint)",
+    False: "score and descriptor maps copied whole",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the pair batch is split over (1 = plain path)")
+    ap.add_argument("--no-host-gather", action="store_true",
+                    help="e2e leg: copy the whole descriptor map to the device instead of gathering taps over the host link")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 comparison leg")
     ap.add_argument("--fmap-layout", default="channels_last", choices=["channels_last", "nchw"])
@@ -241,17 +252,38 @@ def main():
     launches = _lib.launch_count() - l0
     # ---- end to end through the host-buffer call ------------------------
     score_h, fmap_h = score.cpu().pin_memory(), fmap.cpu().pin_memory()   # .cpu() preserves the memory format
-    for _ in range(2):
-        pipe.run_host(score_h, fmap_h)
-    barrier()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(args.steps):
-        kpt_h, matches_h, nm_h = pipe.run_host(score_h, fmap_h)
-    g1.record()
-    torch.cuda.synchronize()
-    ms_e2e = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host is in the loop: take wall clock
+    def time_host(gather):
+        for _ in range(2):
+            pipe.run_host(score_h, fmap_h, gather=gather)
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            res = pipe.run_host(score_h, fmap_h, gather=gather)
+        g1.record()
+        torch.cuda.synchronize()
+        return max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0)), res   # host is in the loop: take wall clock
+
+    # the call's default: once the keypoints are known, exactly the descriptor-map pixels under their taps are
+    # fetched from the pinned map, each once ("stage"); beside it the sampler reading its taps from the pinned
+    # map directly ("direct") and the plain form that copies the whole dense map first
+    modes = (["stage", "direct"] if PairPipeline.host_gather_applies(fmap_h) and not args.no_host_gather else []) + [False]
+    e2e_runs = {}
+    for mode in modes:
+        ms_m, res = time_host(mode)
+        e2e_runs[mode] = [ms_m, res, PairPipeline.h2d_bytes(score, fmap)]
+        if mode == "stage":
+            e2e_runs[mode][2] = score.numel() * 4 + pipe.staged_pixels(fmap_h, dev) * fmap.shape[1] * 4
+        elif mode == "direct":
+            e2e_runs[mode][2] = PairPipeline.h2d_bytes(score, fmap, int(n_kp))
+    head = modes[0]
+    kpt_h, matches_h, nm_h = e2e_runs[head][1]
+    e2e_same = all(torch.equal(a, b) for m in modes for a, b in zip(e2e_runs[m][1], e2e_runs[head][1]))
+    e2e_same = bool(e2e_same and torch.equal(nm_h, nm.cpu()) and torch.equal(kpt_h, feats["kpt"].cpu())
+                    and torch.equal(matches_h[0, :int(nm_h[0])], matches[0, :int(nm_h[0])].cpu()))
+    for m in modes:
+        e2e_runs[m][1] = None
     # ---- per-kernel durations (CUDA events on the launching stream) -----
     pipe.streams = 1                      # per-kernel durations are taken with the kernels running alone
     _lib.profile_enable(True)
@@ -275,10 +307,13 @@ def main():
                  "matches_differing_pair0": len({tuple(x) for x in ematch.tolist()} ^
                                                 {tuple(x) for x in matches[0, :k0].tolist()})}
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms] + [e2e_runs[m][0] for m in modes], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms = float(t[0])
+    for i, m in enumerate(modes):
+        e2e_runs[m][0] = float(t[1 + i])
+    ms_e2e = e2e_runs[head][0]
     total_pairs = P * args.steps * world
     value = total_pairs / (ms / 1e3)
     e2e_value = total_pairs / (ms_e2e / 1e3)
@@ -341,8 +376,14 @@ def main():
                           "l2": f"inputs {((score.numel() + fmap.numel()) * 4) >> 20} MiB per step > 126 MB L2 (no flush needed)",
                           "parallelism": f"pairs sharded over {world} rank(s), no collective"},
                "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                       "h2d_bytes_per_step": PairPipeline.h2d_bytes(score, fmap),
-                       "d2h_bytes_per_step": PairPipeline.d2h_bytes(2 * P, int(n_kp), P)},
+                       "h2d_bytes_per_step": int(e2e_runs[head][2]),
+                       "d2h_bytes_per_step": PairPipeline.d2h_bytes(2 * P, int(n_kp), P),
+                       "input_path": E2E_PATHS[head],
+                       "other_input_paths": {str(m): {"value": total_pairs / (e2e_runs[m][0] / 1e3),
+                                                      "ms_per_step": e2e_runs[m][0] / args.steps,
+                                                      "h2d_bytes_per_step": int(e2e_runs[m][2]), "input_path": E2E_PATHS[m]}
+                                             for m in modes[1:]},
+                       "results_equal_device_path": e2e_same},
                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                "torch_eager_b200": eager, "kernels": kern, "extra_rooflines": extra}
         print(json.dumps(out), flush=True)

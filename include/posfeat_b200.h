@@ -54,6 +54,13 @@ int posfeat_last_error(char* buf, int n);
 /* Number of SMs of the current device (grid sizing for callers), <0 on error. */
 int posfeat_device_sm_count(void);
 
+/* Device-side alias of a page-locked (pinned, mapped) host buffer.  The sampler entry points accept
+ * such a pointer for the descriptor map: the kernel then gathers the four taps of every keypoint
+ * straight over the host link (2 KB per keypoint at D=128) instead of the caller copying the whole
+ * dense map first (34 MB per 896x1200 image) -- the host-buffer form of sample_feat_by_coord,
+ * losses/preprocess_utils.py:40-53.  Fails with POSFEAT_EINVAL for pageable memory. */
+int posfeat_host_device_pointer(const void* host, void** dev_out);
+
 /* Accounting used by bench.py: kernels launched by this process so far, and
  * optional CUDA-event timing of the individual kernels (events are recorded on
  * the launching stream around each launch while enabled; read() synchronises
@@ -137,6 +144,21 @@ int posfeat_sample_pairs_f32(const float* fmap, int B, int D, int h, int w,
                              int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                              const float* coord_n, int n, int do_norm, float* out,
                              void* mnn_workspace, size_t mnn_ws_bytes, void* stream);
+
+/* Host-buffer callers: sparse host->device staging of exactly the map pixels the sampler will read.
+ * fmap_host: device-side alias (posfeat_host_device_pointer) of the pinned dense descriptor map,
+ * fmap_dev: device map with the SAME strides; both channels-last (sc == 1), D % 4 == 0.  One bit per
+ * pixel covered by some keypoint's 2x2 tap block is set (same tap arithmetic as the sampler), then every
+ * marked pixel crosses the host link once (D floats, coalesced) into its place in fmap_dev; unmarked
+ * pixels of fmap_dev are left untouched.  posfeat_sample_*_f32 on fmap_dev with the same coord_n then
+ * returns what it would return on the whole map.  workspace: bitmap + one 64-bit counter;
+ * posfeat_fetch_taps_count reads the number of pixels moved (synchronises the stream). */
+size_t posfeat_fetch_taps_workspace_bytes(int B, int h, int w);
+int posfeat_fetch_taps_f32(const float* fmap_host, float* fmap_dev, int B, int D, int h, int w,
+                           int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                           const float* coord_n, int n, void* workspace, size_t ws_bytes, void* stream);
+int posfeat_fetch_taps_count(const void* workspace, int B, int h, int w, unsigned long long* pixels_out,
+                             void* stream);
 
 /* Backward of the gather (training path, losses/preprocess.py:56-57): accumulates
  * w_tap * g_out [B,n,D] into g_fmap (same strides as fmap, zero-initialised by

@@ -24,6 +24,7 @@ SIGNATURES = {
     "posfeat_last_error": (_i, [C.c_char_p, _i]),
     "posfeat_device_sm_count": (_i, []),
     "posfeat_launch_count": (_i64, []),
+    "posfeat_host_device_pointer": (_i, [_vp, C.POINTER(_vp)]),
     "posfeat_profile_enable": (_i, [_i]),
     "posfeat_profile_slot_count": (_i, []),
     "posfeat_profile_slot_name": (C.c_char_p, [_i]),
@@ -39,6 +40,9 @@ SIGNATURES = {
     "posfeat_sample_l2norm_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _i, _vp,
                                        _vp, _vp]),
     "posfeat_sample_pairs_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "posfeat_fetch_taps_workspace_bytes": (_sz, [_i, _i, _i]),
+    "posfeat_fetch_taps_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _sz, _vp]),
+    "posfeat_fetch_taps_count": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64), _vp]),
     "posfeat_sample_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "posfeat_mnn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "posfeat_mnn_f32": (_i, [_vp, _i, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

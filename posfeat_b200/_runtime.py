@@ -7,6 +7,8 @@ import torch
 from . import _lib
 
 _workspaces = {}
+lib = _lib.load
+check = _lib.check
 
 
 def require_cuda():
@@ -43,5 +45,14 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-lib = _lib.load
-check = _lib.check
+def map_ptr(t: torch.Tensor) -> int:
+    """Address a kernel can dereference: the tensor's own pointer for device memory, the device-side
+    alias (posfeat_host_device_pointer) for a pinned host tensor; pageable host memory raises."""
+    if t.device.type == "cuda":
+        return t.data_ptr()
+    import ctypes as C
+    out = C.c_void_p(0)
+    check(lib().posfeat_host_device_pointer(t.data_ptr(), C.byref(out)))
+    return int(out.value)
+
+

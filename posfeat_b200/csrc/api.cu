@@ -32,7 +32,7 @@ static std::vector<ProfPair> g_prof[PROF_COUNT];
 static cudaEvent_t g_prof_open[PROF_COUNT];
 static const char* kProfNames[PROF_COUNT] = {"nms_candidates", "select_topk", "sample_l2norm", "mnn_prep", "mnn_tc",
                                              "mnn_rescore", "mnn_simt", "mnn_compact", "corr_fwd", "corr_bwd",
-                                             "window_fwd", "window_bwd", "mnn_scan", "mnn_verify"};
+                                             "window_fwd", "window_bwd", "mnn_scan", "mnn_verify", "fetch_taps"};
 
 void prof_begin(int slot, cudaStream_t s) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
@@ -108,6 +108,19 @@ extern "C" int posfeat_last_error(char* buf, int n) {
 }
 
 extern "C" int64_t posfeat_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int posfeat_host_device_pointer(const void* host, void** dev_out) {
+  PF_CHECK_ARG(host && dev_out, "NULL pointer");
+  void* d = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(host), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(POSFEAT_EINVAL, "host pointer %p is not page-locked, mapped memory: %s", host,
+                     cudaGetErrorString(e));
+  }
+  *dev_out = d;
+  return POSFEAT_OK;
+}
 extern "C" int posfeat_profile_enable(int on) {
   g_prof_on.store(on ? 1 : 0);
   return POSFEAT_OK;

@@ -151,6 +151,79 @@ sample_nhwc_kernel(const float* __restrict__ fmap, int D, int h, int w, int64_t 
   }
 }
 
+// ---- sparse host->device staging of exactly the pixels the sampler will read --------------------
+// Host-buffer callers (PairPipeline.run_host): the dense descriptor map stays in pinned host memory;
+// mark_taps_kernel sets one bit per map pixel that some keypoint's 2x2 tap block covers (same
+// make_taps as the sampler, so the cover is exact), fetch_pixels_kernel then moves each marked pixel
+// (D contiguous floats) once over the host link into the same position of a device-resident map, and
+// the ordinary sampler runs on that map.  At 8192 keypoints on a 224x300 map 39 % of the pixels are
+// marked: 13.3 MB cross the link instead of 34.4 MB (dense copy) or 16.8 MB (gathering per keypoint).
+__global__ void __launch_bounds__(256)
+mark_taps_kernel(const float* __restrict__ coord, int n, int h, int w, int words_per_image,
+                 unsigned* __restrict__ bitmap) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float2 g = *reinterpret_cast<const float2*>(coord + ((int64_t)b * n + p) * 2);
+  const Taps t = make_taps(g.x, g.y, h, w);
+  unsigned* bm = bitmap + (int64_t)b * words_per_image;
+  const int i00 = t.y0 * w + t.x0;
+  if (t.in00) atomicOr(bm + (i00 >> 5), 1u << (i00 & 31));
+  if (t.in01) atomicOr(bm + ((i00 + 1) >> 5), 1u << ((i00 + 1) & 31));
+  if (t.in10) atomicOr(bm + ((i00 + w) >> 5), 1u << ((i00 + w) & 31));
+  if (t.in11) atomicOr(bm + ((i00 + w + 1) >> 5), 1u << ((i00 + w + 1) & 31));
+}
+
+template <int VPL>  // float4 per lane and pixel (D <= 128*VPL)
+__global__ void __launch_bounds__(256)
+fetch_pixels_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int w, int64_t sb,
+                    int64_t sy, int64_t sx, int words_per_image, const unsigned* __restrict__ bitmap,
+                    unsigned long long* __restrict__ n_fetched) {
+  constexpr int kInFlight = 4;        // pixels whose loads are issued before the first store
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int wd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wd >= words_per_image) return;
+  unsigned m = bitmap[(int64_t)b * words_per_image + wd];
+  if (!m) return;
+  if (n_fetched && lane == 0) atomicAdd(n_fetched, (unsigned long long)__popc(m));
+  const int64_t ib = b * sb;
+  while (m) {
+    int64_t off[kInFlight];
+    float4 v[kInFlight][VPL];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      off[u] = -1;
+      if (m) {
+        const int pix = wd * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        const int y = pix / w, x = pix - y * w;
+        off[u] = ib + (int64_t)y * sy + (int64_t)x * sx;
+        ++cnt;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u)
+      if (u < cnt) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int c = 4 * (lane + 32 * j);
+          if (c < D) v[u][j] = __ldcs(reinterpret_cast<const float4*>(src + off[u] + c));
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u)
+      if (u < cnt) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int c = 4 * (lane + 32 * j);
+          if (c < D) *reinterpret_cast<float4*>(dst + off[u] + c) = v[u][j];
+        }
+      }
+  }
+}
+
 // backward of the bilinear gather: g_fmap[taps] += w_tap * g_out (float atomics, as
 // ATen's grid_sampler_2d_backward does); gradients w.r.t. the coordinates are not
 // needed on the reference's paths (keypoint coordinates are detached).
@@ -241,6 +314,53 @@ extern "C" int posfeat_sample_pairs_f32(const float* fmap, int B, int D, int h, 
   sample_nhwc_kernel<1, true><<<grid, block, 0, stream>>>(fmap, D, h, w, sb, sy, sx, coord_n, n, nullptr, do_norm, out,
                                                            nullptr, sink);
   PF_LAUNCH_CHECK("sample_nhwc_kernel<sink>");
+  return POSFEAT_OK;
+}
+
+extern "C" size_t posfeat_fetch_taps_workspace_bytes(int B, int h, int w) {
+  if (B < 1 || h < 1 || w < 1) return 0;
+  return ((size_t)B * (size_t)(((int64_t)h * w + 31) / 32) * 4 + 255) / 256 * 256 + 256;
+}
+
+extern "C" int posfeat_fetch_taps_f32(const float* fmap_host, float* fmap_dev, int B, int D, int h, int w, int64_t sb,
+                                      int64_t sc, int64_t sy, int64_t sx, const float* coord_n, int n,
+                                      void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PF_CHECK_ARG(fmap_host && fmap_dev && coord_n && workspace, "NULL pointer");
+  PF_CHECK_ARG(B >= 1 && B <= 65535 && D >= 1 && D <= 512 && h >= 1 && w >= 1 && n >= 0, "bad shape B=%d D=%d h=%d w=%d n=%d",
+               B, D, h, w, n);
+  PF_CHECK_ARG((int64_t)h * w <= 0x7fffffff - 64, "map of %d x %d pixels is too large", h, w);
+  PF_CHECK_ARG(sc == 1 && D % 4 == 0 && sx % 4 == 0 && sy % 4 == 0 && sb % 4 == 0 && ((uintptr_t)fmap_host % 16 == 0) &&
+                   ((uintptr_t)fmap_dev % 16 == 0),
+               "tap staging needs channels-last, 16-byte aligned descriptor maps with D %% 4 == 0");
+  PF_CHECK_ARG(ws_bytes >= posfeat_fetch_taps_workspace_bytes(B, h, w), "workspace too small (%zu bytes)", ws_bytes);
+  if (n == 0) return POSFEAT_OK;
+  const int words = (int)(((int64_t)h * w + 31) / 32);
+  unsigned* bitmap = (unsigned*)workspace;
+  unsigned long long* counter = (unsigned long long*)((char*)workspace + ((size_t)B * words * 4 + 255) / 256 * 256);
+  PF_CUDA(cudaMemsetAsync(workspace, 0, posfeat_fetch_taps_workspace_bytes(B, h, w), stream));
+  ProfScope prof(PROF_FETCH, stream);
+  mark_taps_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(coord_n, n, h, w, words, bitmap);
+  PF_LAUNCH_CHECK("mark_taps_kernel");
+  const int warps = 8;
+  dim3 grid((words + warps - 1) / warps, B);
+  if (D <= 128)
+    fetch_pixels_kernel<1><<<grid, 32 * warps, 0, stream>>>(fmap_host, fmap_dev, D, w, sb, sy, sx, words, bitmap, counter);
+  else if (D <= 256)
+    fetch_pixels_kernel<2><<<grid, 32 * warps, 0, stream>>>(fmap_host, fmap_dev, D, w, sb, sy, sx, words, bitmap, counter);
+  else
+    fetch_pixels_kernel<4><<<grid, 32 * warps, 0, stream>>>(fmap_host, fmap_dev, D, w, sb, sy, sx, words, bitmap, counter);
+  PF_LAUNCH_CHECK("fetch_pixels_kernel");
+  return POSFEAT_OK;
+}
+
+extern "C" int posfeat_fetch_taps_count(const void* workspace, int B, int h, int w, unsigned long long* pixels_out,
+                                        void* stream_) {
+  PF_CHECK_ARG(workspace && pixels_out && B >= 1 && h >= 1 && w >= 1, "bad argument");
+  const int words = (int)(((int64_t)h * w + 31) / 32);
+  const char* counter = (const char*)workspace + ((size_t)B * words * 4 + 255) / 256 * 256;
+  PF_CUDA(cudaMemcpyAsync(pixels_out, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  PF_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
   return POSFEAT_OK;
 }
 

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._runtime import check, lib, stream_ptr, workspace
+from ._runtime import check, lib, map_ptr, stream_ptr, workspace
 from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
@@ -54,7 +54,8 @@ class PairPipeline:
     def sample_for_pairs(self, fmap, kps, ws_key: str = "mnn", out=None):
         """Sampler for the pair path: when the tensor-core matcher will run, one kernel writes the
         descriptors AND the matcher's bf16 operands / norms into its workspace (posfeat_sample_pairs_f32),
-        so the matcher skips its own pass over the descriptors.  Returns (desc, prepared)."""
+        so the matcher skips its own pass over the descriptors.  Returns (desc, prepared).
+        ``fmap`` may live in pinned host memory (see run_host): the kernel then gathers over the host link."""
         b, D, h, w = fmap.shape
         n = kps.shape[1]
         fused = (b % 2 == 0 and n >= 1 and self._tc_applies(n, D) and fmap.dtype == torch.float32 and
@@ -62,13 +63,13 @@ class PairPipeline:
         if not fused:
             return sample_l2norm(fmap, kps, self.normalize, out=out), False
         L = lib()
-        dev = fmap.device
+        dev = kps.device
         kps = kps.contiguous()
         if out is None:
             out = torch.empty((b, n, D), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             ws = workspace(ws_key, L.posfeat_mnn_batched_workspace_bytes(b // 2, n, n, D, _lib.MNN_TC), dev)
-            check(L.posfeat_sample_pairs_f32(fmap.data_ptr(), b, D, h, w, fmap.stride(0), fmap.stride(1), fmap.stride(2),
+            check(L.posfeat_sample_pairs_f32(map_ptr(fmap), b, D, h, w, fmap.stride(0), fmap.stride(1), fmap.stride(2),
                                              fmap.stride(3), kps.data_ptr(), n, int(bool(self.normalize)), out.data_ptr(),
                                              ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return out, True
@@ -99,8 +100,39 @@ class PairPipeline:
                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)))
         return matches, nm
 
-    def run(self, score: torch.Tensor, fmap: torch.Tensor):
+    def stage_taps(self, fmap_host: torch.Tensor, fmap_dev: torch.Tensor, kps: torch.Tensor):
+        """Sparse host->device copy of exactly the descriptor-map pixels the sampler will read for
+        ``kps`` (posfeat_fetch_taps_f32): every pixel under some keypoint's 2x2 tap block crosses the host
+        link once, into its place in ``fmap_dev`` (same shape and strides as the pinned ``fmap_host``)."""
+        b, D, h, w = fmap_host.shape
+        if tuple(fmap_dev.shape) != (b, D, h, w) or fmap_dev.stride() != fmap_host.stride():
+            raise ValueError("fmap_dev must have the shape and strides of fmap_host")
+        L = lib()
+        dev = fmap_dev.device
+        kps = kps.contiguous()
+        with torch.cuda.device(dev):
+            ws = workspace("fetch", L.posfeat_fetch_taps_workspace_bytes(b, h, w), dev)
+            check(L.posfeat_fetch_taps_f32(map_ptr(fmap_host), fmap_dev.data_ptr(), b, D, h, w, fmap_host.stride(0),
+                                           fmap_host.stride(1), fmap_host.stride(2), fmap_host.stride(3), kps.data_ptr(),
+                                           kps.shape[1], ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        return ws
+
+    def staged_pixels(self, fmap_host: torch.Tensor, dev) -> int:
+        """Pixels moved by the last stage_taps call (synchronises)."""
+        import ctypes as C
+        b, D, h, w = fmap_host.shape
+        out = C.c_uint64(0)
+        with torch.cuda.device(dev):
+            ws = workspace("fetch", lib().posfeat_fetch_taps_workspace_bytes(b, h, w), dev)
+            check(lib().posfeat_fetch_taps_count(ws.data_ptr(), b, h, w, C.byref(out), stream_ptr(dev)))
+        return int(out.value)
+
+    def run(self, score: torch.Tensor, fmap: torch.Tensor, stage_from: torch.Tensor = None):
         """Whole path for 2P images -> (features dict, matches, n_matches), on device.
+
+        ``stage_from``: pinned host descriptor map; ``fmap`` is then an uninitialised device buffer of the
+        same shape/strides that receives only the pixels the sampler needs (stage_taps) once the keypoints
+        are known.
 
         With ``streams > 1`` and a fixed ``num_pts`` the batch is cut into that many groups of pairs,
         each queued on its own stream with no host round trip in between: the keypoint count n stays on
@@ -111,7 +143,7 @@ class PairPipeline:
         64 pairs per step: +1.7 % with two streams, negative with more -- the default stays 1."""
         P = score.shape[0] // 2
         num_pts = self.cfg["num_pts"]
-        if self.streams > 1 and num_pts and num_pts >= MIN_PTS and P >= 2 * self.streams:
+        if stage_from is None and self.streams > 1 and num_pts and num_pts >= MIN_PTS and P >= 2 * self.streams:
             out = self._run_streams(score, fmap)
             if out is not None:
                 return out
@@ -125,6 +157,8 @@ class PairPipeline:
         n = detect_finish(r)                      # the one host round trip of the step
         kps = r["kps"][:, :n]
         out = desc_buf if n == cap else desc_buf.view(-1)[:score.shape[0] * n * D].view(score.shape[0], n, D)
+        if stage_from is not None:
+            self.stage_taps(stage_from, fmap, kps)
         desc, prepared = self.sample_for_pairs(fmap, kps, out=out)
         h, w = score.shape[2:]
         feats = {"kps_n": kps, "kpt": denormalize_coords(kps, h, w), "kp_score": r["score"][:, :n],
@@ -164,25 +198,57 @@ class PairPipeline:
         return feats, torch.cat([p[3] for p in parts]), torch.cat([p[4] for p in parts])
 
     # -- host-buffer entry (what a caller holding CPU tensors uses) --------
-    def run_host(self, score_host: torch.Tensor, fmap_host: torch.Tensor):
+    def run_host(self, score_host: torch.Tensor, fmap_host: torch.Tensor, gather=None):
         """Inputs in (pinned) host memory; returns host tensors: kpt [2P,n,2],
-        matches [P,n,2], n_matches [P].  Copies are part of the call."""
+        matches [P,n,2], n_matches [P].  Copies are part of the call, and the host link bounds it.
+
+        ``gather`` selects how the dense descriptor map (34.4 MB per 896x1200 image) reaches the GPU:
+        * ``"stage"`` (default whenever the map is pinned and channels-last): only the score maps are
+          copied whole; once the keypoints are known, exactly the map pixels under their 2x2 tap blocks
+          are fetched from the pinned map, each once (stage_taps: 13.3 MB per image at 8192 keypoints);
+        * ``"direct"`` / ``True``: the sampler reads its taps straight from the pinned map (16.8 MB per
+          image requested: pixels shared by two keypoints cross the link twice);
+        * ``False``: the whole map is copied first (the plain path)."""
         dev = torch.device("cuda", torch.cuda.current_device())
-        key = (tuple(score_host.shape), tuple(fmap_host.shape), tuple(fmap_host.stride()))
+        if gather is None:
+            gather = "stage" if self.host_gather_applies(fmap_host) else False
+        elif gather is True:
+            gather = "direct"
+        if gather not in ("stage", "direct", False):
+            raise ValueError(f"gather must be 'stage', 'direct', True, False or None, got {gather!r}")
+        if gather and not self.host_gather_applies(fmap_host):
+            raise ValueError("host gather needs a pinned, channels-last float32 descriptor map")
+        key = (tuple(score_host.shape), tuple(fmap_host.shape), tuple(fmap_host.stride()), gather)
         if self._host is None or self._host[0] != key:
-            self._host = (key, torch.empty_like(score_host, device=dev), torch.empty_like(fmap_host, device=dev))
+            self._host = None                            # release the old buffers first
+            self._host = (key, torch.empty_like(score_host, device=dev),
+                          None if gather == "direct" else torch.empty_like(fmap_host, device=dev))
         _, s_dev, f_dev = self._host
         s_dev.copy_(score_host, non_blocking=True)
-        f_dev.copy_(fmap_host, non_blocking=True)
-        feats, matches, nm = self.run(s_dev, f_dev)
+        if gather == "stage":
+            feats, matches, nm = self.run(s_dev, f_dev, stage_from=fmap_host)
+        elif gather == "direct":
+            feats, matches, nm = self.run(s_dev, fmap_host)
+        else:
+            f_dev.copy_(fmap_host, non_blocking=True)
+            feats, matches, nm = self.run(s_dev, f_dev)
         out = (feats["kpt"].to("cpu", non_blocking=True), matches.to("cpu", non_blocking=True),
                nm.to("cpu", non_blocking=True))
         torch.cuda.current_stream().synchronize()
         return out
 
     @staticmethod
-    def h2d_bytes(score, fmap):
-        return score.numel() * 4 + fmap.numel() * 4
+    def host_gather_applies(fmap_host):
+        return (fmap_host.device.type == "cpu" and fmap_host.is_pinned() and fmap_host.dtype == torch.float32 and
+                fmap_host.dim() == 4 and fmap_host.is_contiguous(memory_format=torch.channels_last))
+
+    @staticmethod
+    def h2d_bytes(score, fmap, n=None):
+        """Bytes crossing the host link per call; with ``n`` (host gather) the descriptor part is the
+        taps the sampler requests, 4 x D x 4 bytes per keypoint (duplicates included)."""
+        if n is None:
+            return score.numel() * 4 + fmap.numel() * 4
+        return score.numel() * 4 + fmap.shape[0] * n * 4 * fmap.shape[1] * 4
 
     @staticmethod
     def d2h_bytes(n_images, n, P):

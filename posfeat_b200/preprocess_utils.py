@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._runtime import check, lib, ptr, require_cuda, stream_ptr, to_device, workspace
+from ._runtime import check, lib, map_ptr, ptr, require_cuda, stream_ptr, to_device, workspace
 
 MIN_PTS = 128   # losses/preprocess_utils.py:260-261
 
@@ -162,11 +162,12 @@ def generate_kpts_single_noavg(kp_map, nms_radius, num_pts=False, scale=4, stabl
 # -------------------------------------------------------------------- sampler
 def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False, out=None):
     """Kernel-level sampler on device tensors.  x may be NCHW-contiguous or
-    channels_last; returns [b,n,c] float32 (and a bf16 copy if asked)."""
+    channels_last; returns [b,n,c] float32 (and a bf16 copy if asked).  x may also be a pinned host
+    tensor: the kernel then reads the taps over the host link (coord_n decides the device)."""
     L = lib()
     b, c, h, w = x.shape
     n = coord_n.shape[1]
-    dev = x.device
+    dev = coord_n.device
     if out is None:
         out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (b, n, c) or out.dtype != torch.float32 or not out.is_contiguous():
@@ -180,7 +181,7 @@ def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False, out=Non
     if n == 0 or b == 0:
         return (out, obf) if want_bf16 else out
     with torch.cuda.device(dev):
-        check(L.posfeat_sample_l2norm_f32(x.data_ptr(), b, c, h, w, x.stride(0), x.stride(1), x.stride(2),
+        check(L.posfeat_sample_l2norm_f32(map_ptr(x), b, c, h, w, x.stride(0), x.stride(1), x.stride(2),
                                           x.stride(3), coord_n.data_ptr(), n, ptr(n_valid), int(bool(norm)),
                                           out.data_ptr(), ptr(obf), stream_ptr(dev)))
     return (out, obf) if want_bf16 else out

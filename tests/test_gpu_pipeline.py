@@ -100,6 +100,80 @@ def test_pipeline_host_entry_matches_device_entry():
         assert torch.equal(m_h[i, :int(nm_h[i])], matches[i, :int(nm[i])].cpu())
 
 
+def test_pipeline_host_gather_equals_full_copy():
+    """run_host with a pinned channels-last descriptor map: either exactly the pixels under the keypoints'
+    taps are staged on the device (posfeat_fetch_taps_f32, the default) or the sampler reads the taps over the
+    host link (posfeat_host_device_pointer).  Same bits as copying the whole map first; pageable memory and
+    non-channels-last maps are refused for an explicit gather and fall back to the copy by default."""
+    from posfeat_b200 import _lib
+    from posfeat_b200._runtime import map_ptr
+    from posfeat_b200.pairs import PairPipeline
+    from posfeat_b200.preprocess_utils import sample_l2norm
+    score, fmap = small_pairs(3, seed=21, H=320, W=416)
+    cfg = dict(CFG, num_pts=1500)
+    f_cl = fmap.contiguous(memory_format=torch.channels_last).pin_memory()
+    assert PairPipeline.host_gather_applies(f_cl) and not PairPipeline.host_gather_applies(fmap.pin_memory())
+    assert not PairPipeline.host_gather_applies(fmap.contiguous(memory_format=torch.channels_last))
+    for algo in (_lib.MNN_TC, _lib.MNN_SIMT):          # fused sampler+operands, and the plain sampler
+        pipe = PairPipeline(cfg, mnn_algo=algo)
+        runs = [pipe.run_host(score.pin_memory(), f_cl, gather=g) for g in ("stage", "direct", True, False, None)]
+        for r in runs[1:]:
+            for x, y in zip(runs[0], r):
+                assert torch.equal(x, y)
+        assert int(runs[0][2].min()) > 300
+    with pytest.raises(ValueError):
+        pipe.run_host(score.pin_memory(), fmap.pin_memory(), gather=True)
+    with pytest.raises(ValueError):
+        pipe.run_host(score.pin_memory(), f_cl, gather="some")
+    with pytest.raises(_lib.PosfeatError):
+        map_ptr(fmap)                                    # pageable host memory has no device alias
+    # the kernel-level sampler takes the pinned map as well (descriptors bit-equal to the device-resident map)
+    kps = (torch.rand(6, 777, 2, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+    assert torch.equal(sample_l2norm(f_cl, kps, True), sample_l2norm(f_cl.cuda(), kps, True))
+
+
+@pytest.mark.parametrize("D,h,w,n", [(128, 40, 52, 300), (64, 9, 7, 50), (256, 17, 33, 1), (384, 5, 70, 999)])
+def test_stage_taps_moves_exactly_the_sampled_pixels(D, h, w, n):
+    """posfeat_fetch_taps_f32: the device map starts as NaN everywhere; after staging, sampling it equals
+    sampling the whole map, every pixel that arrived is one the reference's bilinear taps touch, and the
+    kernel's pixel count equals the number of pixels that arrived (coordinates include points outside the
+    map, whose taps are partly or wholly dropped by the zeros padding)."""
+    from posfeat_b200.pairs import PairPipeline
+    from posfeat_b200.preprocess_utils import sample_l2norm
+    g = torch.Generator().manual_seed(D + n)
+    b = 4
+    fmap = torch.randn(b, D, h, w, generator=g).contiguous(memory_format=torch.channels_last).pin_memory()
+    kps = (torch.rand(b, n, 2, generator=g) * 2.3 - 1.15)
+    kps[0, 0] = torch.tensor([-1.0, -1.0])
+    kps[1, 0] = torch.tensor([1.0, 1.0])
+    pipe = PairPipeline(CFG)
+    f_dev = torch.full_like(fmap, float("nan"), device="cuda")
+    assert f_dev.stride() == fmap.stride()
+    pipe.stage_taps(fmap, f_dev, kps.cuda())
+    moved = pipe.staged_pixels(fmap, f_dev.device)
+    got = sample_l2norm(f_dev, kps.cuda(), True)
+    want = sample_l2norm(fmap.cuda(), kps.cuda(), True)
+    assert torch.equal(got, want)
+    arrived = ~torch.isnan(f_dev[:, 0]).cpu()                      # [b,h,w]
+    assert int(arrived.sum()) == moved
+    assert torch.equal(f_dev.cpu()[arrived.unsqueeze(1).expand(-1, D, -1, -1)],
+                       fmap[arrived.unsqueeze(1).expand(-1, D, -1, -1)])
+    # expected cover from the reference's unnormalisation (align_corners=False), losses/preprocess_utils.py:48
+    ix = ((kps[..., 0] + 1) * w - 1) / 2
+    iy = ((kps[..., 1] + 1) * h - 1) / 2
+    x0, y0 = torch.floor(ix).long(), torch.floor(iy).long()
+    cover = torch.zeros(b, h, w, dtype=torch.bool)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            xx, yy = x0 + dx, y0 + dy
+            ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            bi = torch.arange(b)[:, None].expand(-1, n)
+            cover[bi[ok], yy[ok], xx[ok]] = True
+    assert torch.equal(arrived, cover)
+    with pytest.raises(ValueError):
+        pipe.stage_taps(fmap, torch.empty(b, D, h, w, device="cuda"), kps.cuda())     # NCHW strides differ
+
+
 def test_batched_matcher_equals_single_calls():
     import posfeat_b200 as Pb
     from posfeat_b200 import _lib
