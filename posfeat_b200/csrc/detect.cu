@@ -589,6 +589,118 @@ __device__ void bitonic_sort_desc(u64* g, int P, u64* s, int CH, bool in_smem) {
   }
 }
 
+// ---- register / shuffle / shared-memory hybrid bitonic sort (descending) ----------------------
+// P = E * kSelThreads keys, E per thread in registers.  Layout A: thread t holds indices t*E + e, so
+// network steps with stride j < E are register compare-exchanges, E <= j < 32E are warp shuffles.  The
+// five strides that cross warps (j >= 32E) are done in layout B, reached through a padded shared-memory
+// transpose: register bits = index bits [10, 10+eb), lane bits = index bits [0, eb) and [eb+5, 10),
+// warp = index bits [eb, eb+5) -- there every one of those strides is a register or shuffle step too.
+// Shared memory is touched twice per stage k >= 64E (10 round trips at P = 8192) instead of once per
+// step (91): the plain network is bound by shared-memory bandwidth (32 B per compare-exchange).
+__device__ __forceinline__ int sort_pad(int i) { return i + (i >> 4) + ((i >> 8) << 3); }
+
+template <int E, int JE>
+__device__ __forceinline__ void cx_reg(u64 (&r)[E], int base, int rshift, int k) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if ((e & JE) == 0) {
+      const bool desc = ((base | (e << rshift)) & k) == 0;
+      const u64 a = r[e], b = r[e | JE];
+      const bool sw = desc ? (a < b) : (a > b);
+      r[e] = sw ? b : a;
+      r[e | JE] = sw ? a : b;
+    }
+  }
+}
+// all register steps with element stride <= JE (JE, JE/2, ..., 1)
+template <int E, int JE>
+__device__ __forceinline__ void cx_reg_from(u64 (&r)[E], int base, int rshift, int k) {
+  if constexpr (JE >= 1) {
+    cx_reg<E, JE>(r, base, rshift, k);
+    cx_reg_from<E, JE / 2>(r, base, rshift, k);
+  }
+}
+// register steps of layout B for stage k: element strides (k/2 >> 10) ... 1, i.e. only those <= JE_MAX
+template <int E, int JE>
+__device__ __forceinline__ void cx_reg_upto(u64 (&r)[E], int base, int rshift, int k, int je_max) {
+  if constexpr (JE >= 1) {
+    if (JE <= je_max) cx_reg<E, JE>(r, base, rshift, k);
+    cx_reg_upto<E, JE / 2>(r, base, rshift, k, je_max);
+  }
+}
+template <int E>
+__device__ __forceinline__ void cx_shfl(u64 (&r)[E], int base, int rshift, int k, int j, int lane_mask) {
+  const bool lower = (base & j) == 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const u64 a = r[e];
+    const u64 b = __shfl_xor_sync(0xffffffffu, a, lane_mask);
+    const bool desc = ((base | (e << rshift)) & k) == 0;
+    const bool keep_max = lower == desc;
+    const bool b_gt = b > a;
+    r[e] = (keep_max == b_gt) ? b : a;
+  }
+}
+
+// buf: P unordered keys in shared memory (buf == s); s: kSortSmemKeys slots.  Sorted keys end up in buf[0..P).
+template <int E>
+__device__ void bitonic_sort_desc_reg(u64* buf, u64* s) {
+  constexpr int EB = E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4;
+  constexpr int P = E * kSelThreads;
+  static_assert(kSelThreads == 1024 && (1 << EB) == E, "layout arithmetic assumes 32 warps and E in {2,4,8,16}");
+  static_assert(P + (P >> 4) + ((P >> 8) << 3) <= kSortSmemKeys, "padded transpose buffer must fit");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64 r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = buf[e * kSelThreads + tid];   // any bijection will do: the input is unordered
+  __syncthreads();
+  const int baseA = tid * E;
+  const int baseB = (lane & (E - 1)) | (warp << EB) | ((lane >> EB) << (EB + 5));
+  // stages inside one thread
+#pragma unroll
+  for (int k = 2; k <= E; k <<= 1) {
+    if (k == 2) cx_reg_from<E, 1>(r, baseA, 0, k);
+    if (k == 4) cx_reg_from<E, (E >= 4 ? 2 : 0)>(r, baseA, 0, k);
+    if (k == 8) cx_reg_from<E, (E >= 8 ? 4 : 0)>(r, baseA, 0, k);
+    if (k == 16) cx_reg_from<E, (E >= 16 ? 8 : 0)>(r, baseA, 0, k);
+  }
+  // stages inside one warp
+  for (int k = 2 * E; k <= 32 * E; k <<= 1) {
+    for (int j = k >> 1; j >= E; j >>= 1) cx_shfl<E>(r, baseA, 0, k, j, j >> EB);
+    cx_reg_from<E, E / 2>(r, baseA, 0, k);
+  }
+  // stages across warps
+  u64* sp = s;
+  for (int k = 64 * E; k <= P; k <<= 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) sp[sort_pad(baseA + e)] = r[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = sp[sort_pad(baseB | (e << 10))];
+    __syncthreads();
+    cx_reg_upto<E, E / 2>(r, baseB, 10, k, (k >> 1) >> 10);
+    for (int j = min(k >> 1, 512); j >= 32 * E; j >>= 1) cx_shfl<E>(r, baseB, 10, k, j, (j >> (EB + 5)) << EB);
+#pragma unroll
+    for (int e = 0; e < E; ++e) sp[sort_pad(baseB | (e << 10))] = r[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = sp[sort_pad(baseA + e)];
+    __syncthreads();
+    for (int j = 16 * E; j >= E; j >>= 1) cx_shfl<E>(r, baseA, 0, k, j, j >> EB);
+    cx_reg_from<E, E / 2>(r, baseA, 0, k);
+  }
+  // sorted, layout A -> buf[0..P) (through the padded buffer: a direct store would be an 8-way bank conflict)
+#pragma unroll
+  for (int e = 0; e < E; ++e) sp[sort_pad(baseA + e)] = r[e];
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = sp[sort_pad(e * kSelThreads + tid)];
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; ++e) buf[e * kSelThreads + tid] = r[e];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, int64_t sy,
               int num_pts, int min_pts, int cap_pts, int n_fixed,
@@ -811,7 +923,10 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   for (int i = G + tid; i < P; i += kSelThreads) buf[i] = 0;
   __syncthreads();
   PF_TICK();
-  bitonic_sort_desc(buf, P, s_keys, kSortSmemKeys, in_smem);
+  if (in_smem && P == 8 * kSelThreads) bitonic_sort_desc_reg<8>(buf, s_keys);
+  else if (in_smem && P == 4 * kSelThreads) bitonic_sort_desc_reg<4>(buf, s_keys);
+  else if (in_smem && P == 2 * kSelThreads) bitonic_sort_desc_reg<2>(buf, s_keys);
+  else bitonic_sort_desc(buf, P, s_keys, kSortSmemKeys, in_smem);
   PF_TICK();
 
   // ---- filler for rows [n_real, n): lowest-index pixels that are not winners
