@@ -31,6 +31,8 @@ constexpr int kBucketMax = 1024;  // boundary bucket small enough to be sorted o
 constexpr int kUnroll = 8;       // independent candidate loads in flight per thread
 
 constexpr int kCntStride = 32;   // int32 slots between the per-image candidate counters
+constexpr int kCntKeyMax = 1;    // slots of the counter line: max of the candidates' score bits and max of their
+constexpr int kCntKeyNegMin = 2; // complement (0 = not recorded by the NMS kernel that ran)
 struct DetectWs {
   int32_t* cand_count;   // [B * kCntStride] positive-score survivors written to cand (one 128-byte line per image:
                          // same-line atomics serialise in the L2 atomic unit)
@@ -463,6 +465,7 @@ nms_quad_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, in
   int n_all = 0;
   float4 A[kHalf];
 #pragma unroll 1
+  unsigned kbits_max = 0u, kbits_nmin = 0u;              // largest score bits / largest ~score bits among emitted survivors
   for (int yb = y0; yb < y1; yb += kQuadBatch) {         // centre rows yb .. yb+7, new rows yb+1 .. yb+8
     mask = 0; maskp = 0;
     load_half(A, yb + 1);
@@ -500,12 +503,24 @@ nms_quad_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, in
         dst[0] = ((u64)__float_as_uint(v0) << 32) | (u64)(ibase - (unsigned)((b0 >> 2) * wi + (b0 & 3)));
         if (two) dst[1] = ((u64)__float_as_uint(v1) << 32) | (u64)(ibase - (unsigned)((b1 >> 2) * wi + (b1 & 3)));
         dst += 2;
+        // key range of the image (v1 == v0 when there is no second survivor)
+        kbits_max = max(kbits_max, max(__float_as_uint(v0), __float_as_uint(v1)));
+        kbits_nmin = max(kbits_nmin, max(~__float_as_uint(v0), ~__float_as_uint(v1)));
       }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_all += __shfl_xor_sync(kFull, n_all, o);
   if (lane == 0 && n_all) atomicAdd(counts + b, n_all);
+  // the selection kernel starts its radix walk at the first bit in which the image's keys differ: leave the
+  // range of the score bits beside the candidate counter (same zero-initialised 128-byte line) so that it does
+  // not need a pass over the candidates to find it
+  kbits_max = __reduce_max_sync(kFull, kbits_max);
+  kbits_nmin = __reduce_max_sync(kFull, kbits_nmin);
+  if (lane == 0 && kbits_nmin) {
+    atomicMax(reinterpret_cast<unsigned*>(cand_count) + b * kCntStride + kCntKeyMax, kbits_max);
+    atomicMax(reinterpret_cast<unsigned*>(cand_count) + b * kCntStride + kCntKeyNegMin, kbits_nmin);
+  }
 }
 
 // ---- phase 2: select + sort + centroid ------------------------------------
@@ -761,7 +776,14 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     // common leading bits (scores of one map share sign/exponent bits): start the
     // radix walk at the first differing bit so the histogram bins actually spread
     u64 kmin = ~0ull, kmax = 0ull;
-    for (int base = 0; base < C; base += kSelThreads * kUnroll) {
+    const unsigned rec_max = (unsigned)cand_count[b * kCntStride + kCntKeyMax];
+    const unsigned rec_nmin = (unsigned)cand_count[b * kCntStride + kCntKeyNegMin];
+    const bool recorded = rec_nmin != 0u && (int64_t)cand_count[b * kCntStride] <= cand_cap;   // block uniform
+    if (recorded) {            // range of the score bits left by the NMS kernel: no pass over the candidates
+      kmin = (u64)(~rec_nmin) << 32;
+      kmax = ((u64)rec_max << 32) | 0xffffffffull;
+    }
+    for (int base = 0; !recorded && base < C; base += kSelThreads * kUnroll) {
       u64 k[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -958,43 +980,11 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     __syncthreads();
   }
 
-  // ---- centroid, score, outputs (:243-247, :266-267)
-  const float stepx = 2.0f / (float)(W - 1), stepy = 2.0f / (float)(H - 1);
-  const float* img = score + b * sb;
+  // ---- winners' interior indices; centroid and score follow in keypoint_outputs_kernel (their 3x3 reads are
+  // scattered over the map: one CTA per image keeps too few of them in flight)
   for (int i = tid; i < n; i += kSelThreads) {
     const unsigned idx = i < n_real ? 0xffffffffu - (unsigned)buf[i] : s_fill[i - n_real];
-    const int y0 = idx / wi, x0 = idx - y0 * wi;
-    if (fullmap) {
-      // generate_kpts_single_noavg (:280-336): the pixel's own grid coordinate and score; (H, W) here
-      // are the virtual padded sizes, the real map is the hi x wi "interior"
-      const int64_t o = (int64_t)b * cap_pts + i;
-      idx_out[o] = (int64_t)idx;
-      kps_out[2 * o + 0] = linspace_pm1(x0, wi, 2.0f / (float)(wi - 1));
-      kps_out[2 * o + 1] = linspace_pm1(y0, hi, 2.0f / (float)(hi - 1));
-      kpscore_out[o] = __ldg(img + (int64_t)(y0 + 1) * sy + x0 + 1);
-      continue;
-    }
-    float sx = 0.f, sy_ = 0.f, sw = 0.f, mx = -INFINITY;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const float gy = linspace_pm1(y0 + dy, H, stepy);
-      const float* row = img + (int64_t)(y0 + dy) * sy + x0;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const float p = __ldg(row + dx);
-        const float gx = linspace_pm1(x0 + dx, W, stepx);
-        sx = __fadd_rn(sx, __fmul_rn(p, gx));
-        sy_ = __fadd_rn(sy_, __fmul_rn(p, gy));
-        sw = __fadd_rn(sw, p);
-        mx = fmaxf(mx, p);
-      }
-    }
-    const float wgt = __fdiv_rn(sw, 9.0f);
-    const int64_t o = (int64_t)b * cap_pts + i;
-    idx_out[o] = (int64_t)idx;
-    kps_out[2 * o + 0] = __fdiv_rn(__fdiv_rn(sx, 9.0f), wgt);
-    kps_out[2 * o + 1] = __fdiv_rn(__fdiv_rn(sy_, 9.0f), wgt);
-    kpscore_out[o] = mx;
+    idx_out[(int64_t)b * cap_pts + i] = (int64_t)idx;
   }
   PF_TICK();
   if (debug && b == 0 && tid == 0) {
@@ -1003,6 +993,57 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     printf("\n");
   }
 #undef PF_TICK
+}
+
+// centroid (3x3 score-weighted mean of the bit-exact linspace grid, :243-246), 3x3 maximum (:247) and the
+// gathers (:266-267) at the winners only; one thread per keypoint, the whole batch in one grid
+__global__ void __launch_bounds__(256)
+keypoint_outputs_kernel(const float* __restrict__ score, int H, int W, int64_t sb, int64_t sy, int cap_pts,
+                        const int32_t* __restrict__ status, const int32_t* __restrict__ n_dev,
+                        const int64_t* __restrict__ idx_in, float* __restrict__ kps_out,
+                        float* __restrict__ kpscore_out, int fullmap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*status != 0 || i >= *n_dev) return;
+  const int hi = H - 2, wi = W - 2;
+  const int64_t o = (int64_t)b * cap_pts + i;
+  const unsigned idx = (unsigned)idx_in[o];
+  const int y0 = idx / wi, x0 = idx - y0 * wi;
+  const float* img = score + b * sb;
+  if (fullmap) {
+    // generate_kpts_single_noavg (:280-336): the pixel's own grid coordinate and score; (H, W) here
+    // are the virtual padded sizes, the real map is the hi x wi "interior"
+    kps_out[2 * o + 0] = linspace_pm1(x0, wi, 2.0f / (float)(wi - 1));
+    kps_out[2 * o + 1] = linspace_pm1(y0, hi, 2.0f / (float)(hi - 1));
+    kpscore_out[o] = __ldg(img + (int64_t)(y0 + 1) * sy + x0 + 1);
+    return;
+  }
+  const float stepx = 2.0f / (float)(W - 1), stepy = 2.0f / (float)(H - 1);
+  float p[9];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const float* row = img + (int64_t)(y0 + dy) * sy + x0;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) p[dy * 3 + dx] = __ldg(row + dx);
+  }
+  float sx = 0.f, sy_ = 0.f, sw = 0.f, mx = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const float gy = linspace_pm1(y0 + dy, H, stepy);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const float v = p[dy * 3 + dx];
+      const float gx = linspace_pm1(x0 + dx, W, stepx);
+      sx = __fadd_rn(sx, __fmul_rn(v, gx));
+      sy_ = __fadd_rn(sy_, __fmul_rn(v, gy));
+      sw = __fadd_rn(sw, v);
+      mx = fmaxf(mx, v);
+    }
+  }
+  const float wgt = __fdiv_rn(sw, 9.0f);
+  kps_out[2 * o + 0] = __fdiv_rn(__fdiv_rn(sx, 9.0f), wgt);
+  kps_out[2 * o + 1] = __fdiv_rn(__fdiv_rn(sy_, 9.0f), wgt);
+  kpscore_out[o] = mx;
 }
 
 // POSFEAT_DETECT_FULLMAP: the whole map plays the role of the interior.  The kernels only ever read
@@ -1126,6 +1167,10 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
                                                    (mode & POSFEAT_DETECT_FULLMAP) ? 1 : 0,
                                                    getenv("POSFEAT_SELECT_DEBUG") ? 1 : 0);
   PF_LAUNCH_CHECK("select_kernel");
+  keypoint_outputs_kernel<<<dim3((cap_pts + 255) / 256, B), 256, 0, stream>>>(
+      score, H, W, stride_b, stride_y, cap_pts, w.status, n_out, idx_out, kps_out, kpscore_out,
+      (mode & POSFEAT_DETECT_FULLMAP) ? 1 : 0);
+  PF_LAUNCH_CHECK("keypoint_outputs_kernel");
   return POSFEAT_OK;
 }
 
