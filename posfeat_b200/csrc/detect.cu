@@ -464,8 +464,8 @@ nms_quad_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, in
   const int sy32 = (int)sy;                                      // host checks the row stride fits
   int n_all = 0;
   float4 A[kHalf];
-#pragma unroll 1
   unsigned kbits_max = 0u, kbits_nmin = 0u;              // largest score bits / largest ~score bits among emitted survivors
+#pragma unroll 1
   for (int yb = y0; yb < y1; yb += kQuadBatch) {         // centre rows yb .. yb+7, new rows yb+1 .. yb+8
     mask = 0; maskp = 0;
     load_half(A, yb + 1);
