@@ -326,7 +326,7 @@ extern "C" int posfeat_fetch_taps_f32(const float* fmap_host, float* fmap_dev, i
                                       int64_t sc, int64_t sy, int64_t sx, const float* coord_n, int n,
                                       void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  PF_CHECK_ARG(fmap_host && fmap_dev && coord_n && workspace, "NULL pointer");
+  PF_CHECK_ARG(fmap_host && fmap_dev && workspace && (coord_n || n == 0), "NULL pointer");
   PF_CHECK_ARG(B >= 1 && B <= 65535 && D >= 1 && D <= 512 && h >= 1 && w >= 1 && n >= 0, "bad shape B=%d D=%d h=%d w=%d n=%d",
                B, D, h, w, n);
   PF_CHECK_ARG((int64_t)h * w <= 0x7fffffff - 64, "map of %d x %d pixels is too large", h, w);
@@ -334,11 +334,11 @@ extern "C" int posfeat_fetch_taps_f32(const float* fmap_host, float* fmap_dev, i
                    ((uintptr_t)fmap_dev % 16 == 0),
                "tap staging needs channels-last, 16-byte aligned descriptor maps with D %% 4 == 0");
   PF_CHECK_ARG(ws_bytes >= posfeat_fetch_taps_workspace_bytes(B, h, w), "workspace too small (%zu bytes)", ws_bytes);
-  if (n == 0) return POSFEAT_OK;
   const int words = (int)(((int64_t)h * w + 31) / 32);
   unsigned* bitmap = (unsigned*)workspace;
   unsigned long long* counter = (unsigned long long*)((char*)workspace + ((size_t)B * words * 4 + 255) / 256 * 256);
   PF_CUDA(cudaMemsetAsync(workspace, 0, posfeat_fetch_taps_workspace_bytes(B, h, w), stream));
+  if (n == 0) return POSFEAT_OK;                       // nothing to stage; the pixel counter reads 0
   ProfScope prof(PROF_FETCH, stream);
   mark_taps_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(coord_n, n, h, w, words, bitmap);
   PF_LAUNCH_CHECK("mark_taps_kernel");

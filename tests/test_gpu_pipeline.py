@@ -172,6 +172,10 @@ def test_stage_taps_moves_exactly_the_sampled_pixels(D, h, w, n):
     assert torch.equal(arrived, cover)
     with pytest.raises(ValueError):
         pipe.stage_taps(fmap, torch.empty(b, D, h, w, device="cuda"), kps.cuda())     # NCHW strides differ
+    # no keypoints: nothing moves and the counter is reset
+    f_dev.fill_(float("nan"))
+    pipe.stage_taps(fmap, f_dev, kps[:, :0].cuda())
+    assert pipe.staged_pixels(fmap, f_dev.device) == 0 and bool(torch.isnan(f_dev).all())
 
 
 def test_batched_matcher_equals_single_calls():
