@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._runtime import check, lib, map_ptr, stream_ptr, workspace
+from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace
 from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
@@ -209,7 +209,6 @@ class PairPipeline:
         * ``"direct"`` / ``True``: the sampler reads its taps straight from the pinned map (16.8 MB per
           image requested: pixels shared by two keypoints cross the link twice);
         * ``False``: the whole map is copied first (the plain path)."""
-        dev = torch.device("cuda", torch.cuda.current_device())
         if gather is None:
             gather = "stage" if self.host_gather_applies(fmap_host) else False
         elif gather is True:
@@ -218,6 +217,8 @@ class PairPipeline:
             raise ValueError(f"gather must be 'stage', 'direct', True, False or None, got {gather!r}")
         if gather and not self.host_gather_applies(fmap_host):
             raise ValueError("host gather needs a pinned, channels-last float32 descriptor map")
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
         key = (tuple(score_host.shape), tuple(fmap_host.shape), tuple(fmap_host.stride()), gather)
         if self._host is None or self._host[0] != key:
             self._host = None                            # release the old buffers first
