@@ -167,7 +167,10 @@ def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False, out=Non
     L = lib()
     b, c, h, w = x.shape
     n = coord_n.shape[1]
-    dev = coord_n.device
+    dev = x.device if x.is_cuda else coord_n.device
+    if dev.type != "cuda":
+        raise RuntimeError("sample_l2norm needs device tensors (a pinned host map is accepted with device coordinates); "
+                           "posfeat_b200 has no CPU fallback")
     if out is None:
         out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (b, n, c) or out.dtype != torch.float32 or not out.is_contiguous():
