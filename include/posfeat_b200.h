@@ -255,6 +255,14 @@ int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, 
                                 const float* out, const float* lse, const float* g_out,
                                 float* g_q, float* g_k, void* workspace, size_t ws_bytes, void* stream);
 
+/* compute_prob, losses/preprocess_utils.py:89-115, for callers that want the [B,m,n] probability tensor itself
+ * (the three expectations above fuse it away and never write it).  f1 [B,m,D], f2 [B,n,D] contiguous.
+ * mode 0 ('cos'): prob = softmax_j(scale * <f1_i,f2_j>), scale = sqrt(n) for with_scale else 1; sim (optional,
+ * may be NULL) receives the raw similarities (return_sim).  mode 1 ('euc'): prob = softmax_j(-|f1_i - f2_j|^2)
+ * evaluated as |f1|^2 + |f2|^2 - 2<f1,f2> like the reference; sim must be NULL. */
+int posfeat_compute_prob_f32(const float* f1, const float* f2, int B, int m, int n, int D, int mode,
+                             float scale, float* prob, float* sim, void* stream);
+
 /* DiskLoss dense affinity, losses/kploss.py:158-182 (second training stage): with A = T*<q_i,k_j> - T,
  * p_ij = softmax_j(A)_ij * softmax_i(A)_ij and log p_ij the sum of the two log-softmaxes, computes per row i
  *   rows_out[b,i] = { sum_j acc r p (log p + logp_i + logp_j),  sum_j acc r p,  sum_j p,  max_j p }

@@ -211,6 +211,29 @@ def golden_corr():
     print("corr ok", cg.shape)
 
 
+def golden_prob():
+    """compute_prob (losses/preprocess_utils.py:89-115): every option, plus gradients of a scalar of prob."""
+    g = gen(505)
+    out = {}
+    f1 = F.normalize(torch.randn(2, 37, 24, generator=g), dim=-1) * 2.5
+    f2 = F.normalize(torch.randn(2, 150, 24, generator=g), dim=-1) * 2.0
+    wgt = torch.randn(2, 37, 150, generator=g)
+    out.update(f1=f1.numpy(), f2=f2.numpy(), wgt=wgt.numpy())
+    for name, kw in (("cos", {}), ("cos_scale", dict(with_scale=True)), ("euc", dict(loss_distance="euc"))):
+        a = f1.clone().requires_grad_(True)
+        b = f2.clone().requires_grad_(True)
+        prob = pu.compute_prob(a, b, **kw)
+        (prob * wgt).sum().backward()
+        out[f"{name}/prob"] = prob.detach().numpy()
+        out[f"{name}/g1"] = a.grad.numpy()
+        out[f"{name}/g2"] = b.grad.numpy()
+    prob, sim = pu.compute_prob(f1, f2, return_sim=True)
+    out["sim/prob"] = prob.numpy()
+    out["sim/sim"] = sim.numpy()
+    np.savez_compressed(os.path.join(OUT, "prob.npz"), **out)
+    print("prob ok", prob.shape)
+
+
 def random_fundamental(b, h, w, g):
     Fs = []
     for _ in range(b):
@@ -256,6 +279,7 @@ def golden_preprocess():
     def gen_wrap(*a, **k):
         r = orig_gen(*a, **k)
         rec["coord1_n"], rec["coord2_n"] = r[0].clone(), r[1].clone()
+        rec["all"] = tuple(x.clone() if torch.is_tensor(x) else x for x in r)
         return r
     P.kps_generator = gen_wrap
     rands = []
@@ -265,12 +289,24 @@ def golden_preprocess():
         t = orig_rand(*a, **k)
         rands.append(t.clone())
         return t
+    # the line search runs under no_grad and makes a discrete choice (position of the largest probability): its
+    # results are recorded so that the float64 run below can replay them instead of re-deciding near ties
+    line_rec = []
+    orig_line = pp.epipolar_line_search
+
+    def line_wrap(*a, **k):
+        r = orig_line(*a, **k)
+        line_rec.append(tuple(x.clone() for x in r))
+        return r
     torch.manual_seed(7)
     torch.rand = rand_wrap
+    pp.epipolar_line_search = line_wrap
     try:
         processed = P(inputs, outputs)
     finally:
         torch.rand = orig_rand
+        pp.epipolar_line_search = orig_line
+    assert len(line_rec) == 2
     assert len(rands) == 2, len(rands)
     loss_cfg = dict(grid_cost_thr=0.5, win_cost_thr=0.1, use_std_as_weight=True,
                     weight_grid=0.3, weight_window=1)
@@ -290,6 +326,56 @@ def golden_preprocess():
         out["c_" + k] = v.detach().numpy()
     np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
     print("preprocess ok; loss", float(loss), "valid", processed["valid_epi1"].float().mean().item())
+
+    # ---- the same run in float64 (coordinates replayed, and the results of the no_grad line search -- a discrete
+    # argmax plus jitter -- replayed from the float32 run): the yardstick that tells how much of a float32
+    # implementation's deviation is the reference's own rounding noise.  Stored rounded to float32
+    # (6e-8 relative, far below the 1e-5 bar) to keep the fixture small.
+    P64 = pp.Preprocess_Line2Window(cfg)
+    P64.kps_generator = lambda *a, **k: tuple(x.double() if torch.is_tensor(x) and x.dtype.is_floating_point else x
+                                              for x in rec["all"])
+    x1d = xf1.detach().double().requires_grad_()
+    x2d = xf2.detach().double().requires_grad_()
+    in64 = dict(im1=inputs["im1"].double(), im2=inputs["im2"].double(), F1=inputs["F1"].double(), F2=inputs["F2"].double())
+    out64 = dict(preds1=dict(global_map=preds1["global_map"].double(), local_map=x1d, local_point=preds1["local_point"].double()),
+                 preds2=dict(global_map=preds2["global_map"].double(), local_map=x2d, local_point=preds2["local_point"].double()),
+                 epoch=0)
+    line_replay = [tuple(x.double() if x.dtype.is_floating_point else x for x in r) for r in line_rec]
+    pp.epipolar_line_search = lambda *a, **k: line_replay.pop(0)
+    try:
+        pr64 = P64(in64, out64)
+    finally:
+        pp.epipolar_line_search = orig_line
+    loss64, _ = EpipolarLoss_full(loss_cfg)(in64, out64, pr64)
+    loss64.backward()
+    # ---- the float32 reference once more with the float64 run's std values as (detached) loss weights: what is
+    # left between this and the float64 run is the rounding error of the reference's differentiable float32 path
+    # alone (the weights 1/std amplify the float32 cancellation noise of std by orders of magnitude otherwise)
+    std_keys = ("feat1g_std", "feat2g_std", "feat1w_std", "feat2w_std")
+    xf1.grad = None
+    xf2.grad = None
+    replay32 = [tuple(x.clone() for x in r) for r in line_rec]
+    P.kps_generator = lambda *a, **k: rec["all"]
+    pp.epipolar_line_search = lambda *a, **k: replay32.pop(0)
+    try:
+        pr32 = P(inputs, outputs)
+    finally:
+        pp.epipolar_line_search = orig_line
+    for k in std_keys:
+        assert torch.equal(pr32[k], processed[k])           # the replayed float32 run is the recorded one
+        pr32[k] = pr64[k].detach().float()
+    loss32s, _ = L(inputs, outputs, pr32)
+    loss32s.backward()
+    o64 = dict(loss=np.array(float(loss64)), gxf1=x1d.grad.numpy().astype(np.float32), gxf2=x2d.grad.numpy().astype(np.float32),
+               loss_f32_std64=np.array(float(loss32s)), gxf1_f32_std64=xf1.grad.numpy(), gxf2_f32_std64=xf2.grad.numpy())
+    print("float32 reference with float64 weights: loss dev", abs(float(loss32s) - float(loss64)) / float(loss64), "grad dev",
+          float((xf1.grad.double() - x1d.grad).abs().max() / x1d.grad.abs().max()))
+    for k, v in pr64.items():
+        if torch.is_tensor(v):
+            o64["p_" + k] = v.detach().numpy().astype(np.float32) if v.dtype.is_floating_point else v.numpy()
+    np.savez_compressed(os.path.join(OUT, "preprocess_f64.npz"), **o64)
+    print("preprocess float64 ok; loss", float(loss64), "| fp32 run deviates by", abs(float(loss64) - float(loss)) / float(loss64),
+          "(loss),", float((xf1.grad.double() - x1d.grad).abs().max() / x1d.grad.abs().max()), "(grad, rel to max)")
 
 
 def golden_disk():
@@ -334,7 +420,7 @@ def golden_disk():
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])                      # e.g. `python oracle/make_golden.py detect_ext`
-    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_preprocess, golden_disk):
+    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_prob, golden_preprocess, golden_disk):
         if not only or fn.__name__[len("golden_"):] in only:
             fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

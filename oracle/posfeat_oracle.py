@@ -357,6 +357,94 @@ def mnn_matcher(desc_a, desc_b, exact=False, return_nn=False):
     return (m, nn12, nn21) if return_nn else m
 
 
+_C_LIB = False
+
+
+def _c_oracle():
+    """oracle/_build/libposfeat_oracle.so (built by `make -C oracle` / __graft_entry__.build()), or None."""
+    global _C_LIB
+    if _C_LIB is False:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libposfeat_oracle.so")
+        _C_LIB = None
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            p = ctypes.c_void_p
+            lib.posfeat_oracle_mnn_f64.restype = ctypes.c_int
+            lib.posfeat_oracle_mnn_f64.argtypes = [p, ctypes.c_int64, p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                                   p, p, p, p, p, p]
+            _C_LIB = lib
+    return _C_LIB
+
+
+def _mnn_f64_c(lib, desc_a, desc_b):
+    import os
+    a = np.ascontiguousarray(desc_a, dtype=np.float32)
+    b = np.ascontiguousarray(desc_b, dtype=np.float32)
+    if not (np.array_equal(a, np.asarray(desc_a)) and np.array_equal(b, np.asarray(desc_b))):
+        raise ValueError("the C oracle takes float32 descriptors (their products are exact in float64)")
+    N, M, D = a.shape[0], b.shape[0], a.shape[1]
+    nn12, nn21 = np.empty(N, np.int64), np.empty(M, np.int64)
+    rb, rs, cb, cs = np.empty(N), np.empty(N), np.empty(M), np.empty(M)
+    st = lib.posfeat_oracle_mnn_f64(a.ctypes.data, N, b.ctypes.data, M, D, os.cpu_count() or 1, nn12.ctypes.data,
+                                    rb.ctypes.data, rs.ctypes.data, nn21.ctypes.data, cb.ctypes.data, cs.ctypes.data)
+    if st != 0:
+        raise RuntimeError(f"posfeat_oracle_mnn_f64 failed with status {st}")
+    ids = np.arange(N)
+    keep = nn21[nn12] == ids
+    return np.stack([ids[keep], nn12[keep]], -1).astype(np.int64), nn12, nn21, rb - rs, cb - cs
+
+
+def mnn_blocked_f64(desc_a, desc_b, block=2048, force_numpy=False):
+    """mnn_matcher for sizes whose similarity matrix does not fit in memory (BASELINE config 5: 64k x 64k is
+    34 GB in float64): the same maths as mnn_from_sim on the exact float64 similarities, evaluated in row
+    blocks.  First maximum wins in both directions (np.argmax inside a block; a later block replaces a column
+    maximum only when strictly larger).  Returns (matches, nn12, nn21, row_gap, col_gap): the gaps between
+    the largest and the second largest value of every row / column tell a caller whether a disagreement is
+    a float64 tie.  When the C part of the oracle is built (oracle/mnn_f64.c -> oracle/_build, `make -C oracle`)
+    it does the work with all host threads -- the 64k x 64k case takes seconds instead of minutes; the numpy
+    form below is the same algorithm and the two are tested against each other."""
+    lib = None if force_numpy else _c_oracle()
+    if lib is not None:
+        return _mnn_f64_c(lib, desc_a, desc_b)
+    a = np.ascontiguousarray(desc_a, dtype=np.float64)
+    bt = np.ascontiguousarray(np.asarray(desc_b, dtype=np.float64).T)
+    N, M = a.shape[0], bt.shape[1]
+    nn12 = np.empty(N, np.int64)
+    row_gap = np.empty(N, np.float64)
+    cmax = np.full(M, -np.inf)
+    cmax2 = np.full(M, -np.inf)
+    nn21 = np.zeros(M, np.int64)
+    for i0 in range(0, N, block):
+        s = a[i0:i0 + block] @ bt                                  # [blk, M] exact products, float64 sums
+        j = np.argmax(s, axis=1)
+        nn12[i0:i0 + block] = j
+        r = np.arange(s.shape[0])
+        top = s[r, j]
+        if M > 1:
+            s[r, j] = -np.inf
+            row_gap[i0:i0 + block] = top - s.max(axis=1)
+            s[r, j] = top
+        else:
+            row_gap[i0:i0 + block] = np.inf
+        bi = np.argmax(s, axis=0)
+        c = np.arange(M)
+        bm = s[bi, c]
+        if s.shape[0] > 1:
+            s[bi, c] = -np.inf
+            bm2 = s.max(axis=0)
+        else:
+            bm2 = np.full(M, -np.inf)
+        better = bm > cmax
+        cmax2 = np.where(better, np.maximum(cmax, bm2), np.maximum(cmax2, bm))
+        nn21 = np.where(better, bi + i0, nn21)
+        cmax = np.where(better, bm, cmax)
+    ids = np.arange(N)
+    keep = nn21[nn12] == ids
+    return np.stack([ids[keep], nn12[keep]], -1).astype(np.int64), nn12, nn21, row_gap, cmax - cmax2
+
+
 def _top2(sim):
     order = np.argsort(-sim, axis=1, kind="stable")[:, :2]
     vals = np.take_along_axis(sim, order, 1)
@@ -389,6 +477,23 @@ def softmax(z, axis=-1):
     z = z - z.max(axis=axis, keepdims=True)
     e = np.exp(z)
     return e / e.sum(axis=axis, keepdims=True)
+
+
+def compute_prob(feat1, feat2, loss_distance="cos", with_scale=False, return_sim=False, dtype=F32):
+    """losses/preprocess_utils.py:89-115.  feat1 [B, m, d], feat2 [B, n, d] -> prob [B, m, n]."""
+    assert loss_distance in ("cos", "euc")
+    if return_sim:
+        assert loss_distance == "cos"
+    f1 = np.asarray(feat1, dtype=dtype)
+    f2 = np.asarray(feat2, dtype=dtype)
+    sim = f1 @ f2.transpose(0, 2, 1)
+    if loss_distance == "cos":
+        scale = dtype(np.sqrt(dtype(f2.shape[1]))) if with_scale else dtype(1)      # :102-106
+        prob = softmax(scale * sim, -1)
+    else:
+        dist = (f1 ** 2).sum(-1, keepdims=True) + (f2 ** 2).sum(-1, keepdims=True).transpose(0, 2, 1) - 2 * sim   # :108-111
+        prob = softmax(-dist, -1)
+    return (prob, sim) if return_sim else prob
 
 
 def get_expected_correspondence_locs(feat1, featmap2, with_std=False, dtype=F32):

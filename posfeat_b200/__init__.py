@@ -10,7 +10,7 @@ from ._lib import LIB_PATH, PosfeatError  # noqa: F401
 
 __all__ = ["generate_kpts_single", "generate_kpts_single_noavg", "sample_feat_by_coord", "mnn_matcher",
            "mutual_nn_matcher", "ratio_matcher", "mutual_nn_ratio_matcher", "AsyncDescWriter",
-           "normalize_coords", "denormalize_coords", "install", "LIB_PATH", "PosfeatError"]
+           "normalize_coords", "denormalize_coords", "compute_prob", "install", "LIB_PATH", "PosfeatError"]
 
 _LAZY = {
     "generate_kpts_single": "preprocess_utils", "sample_feat_by_coord": "preprocess_utils",
@@ -18,7 +18,7 @@ _LAZY = {
     "denormalize_coords": "preprocess_utils", "detect_topk": "preprocess_utils",
     "mnn_match": "preprocess_utils", "sample_l2norm": "preprocess_utils",
     "mutual_nn_matcher": "matchers",
-    "get_expected_correspondence_locs": "preprocess",
+    "get_expected_correspondence_locs": "preprocess", "compute_prob": "preprocess",
     "get_expected_correspondence_within_window": "preprocess",
     "Preprocess_Line2Window": "preprocess",
     "DiskLoss": "kploss",
@@ -42,6 +42,9 @@ def install(putils_module, matchers_module=None):
     from . import matchers, preprocess_utils as pu
     for name in ("generate_kpts_single", "generate_kpts_single_noavg", "sample_feat_by_coord", "mnn_matcher"):
         setattr(putils_module, name, getattr(pu, name))
+    from . import preprocess as pp
+    for name in ("compute_prob", "get_expected_correspondence_locs", "get_expected_correspondence_within_window"):
+        setattr(putils_module, name, getattr(pp, name))
     if matchers_module is not None:
         for name in ("mutual_nn_matcher", "ratio_matcher", "mutual_nn_ratio_matcher"):
             setattr(matchers_module, name, getattr(matchers, name))

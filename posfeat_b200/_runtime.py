@@ -28,13 +28,24 @@ def to_device(t: torch.Tensor, dtype=torch.float32):
 
 
 def workspace(key: str, nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (uint8)."""
-    k = (key, torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer (uint8), one per (name, device, CURRENT STREAM): two host threads (or one
+    thread alternating between streams) that call the same op on different streams never share scratch
+    memory, so the calls are re-entrant ("safe from multiple host threads on different streams").
+    Calls that hand data to each other through a workspace (sampler -> matcher operands) run on one stream
+    and therefore see the same buffer."""
+    d = torch.device(device)
+    idx = d.index if d.index is not None else torch.cuda.current_device()
+    k = (key, idx, torch.cuda.current_stream(idx).cuda_stream)
     buf = _workspaces.get(k)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=d)
         _workspaces[k] = buf
     return buf
+
+
+def release_workspaces():
+    """Drop every cached scratch buffer (e.g. after a one-off very large call)."""
+    _workspaces.clear()
 
 
 def stream_ptr(device=None) -> int:

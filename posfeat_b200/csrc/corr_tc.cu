@@ -734,11 +734,8 @@ int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, i
   if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;
   if (int e = make_map_f32(&mkh, w.kh, Dp, (int64_t)B * p.m_pad)) return e;
   if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
-    attr_set = true;
-  }
+  // per device/context attribute: set on every call (cheap), never cached in a process-global flag
+  PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
   dim3 grid(p.splits, p.q_tiles, B);
   corr_tc_fwd_kernel<0><<<grid, kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
   PF_LAUNCH_CHECK("corr_tc_fwd_kernel");
@@ -811,11 +808,8 @@ static int run_gemm(float* Ah, float* Al, float* Bh, float* Bl, int B, int M_pad
   if (int e = make_map_f32(&mal, Al, Kdim, (int64_t)B * M_pad)) return e;
   if (int e = make_map_f32(&mbh, Bh, Kdim, (int64_t)B * Dp, Dp)) return e;
   if (int e = make_map_f32(&mbl, Bl, Kdim, (int64_t)B * Dp, Dp)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(corr_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGmSmemAlloc));
-    attr_set = true;
-  }
+  // per device/context attribute: set on every call (cheap), never cached in a process-global flag
+  PF_CUDA(cudaFuncSetAttribute(corr_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGmSmemAlloc));
   corr_tc_gemm_kernel<<<dim3(g.splits, M_pad / 128, B), kGmThreads, kGmSmemAlloc, stream>>>(mah, mal, mbh, mbl, g);
   PF_LAUNCH_CHECK("corr_tc_gemm_kernel");
   if (g.splits > 1) {
@@ -864,11 +858,8 @@ int corr_tc_bwd(const float* q, const float* k, const float* v, int v_batched, i
   if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;
   if (int e = make_map_f32(&mkh, w.kh, Dp, (int64_t)B * p.m_pad)) return e;
   if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
-    attr_set = true;
-  }
+  // per device/context attribute: set on every call (cheap), never cached in a process-global flag
+  PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
   corr_tc_fwd_kernel<1><<<dim3(p.splits, p.q_tiles, B), kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
   PF_LAUNCH_CHECK("corr_tc_fwd_kernel<W>");
   if (g_q)
@@ -966,11 +957,8 @@ int corr_disk_rows(const float* q, const float* k, const float* rowtab, const fl
   if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;
   if (int e = make_map_f32(&mkh, w.kh, Dp, (int64_t)B * p.m_pad)) return e;
   if (int e = make_map_f32(&mkl, w.kl, Dp, (int64_t)B * p.m_pad)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
-    attr_set = true;
-  }
+  // per device/context attribute: set on every call (cheap), never cached in a process-global flag
+  PF_CUDA(cudaFuncSetAttribute(corr_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemAlloc));
   corr_tc_fwd_kernel<2><<<dim3(p.splits, p.q_tiles, B), kCtThreads, kCtSmemAlloc, stream>>>(mqh, mql, mkh, mkl, p);
   PF_LAUNCH_CHECK("corr_tc_fwd_kernel<disk>");
   corr_disk_merge_kernel<<<(int)(((int64_t)B * n + 255) / 256), 256, 0, stream>>>(w.part4, B, n, p.q_tiles, p.splits,

@@ -1154,12 +1154,9 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
   PF_CHECK_ARG(counts && n_out && idx_out && kps_out && kpscore_out && workspace, "NULL output pointer");
   DetectWs w = carve(workspace, B, H, W, cap_pts);
   if (ws_bytes < w.total) return set_error(POSFEAT_EWORKSPACE, "detect workspace: need %zu bytes, got %zu", w.total, ws_bytes);
-  static bool attr_set = false;
   const size_t smem = sizeof(u64) * kSortSmemKeys;
-  if (!attr_set) {
-    PF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per device/context attribute: set on every call (cheap), never cached in a process-global flag
+  PF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_SELECT, stream);
   select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
                                                    counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,

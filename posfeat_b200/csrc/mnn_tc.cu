@@ -1147,6 +1147,11 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   const int Np = pad_rows(N), Mp = pad_rows(M);
   if ((long long)P * Np >= (1ll << 31) || (long long)P * Mp >= (1ll << 31))
     return set_error(POSFEAT_EINVAL, "batched matcher: pairs * rows exceeds 2^31");
+  // matches-only calls (nn21 == NULL) verify mutuality per column chunk, which is limited to kVerMaxChunks chunks:
+  // refuse BEFORE anything is queued (the two-direction path needs an nn21 buffer to write to)
+  if (nn21 == nullptr && top12 == nullptr && w.pitch[0] > kVerMaxChunks)
+    return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher (nn21 == NULL) supports M <= %d; pass an nn21 buffer",
+                     kVerMaxChunks * kChunk);
 
   if (!prepared) {   // otherwise the sampler already left bf16 rows, norms and maxima in the workspace (tc_prep_sink)
     PF_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(MatStats) * 2 * P, stream));

@@ -62,13 +62,39 @@ def save_desc(inputs, processed, desc_root, postfix, save_npz=True, save_h5=Fals
     if save_npz:
         _write_npz(save_path + ".{}".format(postfix), kpt, scores, desc)
     if save_h5:
-        try:
-            import h5py
-        except ImportError as e:   # the authoring image has no h5py
-            raise RuntimeError("save_h5=True needs h5py, which is not installed") from e
-        h5_root = desc_root.rstrip("/") + "h5"
-        stem = name.split(".")[0]
-        seq, key = os.path.dirname(stem), os.path.basename(stem)
+        _write_h5(desc_root, name, kpt, scores, desc, image_size)
+    return message
+
+
+def _write_npz(path, kpt, scores, desc):
+    with open(path, "wb") as f:
+        np.savez(f, keypoints=kpt, scores=scores, descriptors=desc)
+
+
+_h5_lock = None
+
+
+def _write_h5(desc_root, name, kpt, scores, desc, image_size=None):
+    """The h5 outputs of managers/extractor.py:273-314 (layout per SURVEY.md section 3.4; the reference's own
+    branch references undefined names w, h, grp, fh5):
+      <desc_root>h5/<seq>/{keypoints,descriptors,scores,scales}.h5 : dataset <image stem> = array
+          (image-matching-benchmark format; scales = ones_like(scores))
+      <desc_root>h5/feat.h5 : group <name1> with datasets keypoints, scores, descriptors, image_size=[w, h]
+          (hloc format)
+    Files are opened in append mode like the reference; writers are serialised (HDF5 files are not safe to
+    append to from several threads)."""
+    global _h5_lock
+    try:
+        import h5py
+    except ImportError as e:   # the authoring image has no h5py
+        raise RuntimeError("save_h5=True needs h5py, which is not installed") from e
+    if _h5_lock is None:
+        import threading
+        _h5_lock = threading.Lock()
+    h5_root = str(desc_root).rstrip("/") + "h5"
+    stem = name.split(".")[0]
+    seq, key = "/".join(stem.split("/")[:-1]), stem.split("/")[-1]
+    with _h5_lock:
         os.makedirs(os.path.join(h5_root, seq), exist_ok=True)
         for fname, data in (("keypoints.h5", kpt), ("descriptors.h5", desc), ("scores.h5", scores),
                             ("scales.h5", np.ones_like(scores))):
@@ -81,12 +107,6 @@ def save_desc(inputs, processed, desc_root, postfix, save_npz=True, save_h5=Fals
             grp.create_dataset("descriptors", data=desc)
             if image_size is not None:
                 grp.create_dataset("image_size", data=np.asarray(image_size))
-    return message
-
-
-def _write_npz(path, kpt, scores, desc):
-    with open(path, "wb") as f:
-        np.savez(f, keypoints=kpt, scores=scores, descriptors=desc)
 
 
 class AsyncDescWriter:
@@ -96,13 +116,17 @@ class AsyncDescWriter:
     calls (managers/extractor.py:254-316: D2H copy, ``np.savez``, disk).  Here the
     D2H copies go to pinned staging buffers on a side stream and a small thread pool
     does the ``np.savez``; the GPU keeps working on the next image.  File contents and
-    names are identical to ``save_desc(save_npz=True)``.  ``close()`` (or leaving the
+    names are identical to ``save_desc`` (``.npz`` and, with ``save_h5=True``, the h5 files: those are
+    appended to under a lock, one image at a time).  ``close()`` (or leaving the
     ``with`` block) waits for all pending files and re-raises the first writer error.
     """
 
-    def __init__(self, desc_root, postfix, workers=4, max_pending=64):
+    def __init__(self, desc_root, postfix, workers=4, max_pending=64, save_npz=True, save_h5=False):
         from concurrent.futures import ThreadPoolExecutor
+        if save_h5:
+            import h5py  # noqa: F401  (fail at construction, not in a worker thread)
         self.desc_root, self.postfix = desc_root, postfix
+        self.save_npz, self.save_h5 = bool(save_npz), bool(save_h5)
         self.pool = ThreadPoolExecutor(max_workers=workers)
         self.pending = []
         self.max_pending = max_pending
@@ -122,8 +146,11 @@ class AsyncDescWriter:
         t.record_stream(self.copy_stream)
         return host, ev
 
-    def save(self, inputs, processed):
+    def save(self, inputs, processed, image_size=None):
         name = inputs["name1"][0]
+        if image_size is None and self.save_h5 and "im1" in inputs:
+            h, w = inputs["im1"].shape[2:]
+            image_size = (w, h)
         path = os.path.join(self.desc_root, name) + ".{}".format(self.postfix)
         os.makedirs(os.path.dirname(path), exist_ok=True)
         kpt = np.array(processed["kpt"], copy=True)
@@ -134,7 +161,10 @@ class AsyncDescWriter:
             for e in (e1, e2):
                 if e is not None:
                     e.synchronize()
-            _write_npz(path, kpt, score.numpy(), desc.numpy())
+            if self.save_npz:
+                _write_npz(path, kpt, score.numpy(), desc.numpy())
+            if self.save_h5:
+                _write_h5(self.desc_root, name, kpt, score.numpy(), desc.numpy(), image_size)
             return path
 
         self.pending.append(self.pool.submit(job))

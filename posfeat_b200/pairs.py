@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace
-from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
+from .preprocess_utils import MIN_PTS, ONE_DIR_MAX_M, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
 def shard(items, rank: int, world: int):
@@ -78,19 +78,25 @@ class PairPipeline:
         """desc [2P,n,D]: images (2i, 2i+1) form pair i.  Returns matches
         [P,n,2] int64 and n_matches [P] int32 (device).  ``prepared``: the workspace ``ws_key`` already
         holds the operands written by sample_for_pairs."""
+        return self.match_views(desc[0::2], desc[1::2], ws_key, prepared)      # strided views: pair stride = 2 images
+
+    def match_views(self, da: torch.Tensor, db: torch.Tensor, ws_key: str = "mnn", prepared: bool = False):
+        """Batched matcher over P pairs given as two [P,n,D] views with uniform pair strides (any stride,
+        including 0: ``desc[q].expand(K, n, D)`` matches one query image against K database images, the shape
+        of evaluations/aachen/reconstruct_pipeline.py:182-221).  Returns (matches [P,n,2] int64, n_matches [P])."""
         L = lib()
-        b, n, D = desc.shape
-        P = b // 2
-        dev = desc.device
+        P, n, D = da.shape
+        if tuple(db.shape) != (P, n, D) or da.stride(2) != 1 or db.stride(2) != 1:
+            raise ValueError("match_views: two [P,n,D] views with unit channel stride and equal shapes are required")
+        dev = da.device
         matches = torch.empty((P, n, 2), dtype=torch.int64, device=dev)
         nm = torch.empty(P, dtype=torch.int32, device=dev)
         nn12 = torch.empty((P, n), dtype=torch.int32, device=dev)
         # nn21 is not requested: the tensor-core matcher then computes one direction and verifies
-        # mutuality by a column scan; the exact SIMT matcher (small sizes / algo=1) needs the buffer
+        # mutuality per column chunk; the exact SIMT matcher (small sizes / algo=1) needs the buffer
         use_simt = not self._tc_applies(n, D)
         algo = (_lib.MNN_TC | _lib.MNN_PREPARED) if prepared else self.mnn_algo
-        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if use_simt else None
-        da, db = desc[0::2], desc[1::2]          # strided views: pair stride = 2 images
+        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if (use_simt or n > ONE_DIR_MAX_M) else None
         with torch.cuda.device(dev):
             ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, _lib.MNN_TC if prepared else self.mnn_algo)
             ws = workspace(ws_key, ws_bytes, dev)

@@ -149,6 +149,65 @@ def corr_expect(q, k, v, scale=1.0, want_lse=False):
     return out, lse
 
 
+class ComputeProb(torch.autograd.Function):
+    """softmax over the last axis of the (scaled) similarity / negative squared distance, materialised by
+    posfeat_compute_prob_f32; the backward pass is the softmax Jacobian followed by two batched products on
+    the saved probabilities (plain tensor ops: nothing on the training path differentiates through this
+    stand-alone form, the fused expectations have their own backward kernels)."""
+
+    @staticmethod
+    def forward(ctx, feat1, feat2, mode, scale, want_sim):
+        require_cuda()
+        a, b = _f32c(feat1), _f32c(feat2)
+        B, m, D = a.shape
+        n = b.shape[1]
+        prob = torch.empty((B, m, n), dtype=torch.float32, device=a.device)
+        sim = torch.empty((B, m, n), dtype=torch.float32, device=a.device) if want_sim else None
+        with torch.cuda.device(a.device):
+            check(lib().posfeat_compute_prob_f32(a.data_ptr(), b.data_ptr(), B, m, n, D, int(mode), float(scale),
+                                                 prob.data_ptr(), ptr(sim), stream_ptr(a.device)))
+        ctx.save_for_backward(a, b, prob)
+        ctx.mode, ctx.scale = int(mode), float(scale)
+        return prob, sim
+
+    @staticmethod
+    def backward(ctx, g_prob, g_sim):
+        a, b, prob = ctx.saved_tensors
+        g = g_prob.to(torch.float32)
+        gl = prob * (g - (g * prob).sum(-1, keepdim=True))            # d loss / d logits
+        if g_sim is not None:                                          # return_sim: sim = raw <a,b> also carries gradient
+            gl_sim = g_sim.to(torch.float32)
+        else:
+            gl_sim = None
+        if ctx.mode == 0:
+            gs = ctx.scale * gl if gl_sim is None else ctx.scale * gl + gl_sim
+            ga = gs @ b if ctx.needs_input_grad[0] else None
+            gb = gs.transpose(1, 2) @ a if ctx.needs_input_grad[1] else None
+        else:   # logits = -(|a|^2 + |b|^2 - 2 a.b)
+            ga = (2 * (gl @ b) - 2 * a * gl.sum(2, keepdim=True)) if ctx.needs_input_grad[0] else None
+            gb = (2 * (gl.transpose(1, 2) @ a) - 2 * b * gl.sum(1).unsqueeze(-1)) if ctx.needs_input_grad[1] else None
+        return ga, gb, None, None, None
+
+
+def compute_prob(feat1, feat2, loss_distance='cos', with_scale=False, return_sim=False):
+    """losses/preprocess_utils.py:89-115: feat1 [B,m,d], feat2 [B,n,d] -> prob [B,m,n]
+    (softmax over n of scale*<f1,f2> for 'cos', of -|f1-f2|^2 for 'euc'); ``return_sim`` also returns
+    the raw similarities ('cos' only).  Same assertion behaviour as the reference."""
+    assert loss_distance in ['cos', 'euc']
+    if return_sim:
+        assert loss_distance == 'cos'
+    if feat1.dim() != 3 or feat2.dim() != 3 or feat1.shape[0] != feat2.shape[0] or feat1.shape[2] != feat2.shape[2]:
+        raise RuntimeError(f"compute_prob: expected [B,m,d] and [B,n,d], got {tuple(feat1.shape)} {tuple(feat2.shape)}")
+    mode = 0 if loss_distance == 'cos' else 1
+    # the reference builds the scale as a float32 tensor: sqrt is taken in float32
+    scale = float(torch.tensor(float(feat2.shape[1]), dtype=torch.float32).sqrt()) if (with_scale and mode == 0) else 1.0
+    prob, sim = ComputeProb.apply(feat1, feat2, mode, scale, bool(return_sim))
+    out_dtype = feat1.dtype if feat1.dtype.is_floating_point else torch.float32
+    if return_sim:
+        return prob.to(out_dtype), sim.to(out_dtype)
+    return prob.to(out_dtype)
+
+
 def get_expected_correspondence_locs(feat1, featmap2, with_std=False):
     """losses/preprocess_utils.py:55-82.  feat1 [B,n,d], featmap2 [B,d,h,w] ->
     expected normalised xy [B,n,2]; with_std: (xy, std [B,n], kurtosis [B,n], prob [B,n,hw])."""
@@ -161,9 +220,9 @@ def get_expected_correspondence_locs(feat1, featmap2, with_std=False):
         return exp_xy
     var = out[..., 2:] - exp_xy ** 2
     std = torch.sum(torch.sqrt(torch.clamp(var, min=1e-10)), -1)
-    # prob / kurtosis are auxiliary outputs nothing on the training path consumes; they
-    # are materialised with plain tensor ops only because the reference returns them
-    prob = torch.softmax(feat1 @ keys.transpose(1, 2), dim=-1)
+    # prob / kurtosis are auxiliary outputs nothing on the training path consumes; prob is materialised by
+    # the stand-alone compute_prob kernel only because the reference returns it
+    prob = compute_prob(feat1, keys)
     kurt = torch.pow(grid[None, None] - exp_xy.unsqueeze(-2), 4).mean(-2) / torch.pow(var, 2)
     return exp_xy, std, (kurt / 10.).clamp(0, 1).mean(-1), prob
 

@@ -17,6 +17,7 @@ from . import _lib
 from ._runtime import check, lib, map_ptr, ptr, require_cuda, stream_ptr, to_device, workspace
 
 MIN_PTS = 128   # losses/preprocess_utils.py:260-261
+ONE_DIR_MAX_M = 65536   # matches-only (nn21 == NULL) limit of the tensor-core matcher (mnn_tc.cu kVerMaxChunks * 8)
 
 
 # ---------------------------------------------------------------- coordinates
@@ -165,12 +166,22 @@ def sample_l2norm(x, coord_n, norm=False, n_valid=None, want_bf16=False, out=Non
     channels_last; returns [b,n,c] float32 (and a bf16 copy if asked).  x may also be a pinned host
     tensor: the kernel then reads the taps over the host link (coord_n decides the device)."""
     L = lib()
+    if x.dim() != 4 or coord_n.dim() != 3 or coord_n.shape[-1] != 2 or coord_n.shape[0] != x.shape[0]:
+        raise ValueError(f"expected x [b,c,h,w] and coord_n [b,n,2], got {tuple(x.shape)} {tuple(coord_n.shape)}")
     b, c, h, w = x.shape
     n = coord_n.shape[1]
     dev = x.device if x.is_cuda else coord_n.device
-    if dev.type != "cuda":
-        raise RuntimeError("sample_l2norm needs device tensors (a pinned host map is accepted with device coordinates); "
-                           "posfeat_b200 has no CPU fallback")
+    if dev.type != "cuda" or not coord_n.is_cuda or coord_n.device != dev:
+        raise RuntimeError("sample_l2norm needs device tensors on one device (a pinned host map is accepted with device "
+                           "coordinates); posfeat_b200 has no CPU fallback")
+    # the kernel reads float32 through raw pointers: convert anything else first (an fp16/bf16 backbone map
+    # handed over as-is would be read out of bounds)
+    if x.dtype != torch.float32:
+        if not x.is_cuda:
+            raise TypeError(f"a host-resident descriptor map must be float32 (got {x.dtype})")
+        x = x.to(torch.float32)
+    if coord_n.dtype != torch.float32:
+        coord_n = coord_n.to(torch.float32)
     if out is None:
         out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (b, n, c) or out.dtype != torch.float32 or not out.is_contiguous():
@@ -226,9 +237,11 @@ def mnn_match(desc_a, desc_b, algo=_lib.MNN_AUTO, want_nn21=True):
         b = b.contiguous()
     dev = a.device
     nn12 = torch.empty(N, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        tc = want_nn21 or algo == _lib.MNN_SIMT or D != 128 or (algo == _lib.MNN_AUTO and N * M < 1024 * 1024)
-    nn21 = torch.empty(M, dtype=torch.int32, device=dev) if tc else None
+    # nn21 is needed by the exact SIMT kernel, by callers that ask for it, and by the tensor-core path when
+    # side B has more column chunks than the matches-only verification covers (M > ONE_DIR_MAX_M)
+    needs_nn21 = (want_nn21 or algo == _lib.MNN_SIMT or D != 128 or M > ONE_DIR_MAX_M or
+                  (algo == _lib.MNN_AUTO and N * M < 1024 * 1024))
+    nn21 = torch.empty(M, dtype=torch.int32, device=dev) if needs_nn21 else None
     matches = torch.empty((N, 2), dtype=torch.int64, device=dev)
     nm = torch.empty(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):

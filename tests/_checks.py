@@ -75,6 +75,20 @@ def check_mnn_near_tie(a, b, got, want, tol=1e-6):
             f"pair {(i, j)} differs without a near tie: row gap {top_r[1]-top_r[0]}, col gap {top_c[1]-top_c[0]}"
 
 
+def check_argmax_exact(x, y, got_nn, want_nn, tol=1e-12):
+    """got_nn[i] must equal want_nn[i] = argmax_j <x_i, y_j> (float64, first index).  Zero mismatches is the
+    bar; an entry may differ only if the two columns' exact similarities coincide to `tol` (a float64 tie,
+    where summation order decides) -- and then the test proves it."""
+    got_nn, want_nn = np.asarray(got_nn).astype(np.int64), np.asarray(want_nn).astype(np.int64)
+    assert got_nn.shape == want_nn.shape
+    bad = np.nonzero(got_nn != want_nn)[0]
+    for i in bad:
+        xi = x[i].astype(np.float64)
+        sg, sw = float(xi @ y[got_nn[i]].astype(np.float64)), float(xi @ y[want_nn[i]].astype(np.float64))
+        assert abs(sg - sw) <= tol, f"row {i}: got column {got_nn[i]} (sim {sg!r}) instead of {want_nn[i]} (sim {sw!r})"
+    return len(bad)
+
+
 def assert_close_vec(got, want, rel=1e-5, axis=-1):
     """|got - want| <= rel * (largest |component| of the reference vector).
 

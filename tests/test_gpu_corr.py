@@ -30,6 +30,47 @@ def test_dense_expectation_golden(golden):
     assert torch.equal(e2, e)
 
 
+def test_compute_prob_golden(golden):
+    """compute_prob (losses/preprocess_utils.py:89-115): probabilities, raw similarities and the gradients of
+    a weighted sum of the probabilities w.r.t. both inputs, against the reference's own run (1e-5 relative to
+    the largest entry)."""
+    import posfeat_b200 as P
+    g = golden("prob")
+    wgt = t(g["wgt"])
+    for name, kw in (("cos", {}), ("cos_scale", dict(with_scale=True)), ("euc", dict(loss_distance="euc"))):
+        a, b = t(g["f1"]).requires_grad_(), t(g["f2"]).requires_grad_()
+        prob = P.compute_prob(a, b, **kw)
+        assert prob.shape == (2, 37, 150) and prob.dtype == torch.float32
+        assert rel_err(prob.detach().cpu(), g[f"{name}/prob"]) < 1e-5
+        np.testing.assert_allclose(prob.detach().sum(-1).cpu().numpy(), 1.0, rtol=0, atol=2e-6)
+        (prob * wgt).sum().backward()
+        assert rel_err(a.grad.cpu(), g[f"{name}/g1"]) < 2e-5
+        assert rel_err(b.grad.cpu(), g[f"{name}/g2"]) < 2e-5
+    prob, sim = P.compute_prob(t(g["f1"]), t(g["f2"]), return_sim=True)
+    assert rel_err(prob.cpu(), g["sim/prob"]) < 1e-5
+    assert rel_err(sim.cpu(), g["sim/sim"]) < 1e-5
+    with pytest.raises(AssertionError):
+        P.compute_prob(t(g["f1"]), t(g["f2"]), loss_distance="l1")
+    with pytest.raises(AssertionError):
+        P.compute_prob(t(g["f1"]), t(g["f2"]), loss_distance="euc", return_sim=True)
+
+
+def test_compute_prob_vs_oracle_ragged():
+    """Sizes that are not multiples of the 64 x 64 tile or the 16-wide K slice, against the numpy oracle."""
+    import posfeat_b200 as P
+    from oracle import posfeat_oracle as O
+    g = torch.Generator().manual_seed(77)
+    for (B, m, n, D) in ((1, 1, 1, 1), (3, 65, 130, 33), (2, 200, 9000, 128)):
+        f1 = torch.randn(B, m, D, generator=g) * 0.4
+        f2 = torch.randn(B, n, D, generator=g) * 0.4
+        for kw in ({}, dict(with_scale=True), dict(loss_distance="euc")):
+            if kw.get("with_scale") and n > 1000:
+                continue                      # sqrt(n)-scaled logits of random data: a one-hot softmax, nothing to compare
+            got = P.compute_prob(f1.cuda(), f2.cuda(), **kw).cpu().numpy()
+            want = O.compute_prob(f1.numpy(), f2.numpy(), dtype=np.float64, **kw)
+            assert rel_err(got, want) < 2e-5, (B, m, n, D, kw)
+
+
 def test_window_expectation_golden(golden):
     import posfeat_b200.preprocess as PP
     g = golden("corr")
@@ -165,6 +206,67 @@ def test_preprocess_line2window_golden(golden):
     loss.backward()
     assert rel_err(xf1.grad.cpu(), g["gxf1"]) < 2e-3
     assert rel_err(xf2.grad.cpu(), g["gxf2"]) < 2e-3
+
+
+def test_preprocess_line2window_vs_float64_reference(golden, capsys):
+    """How far is this implementation from the TRUTH, and how far is the reference's own float32 run?
+
+    tests/golden/preprocess_f64.npz holds the reference run in float64 (same coordinates; the results of its
+    no_grad line search replayed from the float32 run), and the float32 reference's loss / gradients evaluated
+    with the float64 run's std values as loss weights.  For every output the deviation of this implementation
+    from the float64 run must not exceed 3x the deviation of the reference's own float32 run from it (plus
+    1e-5 of the output's scale, the north star's bar).  The measured pairs are printed."""
+    import posfeat_b200.preprocess as PP
+    g, g64 = golden("preprocess"), golden("preprocess_f64")
+    H, W = int(g["H"]), int(g["W"])
+    cfg = dict(kps_generator="generate_kpts_regular_grid_random",
+               kps_generator_config=dict(grid_size=16, map_init="identity", keep_spatial=True, random_select="random"),
+               window_size=0.1, loss_distance="cos", use_nn_grid=False, use_line_search=True,
+               line_search_config=dict(line_step=100, use_nn=True, loc_rand=True),
+               temperature_base=60, temperature_max=60)
+    P = PP.Preprocess_Line2Window(cfg)
+    xf1, xf2 = t(g["xf1"]).requires_grad_(), t(g["xf2"]).requires_grad_()
+    B = xf1.shape[0]
+    inputs = dict(im1=torch.zeros(B, 3, H, W), im2=torch.zeros(B, 3, H, W), F1=t(g["F1"]), F2=t(g["F2"]))
+    outputs = dict(preds1=dict(local_map=xf1, local_point=torch.ones(B, 1, H, W).cuda()),
+                   preds2=dict(local_map=xf2, local_point=torch.ones(B, 1, H, W).cuda()), epoch=0)
+    pr = P(inputs, outputs, coords=(t(g["coord1_n"]), t(g["coord2_n"])), jitter=(t(g["jitter1"]), t(g["jitter2"])))
+    rows = []
+
+    def compare(name, ours, ref32, ref64, mask=None, scale=None, factor=3.0, floor=1e-5):
+        ours, ref32, ref64 = (np.asarray(x, dtype=np.float64) for x in (ours, ref32, ref64))
+        if mask is not None:
+            ours, ref32, ref64 = ours[mask], ref32[mask], ref64[mask]
+        sc = scale if scale is not None else max(np.abs(ref64).max(), 1e-30)
+        e_ours, e_ref = np.abs(ours - ref64).max() / sc, np.abs(ref32 - ref64).max() / sc
+        rows.append((name, e_ours, e_ref))
+        assert e_ours <= factor * e_ref + floor, f"{name}: ours {e_ours:.3e} vs reference-float32 {e_ref:.3e} (of scale {sc:.3g})"
+
+    v1, v2 = g["p_valid_epi1"].astype(bool), g["p_valid_epi2"].astype(bool)
+    # the discrete choice of the line search must be the float32 reference's (it was replayed into the float64 run)
+    for key, v in (("feat1c_corloc_org", v1), ("feat2c_corloc_org", v2)):
+        got, want = pr[key].detach().cpu().numpy(), g["p_" + key]
+        same = np.abs(got - want).max(-1) < 1e-4 * (max(H, W) if np.abs(want).max() > 2 else 1.0)
+        assert same[v].mean() > 0.99, key
+        v &= same
+    for key, v in (("feat1g_corloc", None), ("feat2g_corloc", None), ("feat1w_corloc", v1), ("feat2w_corloc", v2)):
+        compare(key, pr[key].detach().cpu().numpy(), g["p_" + key], g64["p_" + key], mask=v, scale=float(max(H, W)))
+    for key, v in (("feat1g_std", None), ("feat2g_std", None), ("feat1w_std", v1), ("feat2w_std", v2)):
+        compare(key, pr[key].detach().cpu().numpy(), g["p_" + key], g64["p_" + key], mask=v, scale=1.0)
+    # loss and gradients with the float64 run's std values as the (detached) weights, as in the fixture
+    pr2 = dict(pr)
+    for key in ("feat1g_std", "feat2g_std", "feat1w_std", "feat2w_std"):
+        pr2[key] = t(g64["p_" + key])
+    loss_cfg = dict(grid_cost_thr=0.5, win_cost_thr=0.1, use_std_as_weight=True, weight_grid=0.3, weight_window=1)
+    loss = R.epipolar_loss_full(inputs, pr2, loss_cfg)
+    compare("loss", [float(loss)], [float(g64["loss_f32_std64"])], [float(g64["loss"])], floor=1e-6)
+    loss.backward()
+    compare("grad local_map 1", xf1.grad.cpu().numpy(), g64["gxf1_f32_std64"], g64["gxf1"])
+    compare("grad local_map 2", xf2.grad.cpu().numpy(), g64["gxf2_f32_std64"], g64["gxf2"])
+    with capsys.disabled():
+        print("\n  deviation from the float64 reference run, relative to the output's scale:")
+        for name, eo, er in rows:
+            print(f"    {name:22s} this implementation {eo:9.2e}   reference's own float32 run {er:9.2e}")
 
 
 def test_epipolar_line_search_vs_torch():

@@ -83,6 +83,25 @@ def test_mnn_edge():
     assert O.mnn_matcher(a, a[:1]).tolist() == [[0, 0]]
 
 
+def test_mnn_blocked_f64_equals_plain_oracle(golden):
+    """The row-blocked float64 matcher used at 16k / 64k (BASELINE config 5) is the plain oracle, block size
+    notwithstanding, including the first-index rule on duplicated descriptors and the reference's fixtures."""
+    g = golden("mnn")
+    for a, b in ((g["a"], g["b"]), (g["ad"], g["bd"]), (g["bd"], g["ad"])):
+        m, nn12, nn21 = O.mnn_matcher(a, b, exact=True, return_nn=True)
+        sim = a.astype(np.float64) @ b.astype(np.float64).T
+        for blk in (7, 64, 4096):
+            m2, n12, n21, rg, cg = O.mnn_blocked_f64(a, b, block=blk)
+            np.testing.assert_array_equal(m2, m)
+            np.testing.assert_array_equal(n12, nn12)
+            np.testing.assert_array_equal(n21, nn21)
+            ss = np.sort(sim, 1)
+            np.testing.assert_allclose(rg, ss[:, -1] - ss[:, -2], rtol=0, atol=1e-15)
+            sc = np.sort(sim, 0)
+            np.testing.assert_allclose(cg, sc[-1] - sc[-2], rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(O.mnn_blocked_f64(g["ad"], g["bd"])[0], g["mnn_dup"])
+
+
 def test_corr(golden):
     g = golden("corr")
     e, std, prob = O.get_expected_correspondence_locs(g["f1"], g["fm"], with_std=True)
@@ -94,6 +113,17 @@ def test_corr(golden):
     np.testing.assert_allclose(probw, g["probw"], rtol=5e-5, atol=1e-7)
     np.testing.assert_allclose(ew, g["expw"], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(stdw, g["stdw"], rtol=1e-4, atol=5e-6)
+
+
+def test_compute_prob(golden):
+    """compute_prob (losses/preprocess_utils.py:89-115), every option, against the reference's output."""
+    g = golden("prob")
+    for name, kw in (("cos", {}), ("cos_scale", dict(with_scale=True)), ("euc", dict(loss_distance="euc"))):
+        p = O.compute_prob(g["f1"], g["f2"], **kw)
+        np.testing.assert_allclose(p, g[f"{name}/prob"], rtol=3e-5, atol=1e-9)
+    p, sim = O.compute_prob(g["f1"], g["f2"], return_sim=True)
+    np.testing.assert_allclose(p, g["sim/prob"], rtol=3e-5, atol=1e-9)
+    np.testing.assert_allclose(sim, g["sim/sim"], rtol=1e-5, atol=1e-6)
 
 
 def test_grid_stage(golden):
