@@ -141,15 +141,18 @@ def ref_available():
     return ref_runner.available()
 
 
-def cpu_reference_pair(score2, fmap2, cfg=None):
+def cpu_reference_pair(score2, fmap2, cfg=None, need_idx=True):
     """ONE pair through the reference's own torch-CPU functions (oracle/_ref) -- or, when the staged
     reference is absent, through the numpy port (oracle/posfeat_oracle.py).  Returns (kind, idx [2,n],
     matches (K,2))."""
     cfg = cfg or DET_CFG
     if ref_available():
         from oracle import ref_runner
-        kps, desc, m = ref_runner.run_pair(score2, fmap2, dict(cfg))
-        return "reference", ref_runner.keypoint_idx(score2, kps).numpy(), m
+        if not need_idx:                       # timed calls: the stock code path, nothing observed
+            kps, desc, m = ref_runner.run_pair(score2, fmap2, dict(cfg))
+            return "reference", None, m
+        kps, desc, m, idx = ref_runner.run_pair(score2, fmap2, dict(cfg), want_idx=True)
+        return "reference", idx.cpu().numpy(), m
     from oracle import posfeat_oracle as O
     sn, fn = score2.numpy(), fmap2.numpy()
     kps, sc, idx, _ = O.generate_kpts_single(sn, return_idx=True, **{k: v for k, v in cfg.items() if k != "stable"})
@@ -174,11 +177,10 @@ def time_cpu_reference(score, fmap, budget_s=15.0, max_pairs=24):
     done, t0, first = 0, time.perf_counter(), None
     while done < max_pairs and (done == 0 or time.perf_counter() - t0 < budget_s):
         i = done % P
-        r = cpu_reference_pair(score[2 * i:2 * i + 2], fmap[2 * i:2 * i + 2])
-        if first is None:
-            first = r
+        cpu_reference_pair(score[2 * i:2 * i + 2], fmap[2 * i:2 * i + 2], need_idx=False)
         done += 1
     dt = time.perf_counter() - t0
+    first = cpu_reference_pair(score[0:2], fmap[0:2])          # untimed: pair 0 with the keypoint indices, for the parity check
     return kind, done / dt, done, dt, first
 
 
@@ -195,7 +197,7 @@ def run_reference_arm(args, rank, world):
     t0 = time.perf_counter()
     for s in range(steps):
         i = s % 2
-        cpu_reference_pair(score[2 * i:2 * i + 2], fmap[2 * i:2 * i + 2])
+        cpu_reference_pair(score[2 * i:2 * i + 2], fmap[2 * i:2 * i + 2], need_idx=False)
     dt = time.perf_counter() - t0
     v = steps / dt
     what = ("the reference's generate_kpts_single / sample_feat_by_coord / mnn_matcher (oracle/_ref) on CPU tensors"
@@ -588,9 +590,9 @@ def main():
                             out = ref_runner.run_pair(score[2 * i:2 * i + 2], fm_nchw[2 * i:2 * i + 2], dict(DET_CFG))
                         return out
                     ms_r, _ = cuda_time(ref_pass, 3, warmup=2)
-                    kps_r, _, m_r = ref_runner.run_pair(score[0:2], fm_nchw[0:2], dict(DET_CFG))
+                    kps_r, _, m_r, idx_r = ref_runner.run_pair(score[0:2], fm_nchw[0:2], dict(DET_CFG), want_idx=True)
                     torch.backends.cuda.matmul.allow_tf32 = prev
-                    idx_r = ref_runner.keypoint_idx(score[0:2], kps_r).cpu().numpy()
+                    idx_r = idx_r.cpu().numpy()
                     k0 = int(nm[0].item())
                     gs = pixel_matches(feats["idx"][:2].cpu().numpy(), matches[0, :k0].cpu().numpy())
                     ref_b200 = {"value": n_eager / (ms_r * 1e-3), "unit": "pairs/s",

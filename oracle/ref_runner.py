@@ -39,23 +39,30 @@ def modules():
     return _mods
 
 
-def run_pair(score2, fmap2, det_cfg, norm=True):
+def run_pair(score2, fmap2, det_cfg, norm=True, want_idx=False):
     """One image pair through the reference's own functions.  score2 [2,1,H,W], fmap2 [2,D,h,w] (any device).
-    Returns (kps_n [2,n,2], desc [2,n,D], matches (K,2) int64 ndarray)."""
+    Returns (kps_n [2,n,2], desc [2,n,D], matches (K,2) int64 ndarray) and, with ``want_idx``, the keypoint
+    indices the reference's own ``topk`` call returned (losses/preprocess_utils.py:264; the function does not
+    return them, so the call is observed -- not altered -- through a wrapper around Tensor.topk)."""
     import torch
     pu = modules()[0]
+    seen = []
+    orig = torch.Tensor.topk
+
+    def spy(self, *a, **k):
+        r = orig(self, *a, **k)
+        seen.append(r[1])
+        return r
     with torch.no_grad():
-        kps, _ = pu.generate_kpts_single(score2, **det_cfg)
+        if want_idx:
+            torch.Tensor.topk = spy
+        try:
+            kps, _ = pu.generate_kpts_single(score2, **det_cfg)
+        finally:
+            torch.Tensor.topk = orig
         desc = pu.sample_feat_by_coord(fmap2, kps, norm)
         m = pu.mnn_matcher(desc[0], desc[1])
+    if want_idx:
+        assert len(seen) == 1, "generate_kpts_single is expected to call topk exactly once"
+        return kps, desc, m, seen[0]
     return kps, desc, m
-
-
-def keypoint_idx(score2, kps):
-    """Linear interior-grid index of the reference's keypoints is not returned by generate_kpts_single;
-    recover the winners' pixel from the centroid (always within half a pixel of its interior pixel)."""
-    import torch
-    h, w = score2.shape[2:]
-    x = torch.round((kps[..., 0] + 1) * (w - 1) / 2).long() - 1
-    y = torch.round((kps[..., 1] + 1) * (h - 1) / 2).long() - 1
-    return y * (w - 2) + x

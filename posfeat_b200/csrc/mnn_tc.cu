@@ -47,6 +47,7 @@ constexpr int kTcThreads = (4 + kEpiWarps) * 32;
 constexpr float kAccSlack = 3.0e-5f;   // fp32 accumulation error of the tensor core, relative to |x||y|
 constexpr float kEps32 = 1.0e-5f;      // float32 dot-product error bound (>= 128 * 2^-24), relative to |x||y|
 constexpr float kHalfSlack = 9.8e-4f;  // 2 * 2^-11: fp16 rounding of two table entries of magnitude <= 1
+constexpr float kG8Slack = 1.0f - 9.0f / 1024.0f;   // group entries: fp16 rounding + 3 replaced mantissa bits < 8.5 ulps <= 8.5 * 2^-10 relative
 
 constexpr int kSmemX = 0;                      // 2 buffers x 2 K-halves
 constexpr int kSmemY = 4 * kSubBytes;          // kStages x 2 K-halves
@@ -67,18 +68,33 @@ struct DirParams {            // all arrays are batched over pairs: index = pair
   int splits, tiles_per_split, y_tiles;
   int row_blocks;              // NXpad / 256
 };
+// Matches-only path (kLists epilogue): instead of the chunk-maximum table the epilogue leaves
+//   * per (row, 64-column quarter j of the 256-column tiles, column split): a 128-byte LIST of the chunks that came
+//     within delta of the row's running maximum when they were produced -- a superset of the chunks within delta
+//     of the final row maximum (the running maximum only grows), a handful of entries instead of a 2 KB table row;
+//   * per (8 consecutive rows, chunk): the GROUP ENTRY half2(max1 | leader, max2) of the 8 rows' chunk maxima
+//     (non-negative, scaled, fp16 rounded up to a multiple of 8 ulps with the leader's row-in-group in the three
+//     low bits), 1/64 of the similarity matrix's element count.  A column chunk's competitor rows are then the
+//     leaders of the groups with max1 >= threshold, or all 8 rows of a group whose max2 reaches it as well.
+constexpr int kListSlots = 16;          // slot 0: {count, running max}; slots 1..15: {first chunk of a tile quarter | chunk mask << 24, quarter maximum}
+struct ListParams {
+  uint2* lists;                // [pairs][NXpad][4 * splits][kListSlots]
+  unsigned* g8;                // [pairs][pitch][groups]
+  int groups;                  // NXpad / 8
+};
 struct TcParams {
   DirParams d[2];
   int pairs;
   int units0, units_pair;      // units of direction 0 / of both directions, per pair
   int units_total;             // pairs * units_pair
   int debug;   // POSFEAT_TC_DEBUG bits (bring-up only)
+  ListParams L;                // kLists kernels only
 };
 
 // 1 / (max|x| max|y|): keeps every table entry inside [-1, 1]
 __device__ __forceinline__ float table_scale(const DirParams& d, int pair) {
   const float m = __uint_as_float(d.xstats[2 * pair].max_norm) * __uint_as_float(d.ystats[2 * pair].max_norm);
-  return m > 0.f ? 1.f / m : 0.f;
+  return m > 0.f ? 1.f / m : 1.f;      // an all-zero operand: every similarity is 0, any finite scale will do
 }
 
 __device__ __forceinline__ float row_delta(const DirParams& d, int pair, int row) {
@@ -174,6 +190,78 @@ __device__ __forceinline__ uint2 reduce32(const uint32_t (&v)[32], int col0, int
   return r;
 }
 
+// 32 accumulator columns of the row owned by this thread -> four (unscaled) chunk maxima
+template <bool kRagged, int kOff>
+__device__ __forceinline__ void chunkmax32(const uint32_t (&v)[32], int col0, int NY, float (&m)[8]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = __uint_as_float(v[c * 8 + j]);
+      if (kRagged && col0 + c * 8 + j >= NY) f[j] = -INFINITY;   // zero padding rows of Y
+    }
+    m[kOff + c] = max8(f);
+  }
+}
+
+__device__ __forceinline__ __half2 as_h2(unsigned u) { return *reinterpret_cast<const __half2*>(&u); }
+__device__ __forceinline__ unsigned as_u32(__half2 h) { return *reinterpret_cast<const unsigned*>(&h); }
+
+// The 8 chunk maxima of this thread's row -> the group entry of ONE chunk per lane: after three transposing
+// exchanges inside the 8-lane group (rows 8g .. 8g+7 of the warp's 32 rows), lane l holds
+// half2(max1 | leader, max2) of chunk (l & 7) over the group's rows.  Values are scaled into [0, 1], clamped at
+// zero and rounded to fp16 by one conversion, and the three low bits are replaced by the row's index in the group:
+// for non-negative halves the bit pattern orders like the value, so the maximum carries its row along.  A stored
+// value differs from the scaled similarity by less than 8.5 fp16 ulps; the thresholds it is compared with are
+// lowered by that much (kG8Slack).
+__device__ __forceinline__ unsigned g8_reduce(const float (&m)[8], float scale, int lane) {
+  const unsigned lb = (unsigned)(lane & 7) * 0x00010001u;
+  unsigned E[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned h;    // packed fp16 pair of the two scaled values, negative values clamped to zero by the conversion
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(m[2 * k + 1] * scale), "f"(m[2 * k] * scale));
+    E[k] = (h & 0xFFF8FFF8u) | lb;
+  }
+  constexpr unsigned kFull = 0xffffffffu;
+  // exchange over lane bit 2: keep chunks 4*b2 .. 4*b2+3
+  const bool b2 = lane & 4;
+  const unsigned k0 = b2 ? E[2] : E[0], k1 = b2 ? E[3] : E[1];
+  const unsigned r0 = __shfl_xor_sync(kFull, b2 ? E[0] : E[2], 4), r1 = __shfl_xor_sync(kFull, b2 ? E[1] : E[3], 4);
+  const __half2 a1_0 = __hmax2(as_h2(k0), as_h2(r0)), a2_0 = __hmin2(as_h2(k0), as_h2(r0));
+  const __half2 a1_1 = __hmax2(as_h2(k1), as_h2(r1)), a2_1 = __hmin2(as_h2(k1), as_h2(r1));
+  // exchange over lane bit 1: keep chunks 4*b2 + 2*b1 + {0, 1}
+  const bool b1 = lane & 2;
+  const __half2 q1 = b1 ? a1_1 : a1_0, q2 = b1 ? a2_1 : a2_0;
+  const __half2 o1 = as_h2(__shfl_xor_sync(kFull, as_u32(b1 ? a1_0 : a1_1), 2));
+  const __half2 o2 = as_h2(__shfl_xor_sync(kFull, as_u32(b1 ? a2_0 : a2_1), 2));
+  const __half2 n1 = __hmax2(q1, o1), n2 = __hmax2(__hmin2(q1, o1), __hmax2(q2, o2));
+  // exchange over lane bit 0: keep chunk 4*b2 + 2*b1 + b0 as half2(first, second)
+  const bool b0 = lane & 1;
+  const unsigned keep = __byte_perm(as_u32(n1), as_u32(n2), b0 ? 0x7632 : 0x5410);
+  const unsigned recv = __shfl_xor_sync(kFull, __byte_perm(as_u32(n1), as_u32(n2), b0 ? 0x5410 : 0x7632), 1);
+  const __half2 mx = __hmax2(as_h2(keep), as_h2(recv)), mn = __hmin2(as_h2(keep), as_h2(recv));
+  // first = mx.lo, second = max(mn.lo, mx.hi)
+  return as_u32(__hmax2(as_h2(__byte_perm(as_u32(mn), 0u, 0x1010)), mx));
+}
+
+// A full list: the running maximum only grows, so earlier entries below the present threshold are dead -- drop them
+// (this thread's own stores, re-read) before giving up on the row.  Out of line: it almost never runs.
+__device__ __noinline__ int list_compact(uint2* line, int cnt, float thr) {
+  if (cnt > kListSlots - 1) return cnt;          // already overflowed
+  int k = 0;
+  for (int sl = 1; sl < kListSlots; ++sl) {
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(line + sl);
+    if (__uint_as_float((unsigned)(e >> 32)) >= thr) {
+      *reinterpret_cast<volatile unsigned long long*>(line + 1 + k) = e;
+      ++k;
+    }
+  }
+  return k;
+}
+
+template <bool kLists>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -272,6 +360,66 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (++ys == kStages) { ys = 0; yph ^= 1; }
         if (++as == 2) { as = 0; aph ^= 1; }
       }
+    }
+  } else if (warp >= 4 && kLists) {
+    // ===== epilogue, matches-only path: TMEM -> registers -> chunk maxima -> row candidate lists + group entries =====
+    const int quarter = warp & 3, j = (warp - 4) >> 2;
+    const int row_in_block = (int)rank * 128 + quarter * 32 + lane;
+    int as = 0, aph = 0;
+    for (int u = cluster_id; u < p.units_total; u += n_clusters) {
+      const UnitInfo q = decode_unit(p, u);
+      const DirParams& d = p.d[0];
+      const int row = q.rb * kXRows + row_in_block;
+      const float scale = table_scale(d, q.pair);
+      const int NY = d.NY;
+      const bool real_row = row < d.NX;                  // padding rows: no list (their operand rows are zero)
+      const float delta = real_row ? row_delta(d, q.pair, row) : 0.f;
+      uint2* line = p.L.lists + ((((size_t)q.pair * d.NXpad + row) * 4 + j) * d.splits + q.sp) * kListSlots;
+      const size_t gstep = (size_t)32 * p.L.groups;      // one tile further = 32 chunks further
+      unsigned* gdst = p.L.g8 + ((size_t)q.pair * d.pitch + (size_t)q.t0 * 32 + j * 8 + (lane & 7)) * p.L.groups +
+                       (q.rb * 32 + (int)rank * 16 + quarter * 4 + (lane >> 3));
+      float rm = -INFINITY;                              // running maximum of this thread's share of the row
+      float thr_cur = (real_row && !(p.debug & 256)) ? -INFINITY : INFINITY;   // rm - delta; padding rows never emit
+      int cnt = 0;
+      int chunk0 = q.t0 * 32 + j * 8;
+      for (int t = q.t0; t < q.t1; ++t, gdst += gstep, chunk0 += 32) {
+        mbar_wait(bar_acc_full + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(as * 256 + j * 64) + ((uint32_t)(quarter * 32) << 16);
+        const int c0 = t * kYRows + j * 64;
+        const bool full = c0 + 64 <= NY;
+        uint32_t v[32];
+        float m[8];
+        tc_ld32(taddr, v);
+        tc_wait_ld();
+        if (full) chunkmax32<false, 0>(v, c0, NY, m); else chunkmax32<true, 0>(v, c0, NY, m);
+        tc_ld32(taddr + 32, v);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(bar_acc_empty + 8 * as, 0);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        if (full) chunkmax32<false, 4>(v, c0 + 32, NY, m); else chunkmax32<true, 4>(v, c0 + 32, NY, m);
+        // row side: one entry per tile quarter that comes within delta of the running maximum, with the mask of its
+        // chunks that do (the branch is taken by most warps on most tiles -- 32 independent rows -- so it is kept short)
+        const float tm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        if (tm >= thr_cur) {
+          rm = fmaxf(rm, tm);
+          thr_cur = rm - delta;
+          unsigned mask = 0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) mask |= m[c] >= thr_cur ? (1u << (24 + c)) : 0u;
+          if (cnt >= kListSlots - 1) cnt = list_compact(line, cnt, thr_cur);
+          if (cnt < kListSlots - 1) line[1 + cnt] = make_uint2((unsigned)chunk0 | mask, __float_as_uint(tm));
+          ++cnt;
+        }
+        // column side: group entries of the warp's four 8-row groups for the tile's 8 chunks of this quarter
+        if (!(p.debug & 128)) {
+          const unsigned ge = g8_reduce(m, scale, lane);
+          if (!(p.debug & 64)) *gdst = ge;
+        }
+      }
+      if (real_row) line[0] = make_uint2((unsigned)cnt, __float_as_uint(rm));   // cnt >= kListSlots: the list overflowed
     }
   } else if (warp >= 4) {
     // ===== epilogue (both CTAs): TMEM -> registers -> per-chunk maxima -> fp16 table =====
@@ -752,6 +900,11 @@ struct VerifyArgs {
   const float* best8;        // [pairs][NX][8] from the rescoring kernel (valid for the row's own chunk)
   unsigned char* mutual;     // [pairs][NX]
   int nchunks;
+  // group-entry form (kG8): competitors are derived here from the chunk's row of group entries
+  const int* tmin;           // [pairs][nchunks]
+  const unsigned* g8;        // [pairs][pitch][groups]
+  int groups;
+  unsigned long long* dbg;   // POSFEAT_MNN_DEBUG counters (NULL otherwise)
 };
 
 // float32 similarities of one row x (float4 per lane) to the 8 columns of a chunk staged in
@@ -804,18 +957,96 @@ constexpr int kVerWarps = 1;
 // the chunk's 8 columns are evaluated in float32; a member loses its match if another
 // competitor is larger in the member's column.  Comparisons inside the float32 error band are
 // settled exactly (float64), ties by the lower row index.
+// kG8: the competitor list is built here, in shared memory, from the chunk's row of group entries (one coalesced
+// read of groups * 4 bytes, 4 KB at N = 8192) instead of by a scan kernel over a table: a group whose max1 reaches
+// the chunk's threshold contributes its leader row, or all of its 8 rows when max2 reaches the threshold too.
+template <bool kG8>
 __global__ void __launch_bounds__(kVerWarps * 32, 32)
 tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
   __shared__ float s_e[kVerWarps][32][kChunk];                    // competitor matrix of short lists
   __shared__ float s_tmp[kVerWarps][kChunk];
+  __shared__ int s_rows[kG8 ? kVerWarps * kCompCap : 1];
+  __shared__ unsigned short s_ent[kG8 ? kVerWarps * kCompCap : 1];   // group entry (fp16 bits) behind each competitor row
+  __shared__ int s_mi[kG8 ? kVerWarps * 32 : 1], s_mj[kG8 ? kVerWarps * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.y, c = blockIdx.x * kVerWarps + warp;
   const DirParams& d = a.d;
   if (c >= a.nchunks) return;
   const size_t slot = (size_t)pair * a.nchunks + c;
-  const int total = a.comp_cnt[slot];
-  if (total == 0) return;
+  int total;
+  const int* rows;
+  if (kG8) {
+    const int o = a.tmin[slot];
+    if (o == 0x7f7f7f7f) return;                                  // no row has its nearest neighbour in this chunk
+    const __half2 thr2 = __float2half2_rn(__half2float(__float2half_rd(ordered_int_to_float(o))));
+    const uint4* g = reinterpret_cast<const uint4*>(a.g8 + ((size_t)pair * d.pitch + c) * a.groups);
+    const int nvec = a.groups >> 2;                               // groups is a multiple of 32
+    int* myrows = &s_rows[warp * kCompCap];
+    unsigned short* myent = &s_ent[warp * kCompCap];
+    int n = 0;
+    for (int v0 = 0; v0 < nvec; v0 += 128) {
+      uint4 e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = v0 + q * 32 + lane;
+        e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned m0 = __hge2_mask(as_h2(e[q].x), thr2), m1 = __hge2_mask(as_h2(e[q].y), thr2);
+        const unsigned m2 = __hge2_mask(as_h2(e[q].z), thr2), m3 = __hge2_mask(as_h2(e[q].w), thr2);
+        // low half = max1 (hot), high half = max2 (two or more rows reach the threshold)
+        unsigned info = 0;
+        if ((m0 | m1 | m2 | m3) & 0xffffu)
+          info = (m0 & 1u) | (m1 & 1u) << 1 | (m2 & 1u) << 2 | (m3 & 1u) << 3 |
+                 ((m0 >> 16) & 1u) << 4 | ((m1 >> 16) & 1u) << 5 | ((m2 >> 16) & 1u) << 6 | ((m3 >> 16) & 1u) << 7 |
+                 (e[q].x & 7u) << 8 | (e[q].y & 7u) << 11 | (e[q].z & 7u) << 14 | (e[q].w & 7u) << 17;
+        unsigned any = __ballot_sync(0xffffffffu, info != 0);
+        while (any) {
+          const int l = __ffs(any) - 1;
+          any &= any - 1;
+          const unsigned inf = __shfl_sync(0xffffffffu, info, l);
+          const unsigned ex = __shfl_sync(0xffffffffu, e[q].x, l), ey = __shfl_sync(0xffffffffu, e[q].y, l);
+          const unsigned ez = __shfl_sync(0xffffffffu, e[q].z, l), ew = __shfl_sync(0xffffffffu, e[q].w, l);
+          const int g0 = (v0 + q * 32 + l) * 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (!((inf >> k) & 1u)) continue;                    // warp uniform
+            const int r0 = (g0 + k) * 8;
+            const unsigned short ent = (unsigned short)((k == 0 ? ex : k == 1 ? ey : k == 2 ? ez : ew) & 0xffffu);   // max1: bounds every row of the group
+            if ((inf >> (4 + k)) & 1u) {                         // two or more rows of the group matter: take all 8
+              const int add = min(8, d.NX - r0);
+              if (add > 0) {
+                if (lane < add && n + lane < kCompCap) { myrows[n + lane] = r0 + lane; myent[n + lane] = ent; }
+                n += add;
+              }
+            } else {
+              const int r = r0 + (int)((inf >> (8 + 3 * k)) & 7u);
+              if (r < d.NX) {
+                if (lane == 0 && n < kCompCap) { myrows[n] = r; myent[n] = ent; }
+                n += 1;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    total = n;
+    rows = myrows;
+    if (a.dbg && lane == 0) {
+      atomicAdd(a.dbg + 4, 1ull);
+      atomicAdd(a.dbg + 5, (unsigned long long)n);
+      atomicAdd(a.dbg + 6, n > kCompCap ? 1ull : 0ull);
+      atomicAdd(a.dbg + 7, n > 32 ? 1ull : 0ull);
+    }
+    if (total == 0) return;
+  } else {
+    total = a.comp_cnt[slot];
+    if (total == 0) return;
+    rows = a.comp + slot * kCompCap;
+  }
   const float* Xp = a.X + pair * a.strideX;
   const float* Yp = a.Y + pair * a.strideY;
   const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
@@ -856,10 +1087,90 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     }
   };
 
+  if (kG8 && total <= kCompCap) {
+    // Member-centric form.  Members (rows whose nearest neighbour lies in this chunk) are first settled among
+    // themselves from the 8 values the rescoring kernel left for each of them -- in a well-matched pair a weak
+    // member (a row without a true partner, which drags the chunk's threshold down and pulls dozens of noise rows
+    // into the competitor list) loses right there to the column's real partner.  Only the surviving members'
+    // thresholds decide which non-member rows still have to be evaluated: a row whose group entry (an upper
+    // bound of its similarity to every column of the chunk) lies below all of them cannot beat anyone.
+    const unsigned short* ents = &s_ent[warp * kCompCap];
+    int* mi = &s_mi[warp * 32];
+    int* mj = &s_mj[warp * 32];
+    int nmem = 0;
+    for (int q0 = 0; q0 < total; q0 += 32) {
+      const int q = q0 + lane;
+      const int iq = q < total ? rows[q] : -1;
+      const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
+      const bool mem = iq >= 0 && (jq >> 3) == c;
+      const unsigned bal = __ballot_sync(0xffffffffu, mem);
+      if (mem) {
+        const int pos = nmem + __popc(bal & ((1u << lane) - 1u));
+        if (pos < 32) { mi[pos] = iq; mj[pos] = jq; }
+      }
+      nmem += __popc(bal);
+    }
+    __syncwarp();
+    if (nmem == 0) return;
+    if (nmem <= 32) {
+      const bool member = lane < nmem;
+      const int iq = member ? mi[lane] : -1, jq = member ? mj[lane] : -1;
+      if (member) {
+        const float4* b8 = reinterpret_cast<const float4*>(a.best8 + ((size_t)pair * d.NX + iq) * kChunk);
+        *reinterpret_cast<float4*>(&s_e[warp][lane][0]) = __ldg(b8);
+        *reinterpret_cast<float4*>(&s_e[warp][lane][4]) = __ldg(b8 + 1);
+      }
+      __syncwarp();
+      const int cc = member ? jq - c * kChunk : 0;
+      const float mine = member ? s_e[warp][lane][cc] : 0.f;
+      bool lost = false;
+      for (int r = 0; r < nmem; ++r) settle(member, iq, jq, mine, mi[r], s_e[warp][r][cc], lost);
+      // which non-members can still matter
+      const MatStats sx = d.xstats[2 * pair], sy = d.ystats[2 * pair];
+      const float xmax = __uint_as_float(sx.max_norm), ymax = __uint_as_float(sy.max_norm);
+      const float eps_max = __uint_as_float(sx.max_err) * __uint_as_float(sy.max_norm_bf) + xmax * __uint_as_float(sy.max_err) +
+                            kAccSlack * xmax * ymax;
+      const float mm = xmax * ymax;
+      const float scale = mm > 0.f ? 1.f / mm : 1.f;
+      // exact s(i, j) >= mine - band / 2; same threshold construction as in the rescoring kernel
+      float tl = INFINITY;
+      if (member && !lost) {
+        tl = (mine - 0.5f * band - eps_max) * scale - 1e-6f;
+        if (tl > 0.f) tl *= kG8Slack;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, o));
+      if (tl < INFINITY) {
+        bool staged = false;
+        for (int q0 = 0; q0 < total; q0 += 32) {
+          const int q = q0 + lane;
+          const int ir_l = q < total ? rows[q] : -1;
+          bool need = false;
+          if (ir_l >= 0) {
+            const float e = __half2float(__ushort_as_half(ents[q]));
+            need = e >= tl && (__ldg(nn + ir_l) >> 3) != c;
+          }
+          unsigned todo = __ballot_sync(0xffffffffu, need);
+          if (todo && !staged) { stage_y(); staged = true; }
+          while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ir = __shfl_sync(0xffffffffu, ir_l, l);
+            __syncwarp();
+            warp_chunk_dots_f32(load_row(ir), yv, lane, &s_tmp[warp][0]);
+            __syncwarp();
+            settle(member, iq, jq, mine, ir, s_tmp[warp][cc], lost);
+          }
+        }
+      }
+      if (member && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
+      return;
+    }
+    // more than 32 members (many rows share a nearest neighbour): the general paths below
+  }
   if (total <= 32) {
     // common case: the whole competitor matrix fits in shared memory; one pass over the rows
-    const int* rows = a.comp + slot * kCompCap;
-    const int iq = lane < total ? __ldg(rows + lane) : -1;
+    const int iq = lane < total ? rows[lane] : -1;
     const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
     const bool member = iq >= 0 && (jq >> 3) == c;
     if (!__any_sync(0xffffffffu, member)) return;
@@ -898,11 +1209,10 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   }
   stage_y();
   if (total <= kCompCap) {
-    const int* rows = a.comp + slot * kCompCap;
     // long list: members in batches of 32 (one per lane), competitors streamed
     for (int q0 = 0; q0 < total; q0 += 32) {
       const int q = q0 + lane;
-      const int iq = q < total ? __ldg(rows + q) : -1;
+      const int iq = q < total ? rows[q] : -1;
       const int jq = iq >= 0 ? __ldg(nn + iq) : -1;
       const bool member = iq >= 0 && (jq >> 3) == c;
       const unsigned mem = __ballot_sync(0xffffffffu, member);
@@ -923,7 +1233,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
         int ir[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          ir[k] = __ldg(rows + min(r0 + k, total - 1));
+          ir[k] = rows[min(r0 + k, total - 1)];
           xr[k] = load_row(ir[k]);
         }
 #pragma unroll
@@ -967,6 +1277,231 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
       settle(member, i, ji, mine, ip, s_tmp[warp][cc], lost);
     }
     if (member && lost) a.mutual[(size_t)pair * d.NX + i] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ matches-only path, list / group-entry form
+// Rescoring from the candidate lists the kLists epilogue left (one warp per row).  The row's 4 * splits lists
+// (128 bytes each) hold every chunk that came within delta of a running maximum; entries >= F - delta, F the
+// largest value listed, are the candidates -- the same set the table formulation finds, from 512 bytes instead of
+// a 2 KB table row and without the two passes over it.  The rest (float32 re-evaluation of the candidate chunks,
+// exact float64 values inside the float32 error band, first index on ties, per-chunk verification threshold)
+// is the algorithm of tc_rescore_kernel.  A row whose list overflowed is rescored exhaustively.
+struct RescoreListArgs {
+  DirParams d;
+  const uint2* lists;                     // [pairs][NXpad][4 * splits][kListSlots]
+  const float* X; int64_t ldx, strideX;
+  const float* Y; int64_t ldy, strideY;
+  int32_t* nn;                            // [pairs][NX]
+  float* best8;                           // [pairs][NX][8]
+  int* tmin;                              // [pairs][nchunks] ordered ints, pre-set to 0x7f7f7f7f
+  unsigned char* mutual;                  // [pairs][NX], set to 1 here
+  int nchunks;
+  unsigned long long* dbg;                // POSFEAT_MNN_DEBUG counters (NULL otherwise)
+};
+
+constexpr int kRlWarps = 2;
+__global__ void __launch_bounds__(kRlWarps * 32, 32 / kRlWarps)
+tc_rescore_lists_kernel(const RescoreListArgs a) {
+  __shared__ __align__(16) float xs[kRlWarps][kD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DirParams& d = a.d;
+  const int pair = blockIdx.y;
+  const int row = blockIdx.x * kRlWarps + w;
+  if (row >= d.NX) return;
+  const float* __restrict__ Y = a.Y + pair * a.strideY;
+  const int64_t ldy = a.ldy;
+  const size_t prow = (size_t)pair * d.NXpad + row;
+  // the row's lists: 4 * splits lines of 8 uint4; lane l reads vector (l & 7) of line (l >> 3) + 4 * it
+  const uint4* lines = reinterpret_cast<const uint4*>(a.lists + prow * 4 * d.splits * kListSlots);
+  const int nlines = 4 * d.splits;
+  uint4 lv = __ldg(lines + lane);                  // nlines >= 4: the first four lines always exist
+  {
+    const float* xr = a.X + pair * a.strideX + (int64_t)row * a.ldx;
+    float4 xv;
+    if ((((uintptr_t)xr) & 15) == 0) {
+      xv = __ldg(reinterpret_cast<const float4*>(xr) + lane);
+    } else {
+      xv.x = __ldg(xr + lane * 4); xv.y = __ldg(xr + lane * 4 + 1); xv.z = __ldg(xr + lane * 4 + 2); xv.w = __ldg(xr + lane * 4 + 3);
+    }
+    *reinterpret_cast<float4*>(&xs[w][lane * 4]) = xv;
+  }
+  const MatStats ys = d.ystats[2 * pair], xst = d.xstats[2 * pair];
+  const float ymax = __uint_as_float(ys.max_norm);
+  const float xn = d.xnorm[prow];
+  const float delta = 2.f * (d.xerr[prow] * __uint_as_float(ys.max_norm_bf) + xn * __uint_as_float(ys.max_err) +
+                             kAccSlack * xn * ymax);
+  const float band = 2.f * kEps32 * xn * ymax;
+  const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
+  __syncwarp();
+
+  float m32 = -INFINITY;       // running float32 maximum over everything seen
+  float best_s32 = 0.f;        // this lane's column of the float32 similarities of the winner's chunk
+  double bestv = -INFINITY;    // exact best (exact pass only)
+  int besti = 0x7fffffff;
+  bool amb = false;            // two columns within the float32 error band of the maximum: the exact pass decides
+  bool exact = false;
+  const float4* x4 = reinterpret_cast<const float4*>(&xs[w][0]);
+  auto exact_col = [&](int col) {   // whole warp: exact <x, y_col>
+    const float* yr = Y + (int64_t)col * ldy + lane * 4;
+    const float4 xv = x4[lane];
+    double acc = (double)xv.x * (double)__ldg(yr);
+    acc = fma((double)xv.y, (double)__ldg(yr + 1), acc);
+    acc = fma((double)xv.z, (double)__ldg(yr + 2), acc);
+    acc = fma((double)xv.w, (double)__ldg(yr + 3), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (acc > bestv || (acc == bestv && col < besti)) { bestv = acc; besti = col; }
+  };
+  const float4 xme = x4[lane];
+  const int myc = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const int NY = d.NY;
+  auto rescore = [&](int col0) {
+    float pr[kChunk];
+    if (vec_ok) {
+      float4 yv[kChunk];
+      const float* ybase = Y + (int64_t)col0 * ldy;
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) {
+        const int rr = col0 + r < NY ? r : NY - 1 - col0;          // clamped: masked below
+        yv[r] = __ldg(reinterpret_cast<const float4*>(ybase + (int64_t)rr * ldy) + lane);
+      }
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r)
+        pr[r] = fmaf(xme.w, yv[r].w, fmaf(xme.z, yv[r].z, fmaf(xme.y, yv[r].y, xme.x * yv[r].x)));
+    } else {
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) {
+        const float* yr = Y + (int64_t)min(col0 + r, NY - 1) * ldy + lane * 4;
+        pr[r] = fmaf(xme.w, __ldg(yr + 3), fmaf(xme.z, __ldg(yr + 2), fmaf(xme.y, __ldg(yr + 1), xme.x * __ldg(yr))));
+      }
+    }
+    float q4[4], q2[2], s32;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? pr[r] : pr[r + 4], 16);
+        q4[r] = (hi ? pr[r + 4] : pr[r]) + got;
+      }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 8);
+        q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
+      }
+    }
+    {
+      const bool hi = lane & 4;
+      const float got = __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 4);
+      s32 = (hi ? q2[1] : q2[0]) + got;
+    }
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 2);
+    s32 += __shfl_xor_sync(0xffffffffu, s32, 1);
+    if (col0 + myc >= NY) s32 = -INFINITY;
+    float cm = s32;
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if (exact) {
+      // exact pass (rare): every column within the float32 error band of the running maximum is evaluated in
+      // float64; the argmax of the exact values wins, first index on ties
+      m32 = fmaxf(m32, cm);
+      unsigned need = __ballot_sync(0xffffffffu, (lane & 3) == 0 && s32 >= m32 - band);
+      while (need) {
+        const int l = __ffs(need) - 1;
+        need &= need - 1;
+        exact_col(col0 + (l >> 2));
+      }
+      if ((besti >> 3) == (col0 >> 3)) best_s32 = s32;   // the winner moved into this chunk (a chunk is visited once)
+    } else {
+      // float32 pass: the winner is the float32 maximum unless a second column comes within the error band
+      const unsigned near = __ballot_sync(0xffffffffu, (lane & 3) == 0 && s32 >= cm - band);
+      amb |= (near & (near - 1)) != 0 || (cm <= m32 ? cm >= m32 - band : m32 >= cm - band);
+      if (cm > m32) {
+        m32 = cm;
+        besti = col0 + ((__ffs(__ballot_sync(0xffffffffu, (lane & 3) == 0 && s32 == cm)) - 1) >> 2);
+        best_s32 = s32;
+      }
+    }
+  };
+
+  // candidates = listed entries >= F - delta (every chunk when a list overflowed)
+  auto walk = [&](float thr, bool overflow) {
+    if (overflow) {
+      for (int c = 0; c < a.nchunks; ++c) rescore(c * kChunk);
+      return 0;
+    }
+    int ncand = 0;
+    for (int l0 = 0; l0 < nlines; l0 += 4) {
+      const uint4 lw = __ldg(lines + l0 * 8 + lane);
+      const int cnt = (int)__shfl_sync(0xffffffffu, lw.x, lane & ~7);
+      const int s0 = 2 * (lane & 7);
+      const bool c0 = s0 >= 1 && s0 <= cnt && __uint_as_float(lw.y) >= thr;
+      const bool c1 = s0 + 1 <= cnt && __uint_as_float(lw.w) >= thr;
+      unsigned any = __ballot_sync(0xffffffffu, c0 || c1);
+      while (any) {
+        const int l = __ffs(any) - 1;
+        any &= any - 1;
+        const int f0 = __shfl_sync(0xffffffffu, (int)c0, l), f1 = __shfl_sync(0xffffffffu, (int)c1, l);
+        const unsigned ch0 = __shfl_sync(0xffffffffu, lw.x, l), ch1 = __shfl_sync(0xffffffffu, lw.z, l);
+        // an entry names a tile quarter (8 chunks from chunk0) and the chunks of it that were within delta
+        if (f0) for (unsigned mk = ch0 >> 24; mk; mk &= mk - 1) { rescore((int)((ch0 & 0xffffffu) + __ffs(mk) - 1) * kChunk); ++ncand; }
+        if (f1) for (unsigned mk = ch1 >> 24; mk; mk &= mk - 1) { rescore((int)((ch1 & 0xffffffu) + __ffs(mk) - 1) * kChunk); ++ncand; }
+      }
+    }
+    return ncand;
+  };
+
+  // ---- F = largest listed value; overflow flags
+  bool overflow = false;
+  float F = -INFINITY;
+  int dbg_cand = 0, dbg_entries = 0;
+  for (int l0 = 0; l0 < nlines; l0 += 4) {
+    if (l0 > 0) lv = __ldg(lines + l0 * 8 + lane);
+    const int cnt = (int)__shfl_sync(0xffffffffu, lv.x, lane & ~7);        // slot 0 of this lane's line
+    overflow |= cnt >= kListSlots;
+    if ((lane & 7) == 0) dbg_entries += cnt;
+    const int s0 = 2 * (lane & 7);                                        // slots held by this lane: s0, s0 + 1
+    if (s0 >= 1 && s0 <= cnt) F = fmaxf(F, __uint_as_float(lv.y));
+    if (s0 + 1 <= cnt) F = fmaxf(F, __uint_as_float(lv.w));
+  }
+  overflow = __any_sync(0xffffffffu, overflow);
+  F = warp_max(F);
+  const float thr = F - delta;
+  dbg_cand = walk(thr, overflow);
+  if (amb) {            // warp uniform
+    exact = true;
+    m32 = -INFINITY; besti = 0x7fffffff; best_s32 = 0.f;
+    walk(thr, overflow);
+  }
+  if ((lane & 3) == 0) a.best8[((size_t)pair * d.NX + row) * kChunk + myc] = best_s32;
+  if (lane == 0) {
+    const int bj = besti == 0x7fffffff ? 0 : besti;
+    a.nn[(size_t)pair * d.NX + row] = bj;
+    // threshold a competitor's group entry must reach to possibly beat this row at column bj
+    const float xmax = __uint_as_float(xst.max_norm);
+    const float eps_max = __uint_as_float(xst.max_err) * __uint_as_float(ys.max_norm_bf) + xmax * __uint_as_float(ys.max_err) +
+                          kAccSlack * xmax * ymax;
+    const float mm = xmax * ymax;
+    const float scale = mm > 0.f ? 1.f / mm : 1.f;
+    // exact s(i, bj) >= m32 - band / 2 when only the float32 pass ran
+    const float vlow = exact ? __double2float_rd(bestv) : m32 - 0.5f * band;
+    float thr_v = (vlow - eps_max) * scale - 1e-6f;
+    if (thr_v > 0.f) thr_v *= kG8Slack;           // what a stored group entry may lack (see g8_reduce)
+    atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
+    a.mutual[(size_t)pair * d.NX + row] = 1;
+  }
+  if (a.dbg) {
+    dbg_entries = (int)warp_sum((float)dbg_entries);
+    if (lane == 0) {
+      atomicAdd(a.dbg + 0, 1ull);
+      atomicAdd(a.dbg + 1, overflow ? 1ull : 0ull);
+      atomicAdd(a.dbg + 8, amb ? 1ull : 0ull);
+      atomicAdd(a.dbg + 2, (unsigned long long)dbg_cand);
+      atomicAdd(a.dbg + 3, (unsigned long long)dbg_entries);
+    }
   }
 }
 
@@ -1064,11 +1599,26 @@ struct TcWs {
   float* best8;
   int *tmin, *comp_cnt, *comp;
   unsigned char* mutual;
+  uint2* lists;
+  unsigned* g8;
+  unsigned long long* dbg;
+  int list_splits;
   size_t total;
 };
 
+static void choose_splits(int P, int rb0, int yt0, int rb1, int yt1, int G, int* s0, int* s1);
+
+// column splits of the matches-only launch for this problem (the lists are sized by it)
+static int one_dir_splits(int P, int N, int M) {
+  const int Np = (N + kXRows - 1) / kXRows * kXRows;
+  int s0, s1;
+  choose_splits(P, Np / kXRows, (M + kYRows - 1) / kYRows, 0, (N + kYRows - 1) / kYRows, sm_count() / 2, &s0, &s1);
+  return s0;
+}
+
 static TcWs carve_tc(void* base, int P, int N, int M) {
   TcWs w;
+  const int list_splits = one_dir_splits(P, N, M);
   const size_t Np = pad_rows(N), Mp = pad_rows(M);
   size_t off = 0;
   char* p = (char*)base;
@@ -1097,6 +1647,11 @@ static TcWs carve_tc(void* base, int P, int N, int M) {
   w.comp_cnt = w.tmin + P * nch;
   w.comp = (int*)take(sizeof(int) * P * nch * kCompCap);
   w.mutual = (unsigned char*)take((size_t)P * N);
+  // list / group-entry form of the matches-only path
+  w.list_splits = list_splits;
+  w.lists = (uint2*)take(sizeof(uint2) * kListSlots * (size_t)P * Np * 4 * list_splits);
+  w.g8 = (unsigned*)take(sizeof(unsigned) * (size_t)P * w.pitch[0] * (Np / 8));
+  w.dbg = (unsigned long long*)take(sizeof(unsigned long long) * 16);
   w.total = off;
   return w;
 }
@@ -1147,10 +1702,14 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   const int Np = pad_rows(N), Mp = pad_rows(M);
   if ((long long)P * Np >= (1ll << 31) || (long long)P * Mp >= (1ll << 31))
     return set_error(POSFEAT_EINVAL, "batched matcher: pairs * rows exceeds 2^31");
-  // matches-only calls (nn21 == NULL) verify mutuality per column chunk, which is limited to kVerMaxChunks chunks:
+  // matches-only calls (nn21 == NULL): candidate lists + group entries (default), or the chunk-maximum table with a
+  // scan kernel (POSFEAT_MNN_TABLE=1, kept for A/B measurements), which is limited to kVerMaxChunks column chunks:
   // refuse BEFORE anything is queued (the two-direction path needs an nn21 buffer to write to)
-  if (nn21 == nullptr && top12 == nullptr && w.pitch[0] > kVerMaxChunks)
-    return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher (nn21 == NULL) supports M <= %d; pass an nn21 buffer",
+  const bool want_one = nn21 == nullptr && top12 == nullptr;
+  const char* env_table = getenv("POSFEAT_MNN_TABLE");
+  const bool use_lists = want_one && !(env_table && atoi(env_table) != 0);
+  if (want_one && !use_lists && w.pitch[0] > kVerMaxChunks)
+    return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher (nn21 == NULL) in table form supports M <= %d; pass an nn21 buffer",
                      kVerMaxChunks * kChunk);
 
   if (!prepared) {   // otherwise the sampler already left bf16 rows, norms and maxima in the workspace (tc_prep_sink)
@@ -1173,8 +1732,9 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   const int yt0 = (M + kYRows - 1) / kYRows, yt1 = (N + kYRows - 1) / kYRows;
   int s0, s1;
   // nn21 == NULL: matches only -> the second direction is replaced by the column verification
-  const bool one_dir = nn21 == nullptr && top12 == nullptr && w.pitch[0] <= kVerMaxChunks;
+  const bool one_dir = want_one;
   choose_splits(P, rb0, yt0, one_dir ? 0 : rb1, yt1, G, &s0, &s1);
+  if (use_lists && s0 != w.list_splits) return set_error(POSFEAT_EINVAL, "internal: list split count changed (%d vs %d)", s0, w.list_splits);
   auto fill = [&](DirParams& d, int dir, int NX, int NY, int NXpad, int NYpad, int yt, int S) {
     d.xnorm = dir ? w.bnorm : w.anorm;
     d.xerr = dir ? w.berr : w.aerr;
@@ -1199,14 +1759,52 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     p.debug = dbg ? atoi(dbg) : 0;
   }
 
-  PF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+  p.L = ListParams{w.lists, w.g8, Np / 8};
   const int grid = 2 * (p.units_total < G ? p.units_total : G);
   prof_begin(PROF_MNN_TC, stream);
-  mnn_tc_kernel<<<grid, kTcThreads, kSmemAlloc, stream>>>(mapA, mapB, p);
+  if (use_lists) {
+    PF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    mnn_tc_kernel<true><<<grid, kTcThreads, kSmemAlloc, stream>>>(mapA, mapB, p);
+  } else {
+    PF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc));
+    mnn_tc_kernel<false><<<grid, kTcThreads, kSmemAlloc, stream>>>(mapA, mapB, p);
+  }
   prof_end(PROF_MNN_TC, stream);
   PF_LAUNCH_CHECK("mnn_tc_kernel");
+  if (p.debug & 0x1000) return POSFEAT_OK;     // bring-up timing of the tensor kernel alone (results are not produced)
 
   const int nchunks = (M + kChunk - 1) / kChunk;
+  if (P > 65535) return set_error(POSFEAT_EINVAL, "batched matcher: at most 65535 pairs per call");
+  if (use_lists) {
+    PF_CUDA(cudaMemsetAsync(w.tmin, 0x7f, sizeof(int) * (size_t)P * nchunks, stream));
+    const bool dbg_on = getenv("POSFEAT_MNN_DEBUG") != nullptr;
+    if (dbg_on) PF_CUDA(cudaMemsetAsync(w.dbg, 0, sizeof(unsigned long long) * 16, stream));
+    RescoreListArgs ra{p.d[0], w.lists, A, lda, strideA, Bm, ldb, strideB, nn12, w.best8, w.tmin, w.mutual, nchunks,
+                       dbg_on ? w.dbg : nullptr};
+    prof_begin(PROF_MNN_RESCORE, stream);
+    tc_rescore_lists_kernel<<<dim3((unsigned)((N + kRlWarps - 1) / kRlWarps), (unsigned)P), kRlWarps * 32, 0, stream>>>(ra);
+    prof_end(PROF_MNN_RESCORE, stream);
+    PF_LAUNCH_CHECK("tc_rescore_lists_kernel");
+    VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, nullptr, nullptr, w.best8, w.mutual, nchunks, w.tmin, w.g8, Np / 8,
+                  dbg_on ? w.dbg : nullptr};
+    prof_begin(PROF_MNN_VERIFY, stream);
+    tc_verify_kernel<true><<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
+    prof_end(PROF_MNN_VERIFY, stream);
+    PF_LAUNCH_CHECK("tc_verify_kernel<g8>");
+    prof_begin(PROF_MNN_COMPACT, stream);
+    tc_compact_flags_kernel<<<P, 1024, 0, stream>>>(nn12, w.mutual, N, matches, n_matches);
+    prof_end(PROF_MNN_COMPACT, stream);
+    PF_LAUNCH_CHECK("tc_compact_flags_kernel");
+    if (dbg_on) {   // diagnostics only: synchronises
+      unsigned long long h[9];
+      PF_CUDA(cudaMemcpyAsync(h, w.dbg, sizeof(h), cudaMemcpyDeviceToHost, stream));
+      PF_CUDA(cudaStreamSynchronize(stream));
+      fprintf(stderr, "posfeat mnn lists: P=%d N=%d M=%d splits=%d | rows %llu overflow %llu exact-pass %llu candidates %llu list-entries %llu | "
+                      "chunks %llu competitors %llu overflow-chunks %llu long-chunks(>32) %llu\n", P, N, M, s0, h[0], h[1], h[8],
+              h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
+    return POSFEAT_OK;
+  }
   if (one_dir) {
     PF_CUDA(cudaMemsetAsync(w.tmin, 0x7f, sizeof(int) * (size_t)P * nchunks, stream));
     PF_CUDA(cudaMemsetAsync(w.comp_cnt, 0, sizeof(int) * (size_t)P * nchunks, stream));
@@ -1216,7 +1814,6 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   RescoreArgs r1{p.d[1], Bm, ldb, strideB, A, lda, strideA, nn21, nullptr, top21, nullptr, nullptr, nullptr, 0};
   if (one_dir) r1.d.NX = 0;
   const dim3 resc_grid((unsigned)((N + (one_dir ? 0 : M) + kResWarps - 1) / kResWarps), (unsigned)P);
-  if (P > 65535) return set_error(POSFEAT_EINVAL, "batched matcher: at most 65535 pairs per call");
   prof_begin(PROF_MNN_RESCORE, stream);
   if (top12) tc_rescore_kernel<true, true><<<resc_grid, kResWarps * 32, 0, stream>>>(r0, r1, P);
   else if (one_dir) tc_rescore_kernel<false, false><<<resc_grid, kResWarps * 32, 0, stream>>>(r0, r1, P);
@@ -1225,7 +1822,6 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   PF_LAUNCH_CHECK("tc_rescore_kernel");
   if (top12) return POSFEAT_OK;      // ratio-test callers apply their own acceptance rule to (nn, top2)
   if (!one_dir) {
-    if (nn21 == nullptr) return set_error(POSFEAT_EUNSUPPORTED, "matches-only matcher supports M <= %d", kVerMaxChunks * kChunk);
     return launch_mutual_compact_batched(nn12, nn21, P, N, M, matches, n_matches, stream);
   }
   // enough CTAs to fill the chip also when a single small pair is matched
@@ -1236,9 +1832,9 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   tc_scan_kernel<<<dim3((N + scan_rows - 1) / scan_rows, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
   prof_end(PROF_MNN_SCAN, stream);
   PF_LAUNCH_CHECK("tc_scan_kernel");
-  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.best8, w.mutual, nchunks};
+  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.best8, w.mutual, nchunks, nullptr, nullptr, 0, nullptr};
   prof_begin(PROF_MNN_VERIFY, stream);
-  tc_verify_kernel<<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
+  tc_verify_kernel<false><<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
   prof_end(PROF_MNN_VERIFY, stream);
   PF_LAUNCH_CHECK("tc_verify_kernel");
   prof_begin(PROF_MNN_COMPACT, stream);

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace
-from .preprocess_utils import MIN_PTS, ONE_DIR_MAX_M, denormalize_coords, detect_finish, detect_topk, sample_l2norm
+from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
 def shard(items, rank: int, world: int):
@@ -96,7 +96,7 @@ class PairPipeline:
         # mutuality per column chunk; the exact SIMT matcher (small sizes / algo=1) needs the buffer
         use_simt = not self._tc_applies(n, D)
         algo = (_lib.MNN_TC | _lib.MNN_PREPARED) if prepared else self.mnn_algo
-        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if (use_simt or n > ONE_DIR_MAX_M) else None
+        nn21 = torch.empty((P, n), dtype=torch.int32, device=dev) if use_simt else None
         with torch.cuda.device(dev):
             ws_bytes = L.posfeat_mnn_batched_workspace_bytes(P, n, n, D, _lib.MNN_TC if prepared else self.mnn_algo)
             ws = workspace(ws_key, ws_bytes, dev)

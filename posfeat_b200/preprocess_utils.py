@@ -17,7 +17,6 @@ from . import _lib
 from ._runtime import check, lib, map_ptr, ptr, require_cuda, stream_ptr, to_device, workspace
 
 MIN_PTS = 128   # losses/preprocess_utils.py:260-261
-ONE_DIR_MAX_M = 65536   # matches-only (nn21 == NULL) limit of the tensor-core matcher (mnn_tc.cu kVerMaxChunks * 8)
 
 
 # ---------------------------------------------------------------- coordinates
@@ -237,9 +236,9 @@ def mnn_match(desc_a, desc_b, algo=_lib.MNN_AUTO, want_nn21=True):
         b = b.contiguous()
     dev = a.device
     nn12 = torch.empty(N, dtype=torch.int32, device=dev)
-    # nn21 is needed by the exact SIMT kernel, by callers that ask for it, and by the tensor-core path when
-    # side B has more column chunks than the matches-only verification covers (M > ONE_DIR_MAX_M)
-    needs_nn21 = (want_nn21 or algo == _lib.MNN_SIMT or D != 128 or M > ONE_DIR_MAX_M or
+    # nn21 is needed by the exact SIMT kernel and by callers that ask for it; the tensor-core path without it
+    # contracts one direction only (candidate lists + group entries, any M)
+    needs_nn21 = (want_nn21 or algo == _lib.MNN_SIMT or D != 128 or
                   (algo == _lib.MNN_AUTO and N * M < 1024 * 1024))
     nn21 = torch.empty(M, dtype=torch.int32, device=dev) if needs_nn21 else None
     matches = torch.empty((N, 2), dtype=torch.int64, device=dev)

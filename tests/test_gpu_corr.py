@@ -251,8 +251,12 @@ def test_preprocess_line2window_vs_float64_reference(golden, capsys):
         v &= same
     for key, v in (("feat1g_corloc", None), ("feat2g_corloc", None), ("feat1w_corloc", v1), ("feat2w_corloc", v2)):
         compare(key, pr[key].detach().cpu().numpy(), g["p_" + key], g64["p_" + key], mask=v, scale=float(max(H, W)))
+    # std = sum_xy sqrt(clamp(E[c^2] - E[c]^2)): the subtraction cancels to a few float32 ulps of E[c^2] <= 1, and the
+    # square root amplifies that by 1 / (2 std); at the reference's clamps (1e-6 grid stage, 1e-10 window) a
+    # variance error of 4 ulp (2.4e-7) per axis becomes up to 2.4e-4 in std.  Which of two float32 evaluations lands
+    # closer to the float64 value there is luck, so the floor for std is that bound (5e-4 for the two axes), not 1e-5.
     for key, v in (("feat1g_std", None), ("feat2g_std", None), ("feat1w_std", v1), ("feat2w_std", v2)):
-        compare(key, pr[key].detach().cpu().numpy(), g["p_" + key], g64["p_" + key], mask=v, scale=1.0)
+        compare(key, pr[key].detach().cpu().numpy(), g["p_" + key], g64["p_" + key], mask=v, scale=1.0, floor=5e-4)
     # loss and gradients with the float64 run's std values as the (detached) weights, as in the fixture
     pr2 = dict(pr)
     for key in ("feat1g_std", "feat2g_std", "feat1w_std", "feat2w_std"):

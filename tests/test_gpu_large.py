@@ -64,10 +64,10 @@ def test_mnn_large_vs_blocked_f64(N, M, noise):
     torch.cuda.empty_cache()
 
 
-def test_mnn_more_than_65536_columns():
-    """M > 65536: the matches-only form is not available on the tensor-core path; the wrappers then pass an
-    nn21 buffer (both directions), and a direct C call without one is refused before anything is queued."""
-    import ctypes
+def test_mnn_more_than_65536_columns(monkeypatch):
+    """M > 65536 without an nn21 buffer: the list / group-entry form of the matches-only path has no column limit;
+    the table form kept for A/B measurements (POSFEAT_MNN_TABLE=1) has one and must refuse BEFORE anything is
+    queued (no sticky CUDA error, outputs untouched)."""
     import posfeat_b200 as P
     from posfeat_b200 import _lib
     from posfeat_b200._runtime import stream_ptr, workspace
@@ -78,6 +78,9 @@ def test_mnn_more_than_65536_columns():
     want, nn12, nn21, rg, cg = O.mnn_blocked_f64(a.numpy(), b.numpy())
     got = P.mnn_matcher(a.cuda(), b.cuda(), algo=2)
     assert assert_matches_exact(a, b, got, want, rg, cg) == 0
+    m2, k2, _, g21 = P.mnn_match(a.cuda(), b.cuda(), algo=2, want_nn21=True)      # two directions, table form
+    assert check_argmax_exact(b.numpy(), a.numpy(), g21.cpu().numpy(), nn21) == 0
+    np.testing.assert_array_equal(m2[:int(k2)].cpu().numpy(), got)
     L = _lib.load()
     ac, bc = a.cuda(), b.cuda()
     o12 = torch.empty(N, dtype=torch.int32, device="cuda")
@@ -85,11 +88,67 @@ def test_mnn_more_than_65536_columns():
     nm = torch.zeros(1, dtype=torch.int32, device="cuda")
     ws = workspace("mnn", L.posfeat_mnn_workspace_bytes(N, M, 128, 2), ac.device)
     torch.cuda.synchronize()
+    monkeypatch.setenv("POSFEAT_MNN_TABLE", "1")
     st = L.posfeat_mnn_f32(ac.data_ptr(), N, 128, bc.data_ptr(), M, 128, 128, 2, o12.data_ptr(), None, mt.data_ptr(),
                            nm.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(ac.device))
+    monkeypatch.delenv("POSFEAT_MNN_TABLE")
     assert st == 4 and "nn21" in _lib.last_error()
     torch.cuda.synchronize()                    # no sticky error: nothing was launched
     assert int(nm.item()) == 0
+
+
+@pytest.mark.parametrize("N,M", [(1500, 1300), (4096, 4096), (777, 2049), (1, 5), (130, 1), (3000, 8192), (8192, 8192)])
+def test_mnn_list_form_equals_table_form(monkeypatch, N, M):
+    """The two formulations of the matches-only path -- candidate lists + group entries (default) and the
+    chunk-maximum table + scan kernel (POSFEAT_MNN_TABLE=1) -- return the same nn12 and the same match list, on
+    well-matched, noisy and unrelated descriptor sets (the latter stress the column verification: many
+    competitors per chunk)."""
+    import posfeat_b200 as P
+    for noise, seed in ((0.3, 1), (1.0, 2), (None, 3)):
+        a = unit_desc(N, 128, 40 + seed)
+        b = unit_desc(M, 128, 50 + seed, base=a if (M <= N and noise is not None) else None, noise=noise or 0.0)
+        ac, bc = a.cuda(), b.cuda()
+        m1, k1, n1, _ = P.mnn_match(ac, bc, algo=2, want_nn21=False)
+        monkeypatch.setenv("POSFEAT_MNN_TABLE", "1")
+        m0, k0, n0, _ = P.mnn_match(ac, bc, algo=2, want_nn21=False)
+        monkeypatch.delenv("POSFEAT_MNN_TABLE")
+        np.testing.assert_array_equal(n1.cpu().numpy(), n0.cpu().numpy())
+        np.testing.assert_array_equal(m1[:int(k1)].cpu().numpy(), m0[:int(k0)].cpu().numpy())
+        want, nn12, nn21, rg, cg = O.mnn_blocked_f64(a.numpy(), b.numpy())
+        assert check_argmax_exact(a.numpy(), b.numpy(), n1.cpu().numpy(), nn12) == 0
+        assert assert_matches_exact(a, b, m1[:int(k1)].cpu().numpy(), want, rg, cg) == 0
+
+
+def test_mnn_list_overflow_and_duplicates():
+    """Adversarial inputs for the list form: (a) columns ordered so that every row's chunk maxima keep rising
+    tile after tile (the 15-entry lists overflow -> exhaustive rescoring of those rows), (b) blocks of identical
+    descriptors (every group entry of a chunk ties -> the competitor list overflows -> exhaustive verification),
+    (c) all-negative similarities (thresholds <= 0)."""
+    import posfeat_b200 as P
+    g = torch.Generator().manual_seed(5)
+    # (a) b_j = normalize(u + eps_j * noise) with eps decreasing in j: similarity to a = u rises with j
+    u = torch.nn.functional.normalize(torch.randn(1, 128, generator=g), dim=1)
+    M = 8192
+    eps = torch.linspace(2.0, 0.0, M).unsqueeze(1)
+    b = torch.nn.functional.normalize(u + eps * torch.randn(M, 128, generator=g) * 0.2, dim=1)
+    a = torch.nn.functional.normalize(u + 0.05 * torch.randn(600, 128, generator=g), dim=1)
+    for x, y in ((a, b), (b, a)):
+        want, nn12, nn21, rg, cg = O.mnn_blocked_f64(x.numpy(), y.numpy())
+        m, k, n12, _ = P.mnn_match(x.cuda(), y.cuda(), algo=2, want_nn21=False)
+        assert check_argmax_exact(x.numpy(), y.numpy(), n12.cpu().numpy(), nn12) == 0
+        assert assert_matches_exact(x, y, m[:int(k)].cpu().numpy(), want, rg, cg) == 0
+    # (b) many identical rows and columns
+    z = torch.nn.functional.normalize(torch.randn(6, 128, generator=g), dim=1).repeat(400, 1)
+    zp = z[torch.randperm(z.shape[0], generator=g)]
+    want = O.mnn_blocked_f64(z.numpy(), zp.numpy())[0]
+    m, k, _, _ = P.mnn_match(z.cuda(), zp.cuda(), algo=2, want_nn21=False)
+    np.testing.assert_array_equal(m[:int(k)].cpu().numpy(), want)      # exact ties: first index, no allowance needed
+    # (c) every similarity negative
+    v = torch.nn.functional.normalize(torch.rand(1500, 128, generator=g) + 0.1, dim=1)
+    want, nn12, _, rg, cg = O.mnn_blocked_f64(v.numpy(), (-v).numpy())
+    m, k, n12, _ = P.mnn_match(v.cuda(), (-v).cuda(), algo=2, want_nn21=False)
+    assert check_argmax_exact(v.numpy(), (-v).numpy(), n12.cpu().numpy(), nn12) == 0
+    assert assert_matches_exact(v, -v, m[:int(k)].cpu().numpy(), want, rg, cg) == 0
 
 
 def _pipeline_case(H, W, cfg, seed, P=1):
@@ -143,9 +202,9 @@ def test_pair_pipeline_full_size_vs_oracle(name, H, W, cfg):
     # ---- the reference's own functions (torch CPU), when staged ----
     from oracle import ref_runner
     if ref_runner.available():
-        kps_r, desc_r, m_r = ref_runner.run_pair(score, fmap, dict(cfg))
+        kps_r, desc_r, m_r, idx_r = ref_runner.run_pair(score, fmap, dict(cfg), want_idx=True)
         assert kps_r.shape[1] == n
-        idx_r = ref_runner.keypoint_idx(score, kps_r).numpy()
+        idx_r = idx_r.numpy()
         for b in range(2):
             assert set(idx_r[b].tolist()) == set(idx[b].tolist())
             # same order wherever the selected score is unique
