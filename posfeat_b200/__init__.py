@@ -21,7 +21,7 @@ _LAZY = {
     "get_expected_correspondence_locs": "preprocess", "compute_prob": "preprocess",
     "get_expected_correspondence_within_window": "preprocess",
     "Preprocess_Line2Window": "preprocess",
-    "DiskLoss": "kploss",
+    "DiskLoss": "kploss", "EpipolarLoss_full": "epipolarloss", "GradAllReducer": "dist",
     "process": "extractor", "save_desc": "extractor", "FeatureExtractor": "extractor",
     "AsyncDescWriter": "extractor", "generate_kpts_single_noavg": "preprocess_utils",
     "ratio_matcher": "matchers", "mutual_nn_ratio_matcher": "matchers",

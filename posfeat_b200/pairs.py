@@ -16,9 +16,7 @@ from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace
 from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
-def shard(items, rank: int, world: int):
-    """Static round-robin sharding of an image / pair list (no communication)."""
-    return list(items)[rank::world]
+from .dist import shard  # noqa: E402,F401  (kept importable from here: static round-robin sharding, no communication)
 
 
 class PairPipeline:
@@ -34,6 +32,8 @@ class PairPipeline:
         self.streams = int(streams)          # >1: batches are split over CUDA streams (see run)
         self._side = None
         self._host = None
+        self._hstreams = None
+        self._fetch_ws = []
 
     # -- per-image stage -------------------------------------------------
     def extract(self, score: torch.Tensor, fmap: torch.Tensor):
@@ -121,17 +121,21 @@ class PairPipeline:
             check(L.posfeat_fetch_taps_f32(map_ptr(fmap_host), fmap_dev.data_ptr(), b, D, h, w, fmap_host.stride(0),
                                            fmap_host.stride(1), fmap_host.stride(2), fmap_host.stride(3), kps.data_ptr(),
                                            kps.shape[1], ws.data_ptr(), ws.numel(), stream_ptr(dev)))
+        self._fetch_ws.append((ws, b, h, w))
+        del self._fetch_ws[:-64]                  # bounded: direct callers of run(stage_from=...) never reset it
         return ws
 
-    def staged_pixels(self, fmap_host: torch.Tensor, dev) -> int:
-        """Pixels moved by the last stage_taps call (synchronises)."""
+    def staged_pixels(self, fmap_host: torch.Tensor = None, dev=None) -> int:
+        """Pixels moved by the stage_taps calls of the last run_host / run (synchronises)."""
         import ctypes as C
-        b, D, h, w = fmap_host.shape
-        out = C.c_uint64(0)
-        with torch.cuda.device(dev):
-            ws = workspace("fetch", lib().posfeat_fetch_taps_workspace_bytes(b, h, w), dev)
-            check(lib().posfeat_fetch_taps_count(ws.data_ptr(), b, h, w, C.byref(out), stream_ptr(dev)))
-        return int(out.value)
+        total = 0
+        for ws, b, h, w in self._fetch_ws:
+            out = C.c_uint64(0)
+            with torch.cuda.device(ws.device):
+                torch.cuda.synchronize(ws.device)
+                check(lib().posfeat_fetch_taps_count(ws.data_ptr(), b, h, w, C.byref(out), stream_ptr(ws.device)))
+            total += int(out.value)
+        return total
 
     def run(self, score: torch.Tensor, fmap: torch.Tensor, stage_from: torch.Tensor = None):
         """Whole path for 2P images -> (features dict, matches, n_matches), on device.
@@ -204,8 +208,8 @@ class PairPipeline:
         return feats, torch.cat([p[3] for p in parts]), torch.cat([p[4] for p in parts])
 
     # -- host-buffer entry (what a caller holding CPU tensors uses) --------
-    def run_host(self, score_host: torch.Tensor, fmap_host: torch.Tensor, gather=None):
-        """Inputs in (pinned) host memory; returns host tensors: kpt [2P,n,2],
+    def run_host(self, score_host: torch.Tensor, fmap_host: torch.Tensor, gather=None, chunks=None):
+        """Inputs in (pinned) host memory; returns host tensors (pinned): kpt [2P,n,2],
         matches [P,n,2], n_matches [P].  Copies are part of the call, and the host link bounds it.
 
         ``gather`` selects how the dense descriptor map (34.4 MB per 896x1200 image) reaches the GPU:
@@ -214,7 +218,14 @@ class PairPipeline:
           are fetched from the pinned map, each once (stage_taps: 13.3 MB per image at 8192 keypoints);
         * ``"direct"`` / ``True``: the sampler reads its taps straight from the pinned map (16.8 MB per
           image requested: pixels shared by two keypoints cross the link twice);
-        * ``False``: the whole map is copied first (the plain path)."""
+        * ``False``: the whole map is copied first (the plain path).
+
+        ``chunks``: the batch is cut into that many groups of whole pairs, each on its own stream (default 2 for
+        batches of 8 pairs or more with a fixed ``num_pts``): one group's selection / sampling / matching and its
+        device->host result copy run under the next group's host->device traffic, and the host's wait for a
+        group's keypoint count no longer idles the link.  The detector couples the images of one call through
+        ``n = min`` over the batch (losses/preprocess_utils.py:251-259); if a group comes back with fewer than
+        ``num_pts`` keypoints the call is redone unsplit, so the result never depends on ``chunks``."""
         if gather is None:
             gather = "stage" if self.host_gather_applies(fmap_host) else False
         elif gather is True:
@@ -231,18 +242,69 @@ class PairPipeline:
             self._host = (key, torch.empty_like(score_host, device=dev),
                           None if gather == "direct" else torch.empty_like(fmap_host, device=dev))
         _, s_dev, f_dev = self._host
+        P = score_host.shape[0] // 2
+        num_pts = self.cfg["num_pts"]
+        if chunks is None:
+            chunks = 2 if (P >= 8 and num_pts and num_pts >= MIN_PTS and score_host.is_pinned()) else 1
+        chunks = max(1, min(int(chunks), P))
+        self._fetch_ws = []
+        if chunks > 1 and num_pts and num_pts >= MIN_PTS:
+            out = self._run_host_chunks(score_host, fmap_host, s_dev, f_dev, gather, chunks)
+            if out is not None:
+                return out
+            self._fetch_ws = []
         s_dev.copy_(score_host, non_blocking=True)
-        if gather == "stage":
-            feats, matches, nm = self.run(s_dev, f_dev, stage_from=fmap_host)
-        elif gather == "direct":
-            feats, matches, nm = self.run(s_dev, fmap_host)
-        else:
-            f_dev.copy_(fmap_host, non_blocking=True)
-            feats, matches, nm = self.run(s_dev, f_dev)
-        out = (feats["kpt"].to("cpu", non_blocking=True), matches.to("cpu", non_blocking=True),
-               nm.to("cpu", non_blocking=True))
+        feats, matches, nm = self._run_one(s_dev, f_dev, fmap_host, gather)
+        pin = score_host.is_pinned()
+        n = feats["n"]
+        out = (torch.empty((2 * P, n, 2), dtype=torch.float32, pin_memory=pin),
+               torch.empty((P, n, 2), dtype=torch.int64, pin_memory=pin), torch.empty(P, dtype=torch.int32, pin_memory=pin))
+        for dst, src in zip(out, (feats["kpt"], matches, nm)):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out
+
+    def _run_one(self, s_dev, f_dev, fmap_host, gather):
+        if gather == "stage":
+            return self.run(s_dev, f_dev, stage_from=fmap_host)
+        if gather == "direct":
+            return self.run(s_dev, fmap_host)
+        f_dev.copy_(fmap_host, non_blocking=True)
+        return self.run(s_dev, f_dev)
+
+    def _run_host_chunks(self, score_host, fmap_host, s_dev, f_dev, gather, chunks):
+        dev = s_dev.device
+        P = score_host.shape[0] // 2
+        cap = int(self.cfg["num_pts"])
+        if self._hstreams is None or len(self._hstreams) != chunks:
+            self._hstreams = [torch.cuda.Stream(device=dev) for _ in range(chunks)]
+        main = torch.cuda.current_stream(dev)
+        bounds = [2 * ((P * g) // chunks) for g in range(chunks + 1)]
+        pin = score_host.is_pinned()
+        kpt_h = torch.empty((2 * P, cap, 2), dtype=torch.float32, pin_memory=pin)
+        m_h = torch.empty((P, cap, 2), dtype=torch.int64, pin_memory=pin)
+        nm_h = torch.empty(P, dtype=torch.int32, pin_memory=pin)
+        # every group's score maps are queued first: the link works on group g+1 while the host waits for group g's count
+        for g, st in enumerate(self._hstreams):
+            lo, hi = bounds[g], bounds[g + 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                s_dev[lo:hi].copy_(score_host[lo:hi], non_blocking=True)
+        ok = True
+        for g, st in enumerate(self._hstreams):
+            lo, hi = bounds[g], bounds[g + 1]
+            with torch.cuda.stream(st):
+                feats, matches, nm = self._run_one(s_dev[lo:hi], None if f_dev is None else f_dev[lo:hi], fmap_host[lo:hi], gather)
+                if feats["n"] != cap:          # an image ran short: n couples the whole batch -> redo unsplit
+                    ok = False
+                    break
+                kpt_h[lo:hi].copy_(feats["kpt"], non_blocking=True)
+                m_h[lo // 2:hi // 2].copy_(matches, non_blocking=True)
+                nm_h[lo // 2:hi // 2].copy_(nm, non_blocking=True)
+        for st in self._hstreams:
+            st.synchronize()
+            main.wait_stream(st)
+        return (kpt_h, m_h, nm_h) if ok else None
 
     @staticmethod
     def host_gather_applies(fmap_host):

@@ -100,6 +100,28 @@ def test_pipeline_host_entry_matches_device_entry():
         assert torch.equal(m_h[i, :int(nm_h[i])], matches[i, :int(nm[i])].cpu())
 
 
+@pytest.mark.parametrize("gather", ["stage", "direct", False])
+def test_pipeline_host_entry_chunked_equals_unsplit(gather):
+    """run_host cut into groups of pairs on separate streams (the default from 8 pairs on) returns exactly what the
+    unsplit call returns; when an image has fewer survivors than num_pts (n couples the whole batch through
+    min()) the call falls back to the unsplit form."""
+    from posfeat_b200.pairs import PairPipeline
+    score, fmap = small_pairs(9, seed=13)
+    f_cl = fmap.contiguous(memory_format=torch.channels_last).pin_memory()
+    sp = score.pin_memory()
+    for cfg, short in ((CFG, False), (dict(CFG, num_pts=6000), True)):
+        pipe = PairPipeline(cfg)
+        one = pipe.run_host(sp, f_cl, gather=gather, chunks=1)
+        for chunks in (None, 2, 3):
+            got = pipe.run_host(sp, f_cl, gather=gather, chunks=chunks)
+            assert all(t.is_pinned() for t in got)
+            assert (got[0].shape[1] < cfg["num_pts"]) == short
+            for a, b in zip(got, one):
+                assert torch.equal(a, b)
+        if gather == "stage" and not short:
+            assert pipe.staged_pixels() > 0
+
+
 def test_pipeline_host_gather_equals_full_copy():
     """run_host with a pinned channels-last descriptor map: either exactly the pixels under the keypoints'
     taps are staged on the device (posfeat_fetch_taps_f32, the default) or the sampler reads the taps over the
