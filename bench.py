@@ -362,6 +362,7 @@ def main():
     ap.add_argument("--passes", type=int, default=20, help="passes over the resident batch per step (device-resident leg)")
     ap.add_argument("--e2e-passes", type=int, default=1, help="run_host calls per step of the e2e leg")
     ap.add_argument("--streams", type=int, default=1, help="CUDA streams the pair batch is split over (1 = plain path)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="run_host groups (0 = the call's default)")
     ap.add_argument("--no-host-gather", action="store_true",
                     help="e2e leg: copy the whole descriptor map to the device instead of gathering taps over the host link")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -446,13 +447,13 @@ def main():
 
     def time_host(gather, steps):
         for _ in range(2):
-            pipe.run_host(score_h, fmap_h, gather=gather)
+            pipe.run_host(score_h, fmap_h, gather=gather, chunks=args.e2e_chunks or None)
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(steps * args.e2e_passes):
-            res = pipe.run_host(score_h, fmap_h, gather=gather)
+            res = pipe.run_host(score_h, fmap_h, gather=gather, chunks=args.e2e_chunks or None)
         g1.record()
         torch.cuda.synchronize()
         return max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0)), res   # host is in the loop: take wall clock

@@ -286,3 +286,22 @@ def test_install_patches_reference_style_module():
     det = getattr(fake, "generate_kpts_single")                 # managers/extractor.py:87 style dispatch
     k, s = det(torch.rand(1, 1, 40, 48).cuda() + 0.1, nms_radius=1, num_pts=140)
     assert tuple(k.shape) == (1, 140, 2) and tuple(s.shape) == (1, 140, 1)
+
+
+def test_matching_driver_on_device(tmp_path):
+    """The feature-file driver with the CUDA matcher (its default): descriptors are cached on the device, results
+    equal the oracle's per pair and the HPatches score equals the single-process reference loop."""
+    import test_matching_driver as T
+    from posfeat_b200 import matching_driver as MD
+    root = str(tmp_path)
+    T._write_features(root)
+    res = MD.hpatches_benchmark(T.SEQS, root, T.METHOD, T._homography)
+    ri, rv, rtype, rfeats, rmatches = T._reference_loop(root)
+    for t in ri:
+        assert abs(res[0][t] - ri[t]) < 1e-12 and abs(res[1][t] - rv[t]) < 1e-12
+    np.testing.assert_array_equal(res[2][2], rmatches)
+    pairs = MD.hpatches_pairs(T.SEQS[:2])
+    got = MD.match_pairs(pairs, root, T.METHOD)
+    for (a, b), m in got.items():
+        za, zb = np.load(os.path.join(root, f"{a}.{T.METHOD}")), np.load(os.path.join(root, f"{b}.{T.METHOD}"))
+        np.testing.assert_array_equal(m, O.mnn_matcher(za["descriptors"], zb["descriptors"], exact=True))
