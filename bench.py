@@ -314,7 +314,7 @@ def workload_aachen(dev, n_img=32, n_ret=20, iters=3, num_pts=None):
     if nms_ms:
         nb = 4.0 * n_img * h * w
         out["nms_hbm_frac"] = nb / (nms_ms * 1e-3) / 1e9 / pk["hbm"]
-        sel = ker.get("select_topk", 0.0)
+        sel = ker.get("select_topk", 0.0) + ker.get("keypoint_outputs", 0.0)
         out["nms_topk_hbm_frac"] = (nb + 20.0 * n * n_img) / ((nms_ms + sel) * 1e-3) / 1e9 / pk["hbm"]
     return out
 
@@ -527,6 +527,8 @@ def main():
                     "frac_of_sustained_peak": ach / pk["bf16_sustained"]}
         nms_ms = kern.get("nms_candidates", {}).get("ms_per_launch")
         sel_ms = kern.get("select_topk", {}).get("ms_per_launch")
+        if sel_ms:
+            sel_ms += kern.get("keypoint_outputs", {}).get("ms_per_launch", 0.0)
         extra = {}
         if nms_ms:
             nbytes = 4.0 * 2 * P * H * W

@@ -32,7 +32,8 @@ static std::vector<ProfPair> g_prof[PROF_COUNT];
 static cudaEvent_t g_prof_open[PROF_COUNT];
 static const char* kProfNames[PROF_COUNT] = {"nms_candidates", "select_topk", "sample_l2norm", "mnn_prep", "mnn_tc",
                                              "mnn_rescore", "mnn_simt", "mnn_compact", "corr_fwd", "corr_bwd",
-                                             "window_fwd", "window_bwd", "mnn_scan", "mnn_verify", "fetch_taps"};
+                                             "window_fwd", "window_bwd", "mnn_scan", "mnn_verify", "fetch_taps",
+                                             "keypoint_outputs"};
 
 void prof_begin(int slot, cudaStream_t s) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;

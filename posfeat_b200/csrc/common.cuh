@@ -65,7 +65,7 @@ void count_launch();
 enum ProfSlot {
   PROF_NMS = 0, PROF_SELECT, PROF_SAMPLE, PROF_MNN_PREP, PROF_MNN_TC, PROF_MNN_RESCORE, PROF_MNN_SIMT,
   PROF_MNN_COMPACT, PROF_CORR_FWD, PROF_CORR_BWD, PROF_WIN_FWD, PROF_WIN_BWD, PROF_MNN_SCAN, PROF_MNN_VERIFY,
-  PROF_FETCH, PROF_COUNT
+  PROF_FETCH, PROF_KPOUT, PROF_COUNT
 };
 void prof_begin(int slot, cudaStream_t s);
 void prof_end(int slot, cudaStream_t s);

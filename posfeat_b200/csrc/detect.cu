@@ -446,10 +446,22 @@ nms_quad_r1_kernel(const float* __restrict__ score, int H, int W, int64_t sb, in
       const bool k2 = c2 > fmaxf(fmaxf(a2, c1), tv) && c2 >= fmaxf(c3, n2);
       const bool k3 = c3 > fmaxf(fmaxf(a3, c2), tv) && c3 >= fmaxf(cr, n3);
       const int sh = shift + 4 * k;
+      if (kPosThr) {
+        // chained predicate + one predicated OR per pixel (the compiler otherwise emits two SETP, two SEL and an add)
+        auto keep_bit = [&](float c, float m_gt, float m_ge, unsigned bit) {
+          asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.ge.and.f32 p, %1, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
+              : "+r"(mask) : "f"(c), "f"(m_gt), "f"(m_ge), "r"(bit));
+        };
+        keep_bit(c0, fmaxf(fmaxf(a0, cl), tv), fmaxf(c1, n0), 1u << sh);
+        keep_bit(c1, fmaxf(fmaxf(a1, c0), tv), fmaxf(c2, n1), 2u << sh);
+        keep_bit(c2, fmaxf(fmaxf(a2, c1), tv), fmaxf(c3, n2), 4u << sh);
+        keep_bit(c3, fmaxf(fmaxf(a3, c2), tv), fmaxf(cr, n3), 8u << sh);
+      } else {
       if (k0) mask |= 1u << sh;
       if (k1) mask |= 2u << sh;
       if (k2) mask |= 4u << sh;
       if (k3) mask |= 8u << sh;
+      }
       if (!kPosThr) {
         if (k0 && c0 > 0.f) maskp |= 1u << sh;
         if (k1 && c1 > 0.f) maskp |= 2u << sh;
@@ -727,6 +739,8 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* s_keys = (u64*)smem_raw;  // kSortSmemKeys
   __shared__ unsigned s_hist[1 << kDigitBits];
+  __shared__ unsigned s_off[1 << kDigitBits];      // rank path: keys in higher bins (= first output slot of the bin)
+  __shared__ int s_maxbin;
   __shared__ unsigned s_bitmap[kFillBitmapWords];
   __shared__ unsigned s_fill[kFillMax];
   __shared__ int s_cnt, s_cnt_lo;
@@ -772,6 +786,8 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   bool split = false;
   int hi_shift = 0, n_above = 0;
   u64 hi_prefix = 0;
+  int passes = 0, rank_shift = 0, rank_bucket = 0;
+  u64 rank_base = 0;
   if (C > kSortSmemKeys) {
     // common leading bits (scores of one map share sign/exponent bits): start the
     // radix walk at the first differing bit so the histogram bins actually spread
@@ -808,24 +824,27 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
         kmin = s_red[0][k] < kmin ? s_red[0][k] : kmin;
         kmax = s_red[1][k] > kmax ? s_red[1][k] : kmax;
       }
-      const u64 diff = kmin ^ kmax;
-      const int top = diff ? 63 - __clzll((long long)diff) : kDigitBits - 1;      // highest differing bit
-      int sh = top - (kDigitBits - 1);
-      if (sh < 0) sh = 0;
-      s_shift0 = sh;
-      s_prefix = sh + kDigitBits < 64 ? (kmax >> (sh + kDigitBits)) : 0ull;       // shared by every key
+      // bucket = [base, base + 2^width): starts as the smallest power-of-two window over [kmin, kmax] anchored at
+      // kmin, so the 2048 bins of the first pass spread over the keys' actual RANGE (a bit field that starts at
+      // the highest differing bit lands on the exponent and leaves a boundary bucket of thousands of keys)
+      const u64 range = kmax - kmin;
+      s_shift0 = range ? 64 - __clzll((long long)range) : 1;                       // width in bits, 1 .. 63
+      s_prefix = kmin;                                                              // base
       s_above = 0;
       s_done = 0;
     }
     __syncthreads();
     PF_TICK();
-    int shift = s_shift0, bits = kDigitBits;       // current digit = key bits [shift, shift + bits)
+    int width = s_shift0;                           // current bucket: keys k with (k - base) >> width == 0
+    int shift = 0;
+    if (tid == 0) s_maxbin = 0;
     for (;;) {
+      ++passes;
       for (int i = tid; i < (1 << kDigitBits); i += kSelThreads) s_hist[i] = 0;
       __syncthreads();
-      const u64 prefix = s_prefix;
-      const bool top_pass = shift + bits >= 64;
-      const unsigned dmask = (1u << bits) - 1u;
+      const u64 base_key = s_prefix;
+      shift = width > kDigitBits ? width - kDigitBits : 0;         // digit = (k - base) >> shift, < 2^(width - shift)
+      const int nb = 1 << (width - shift);
       for (int base = 0; base < C; base += kSelThreads * kUnroll) {
         u64 k[kUnroll];
 #pragma unroll
@@ -836,15 +855,14 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const int i = base + u * kSelThreads + tid;
-          if (i < C && (top_pass || (k[u] >> (shift + bits)) == prefix))
-            atomicAdd(&s_hist[(unsigned)(k[u] >> shift) & dmask], 1u);
+          const u64 off = k[u] - base_key;                          // keys below the bucket wrap to huge offsets
+          if (i < C && (off >> width) == 0) atomicAdd(&s_hist[(unsigned)(off >> shift)], 1u);
         }
       }
       __syncthreads();
       // find the digit d with  above(d) < n_real <= above(d) + hist[d]  (above = keys in higher
       // bins): block-wide suffix sum, two bins per thread
       {
-        const int nb = (int)dmask + 1;
         const int b1 = 2 * tid + 1, b0 = 2 * tid;
         const int h1 = b1 < nb ? (int)s_hist[b1] : 0, h0 = b0 < nb ? (int)s_hist[b0] : 0;
         // inclusive scan over threads in DESCENDING tid order
@@ -860,13 +878,15 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
         for (int wq = (tid >> 5) + 1; wq < kSelThreads / 32; ++wq) higher += s_wsum[wq];
         const int above1 = s_above + higher + (inc - v);  // keys in bins > b1
         const int above0 = above1 + h1;                   // keys in bins > b0
+        if (b1 < nb) s_off[b1] = (unsigned)above1;
+        if (b0 < nb) s_off[b0] = (unsigned)above0;
         __syncthreads();                                  // everyone has read s_above
         const bool hit1 = b1 < nb && above1 < n_real && n_real <= above1 + h1;
         const bool hit0 = b0 < nb && !hit1 && above0 < n_real && (n_real <= above0 + h0 || b0 == 0);
         if (hit1 || hit0) {
           const int d = hit1 ? b1 : b0;
           const int cum = hit1 ? above1 : above0;
-          s_prefix = (prefix << bits) | (u64)d;
+          s_prefix = base_key + ((u64)d << shift);        // the boundary bin becomes the bucket
           s_above = cum;
           s_G = cum + (hit1 ? h1 : h0);
           const int bucket = hit1 ? h1 : h0;
@@ -874,13 +894,27 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
         }
       }
       __syncthreads();
+      if (s_done && passes == 1) {
+        // largest bin above the boundary bin (the rank path orders every bin by counting, quadratic in its size)
+        const int d = (int)((s_prefix - base_key) >> shift);
+        const int b1 = 2 * tid + 1, b0 = 2 * tid;
+        int m = 0;
+        if (b1 < nb && b1 > d) m = max(m, (int)s_hist[b1]);
+        if (b0 < nb && b0 > d) m = max(m, (int)s_hist[b0]);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicMax(&s_maxbin, m);
+        rank_base = base_key;
+        rank_shift = shift;
+        rank_bucket = (int)s_hist[d];
+        __syncthreads();
+      }
+      width = shift;
       if (s_done) break;
-      if (shift >= kDigitBits) { shift -= kDigitBits; } else { bits = shift; shift = 0; }
     }
-    LB = s_prefix << shift;
+    LB = s_prefix;
     G = s_G;
-    hi_shift = shift;
-    hi_prefix = s_prefix;
+    hi_shift = width;                               // boundary bucket: (k - LB) >> hi_shift == 0
+    hi_prefix = 0;
     n_above = s_above;
     split = true;
   }
@@ -893,6 +927,59 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     return;
   }
   PF_TICK();
+  // ---- rank path (one histogram pass sufficed, every bin small): the histogram already says where each bin of
+  // winners starts in the output, so the gather drops every key into its bin's slot range and the order inside a
+  // bin comes from counting the larger keys of that bin -- no sorting network at all (the two bitonic sorts were
+  // 40 % of this kernel).  Keys are distinct (the pixel index is part of them), so the ranks are a permutation.
+  constexpr int kRankPerThread = 9;
+  const bool ranked = split && passes == 1 && in_smem && G <= kRankPerThread * kSelThreads && s_maxbin <= 512 &&
+                      rank_bucket <= kBucketMax;
+  if (ranked) {
+    for (int i = tid; i < (1 << kDigitBits); i += kSelThreads) s_hist[i] = 0;     // becomes the per-bin cursor, then the count
+    __syncthreads();
+    for (int base = 0; base < C; base += kSelThreads * kUnroll) {
+      u64 k[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = base + u * kSelThreads + tid;
+        k[u] = i < C ? keys[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = base + u * kSelThreads + tid;
+        if (i < C && k[u] >= LB) {
+          const unsigned bin = (unsigned)((k[u] - rank_base) >> rank_shift);
+          buf[s_off[bin] + atomicAdd(&s_hist[bin], 1u)] = k[u];
+        }
+      }
+    }
+    __syncthreads();
+    PF_TICK();
+    u64 mine[kRankPerThread];
+    int fin[kRankPerThread];
+#pragma unroll
+    for (int e = 0; e < kRankPerThread; ++e) {
+      const int p = e * kSelThreads + tid;
+      fin[e] = -1;
+      if (p < G) {
+        const u64 key = buf[p];
+        const unsigned bin = (unsigned)((key - rank_base) >> rank_shift);
+        const int start = (int)s_off[bin], cnt = (int)s_hist[bin];
+        int r = 0;
+        for (int q = 0; q < cnt; ++q) r += buf[start + q] > key ? 1 : 0;
+        mine[e] = key;
+        fin[e] = start + r;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kRankPerThread; ++e)
+      if (fin[e] >= 0) buf[fin[e]] = mine[e];
+    __syncthreads();
+    G = n_real;          // buf[0, n_real) holds the winners in final order
+    PF_TICK();
+    PF_TICK();
+  } else {
   // ---- gather keys >= LB: certain winners from the front, boundary-bucket keys from the back
   if (tid == 0) { s_cnt = 0; s_cnt_lo = 0; }
   __syncthreads();
@@ -907,7 +994,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
     for (int u = 0; u < kUnroll; ++u) {
       const int i = base + u * kSelThreads + tid;
       const bool take = i < C && k[u] >= LB;
-      const bool lo = take && split && (k[u] >> hi_shift) == hi_prefix;
+      const bool lo = take && split && ((k[u] - LB) >> hi_shift) == hi_prefix;
       const bool hi = take && !lo;
       const unsigned bal_hi = __ballot_sync(0xffffffffu, hi);
       const unsigned bal_lo = __ballot_sync(0xffffffffu, lo);
@@ -950,6 +1037,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   else if (in_smem && P == 2 * kSelThreads) bitonic_sort_desc_reg<2>(buf, s_keys);
   else bitonic_sort_desc(buf, P, s_keys, kSortSmemKeys, in_smem);
   PF_TICK();
+  }   // !ranked
 
   // ---- filler for rows [n_real, n): lowest-index pixels that are not winners
   const int f = n - n_real;
@@ -1157,13 +1245,15 @@ extern "C" int posfeat_detect_select_f32(const float* score, int B, int H, int W
   const size_t smem = sizeof(u64) * kSortSmemKeys;
   // per device/context attribute: set on every call (cheap), never cached in a process-global flag
   PF_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(PROF_SELECT, stream);
+  prof_begin(PROF_SELECT, stream);
   select_kernel<<<B, kSelThreads, smem, stream>>>(score, B, H, W, stride_b, stride_y, num_pts, min_pts, cap_pts, n_fixed,
                                                    counts, w.cand_count, w.cand, w.cand_cap, w.sortbuf, w.sort_cap,
                                                    w.status, n_out, idx_out, kps_out, kpscore_out,
                                                    (mode & POSFEAT_DETECT_FULLMAP) ? 1 : 0,
                                                    getenv("POSFEAT_SELECT_DEBUG") ? 1 : 0);
+  prof_end(PROF_SELECT, stream);
   PF_LAUNCH_CHECK("select_kernel");
+  ProfScope prof(PROF_KPOUT, stream);
   keypoint_outputs_kernel<<<dim3((cap_pts + 255) / 256, B), 256, 0, stream>>>(
       score, H, W, stride_b, stride_y, cap_pts, w.status, n_out, idx_out, kps_out, kpscore_out,
       (mode & POSFEAT_DETECT_FULLMAP) ? 1 : 0);

@@ -284,8 +284,11 @@ def get_expected_correspondence_within_window(feat1, featmap2, coord2_n, window_
     if with_sim:
         raise NotImplementedError("with_sim=True (visualisation only) is not supported")
     B, d, h2, w2 = featmap2.shape
-    offsets = gen_grid(-window_size, window_size, -window_size, window_size,
-                       int(window_size * h2), int(window_size * w2)).to(coord2_n)
+    okey = ("win", float(window_size), h2, w2, str(coord2_n.device), coord2_n.dtype)
+    offsets = _grid_cache.get(okey)
+    if offsets is None:       # built once: a per-call host->device copy would also forbid CUDA-graph capture of the step
+        offsets = _grid_cache[okey] = gen_grid(-window_size, window_size, -window_size, window_size,
+                                               int(window_size * h2), int(window_size * w2)).to(coord2_n)
     exp_xy, std, prob = WindowExpect.apply(feat1, featmap2, coord2_n, offsets)
     coord_grid = coord2_n.unsqueeze(-2) + offsets[None, None]
     if with_std:

@@ -20,15 +20,28 @@ MIN_PTS = 128   # losses/preprocess_utils.py:260-261
 
 
 # ---------------------------------------------------------------- coordinates
+_centres = {}
+
+
+def _centre(h, w, device):
+    """[(w-1)/2, (h-1)/2] on ``device``, built once per (h, w, device): creating it per call would be a
+    pageable host->device copy on every call (and makes the callers impossible to capture in a CUDA graph)."""
+    key = (int(h), int(w), str(device))
+    c = _centres.get(key)
+    if c is None:
+        c = _centres[key] = torch.tensor([(w - 1) / 2., (h - 1) / 2.], dtype=torch.float32).to(device)
+    return c
+
+
 def normalize_coords(coord, h, w):
     """losses/preprocess_utils.py:14-26 (plain tensor arithmetic, no kernel)."""
-    c = torch.tensor([(w - 1) / 2., (h - 1) / 2.], device=coord.device, dtype=torch.float32)
+    c = _centre(h, w, coord.device)
     return (coord - c) / c
 
 
 def denormalize_coords(coord_norm, h, w):
     """losses/preprocess_utils.py:28-38."""
-    c = torch.tensor([(w - 1) / 2., (h - 1) / 2.], device=coord_norm.device, dtype=torch.float32)
+    c = _centre(h, w, coord_norm.device)
     return coord_norm * c + c
 
 
