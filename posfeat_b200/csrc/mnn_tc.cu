@@ -977,20 +977,29 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   int total;
   const int* rows;
   if (kG8) {
+    const uint4* g = reinterpret_cast<const uint4*>(a.g8 + ((size_t)pair * d.pitch + c) * a.groups);
+    const int nvec = a.groups >> 2;                               // groups is a multiple of 32
+    // the first block of group entries is requested together with the threshold (almost every chunk has members):
+    // one memory round trip less on this kernel's dependent chain
+    uint4 e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = q * 32 + lane;
+      e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
+    }
     const int o = a.tmin[slot];
     if (o == 0x7f7f7f7f) return;                                  // no row has its nearest neighbour in this chunk
     const __half2 thr2 = __float2half2_rn(__half2float(__float2half_rd(ordered_int_to_float(o))));
-    const uint4* g = reinterpret_cast<const uint4*>(a.g8 + ((size_t)pair * d.pitch + c) * a.groups);
-    const int nvec = a.groups >> 2;                               // groups is a multiple of 32
     int* myrows = &s_rows[warp * kCompCap];
     unsigned short* myent = &s_ent[warp * kCompCap];
     int n = 0;
     for (int v0 = 0; v0 < nvec; v0 += 128) {
-      uint4 e[4];
+      if (v0 > 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int v = v0 + q * 32 + lane;
-        e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 4; ++q) {
+          const int v = v0 + q * 32 + lane;
+          e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
