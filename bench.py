@@ -263,6 +263,15 @@ def workload_c1(dev, iters=200):
     ker = kernel_times(lambda: pipe.run(score, fmap), 20)
     out = {"workload": "c1_pair_480x640_k4096", "ms_per_pair": ms, "pairs_per_s": 1e3 / ms, "keypoints": int(feats["n"]),
            "matches": int(nm[0]), "kernel_ms": {k: round(v, 5) for k, v in ker.items()}}
+    try:        # the same call captured in a CUDA graph (one submission instead of ~12 launches and a mid-call host wait)
+        from posfeat_b200.pairs import GraphedPairPipeline
+        gp = GraphedPairPipeline(pipe, score.shape, fmap.shape)
+        ms_g, (gf, gm, gnm) = cuda_time(lambda: gp(score, fmap), iters, warmup=5)
+        out["cuda_graph"] = {"ms_per_pair": ms_g, "pairs_per_s": 1e3 / ms_g,
+                             "equal_plain_call": bool(torch.equal(gf["idx"], feats["idx"]) and torch.equal(gnm, nm) and
+                                                      torch.equal(gm[0, :int(nm[0])], matches[0, :int(nm[0])]))}
+    except Exception as e:
+        out["cuda_graph"] = {"error": repr(e)[:200]}
     try:
         kind, idx_r, m_r = cpu_reference_pair(score.cpu(), fmap.cpu().contiguous(), C1_CFG)
         k0 = int(nm[0])

@@ -28,6 +28,7 @@ constexpr int kFillBitmapWords = 2048;    // filler search covers the first 6553
 constexpr int kFillMax = 4096;
 constexpr int kDigitBits = 11;   // radix-select digit width (2048-bin shared histogram)
 constexpr int kBucketMax = 1024;  // boundary bucket small enough to be sorted on its own
+constexpr int kRadixMinKeys = 2048;  // fewer candidates than this are simply sorted; more go through the histogram (rank path)
 constexpr int kUnroll = 8;       // independent candidate loads in flight per thread
 
 constexpr int kCntStride = 32;   // int32 slots between the per-image candidate counters
@@ -788,7 +789,7 @@ select_kernel(const float* __restrict__ score, int B, int H, int W, int64_t sb, 
   u64 hi_prefix = 0;
   int passes = 0, rank_shift = 0, rank_bucket = 0;
   u64 rank_base = 0;
-  if (C > kSortSmemKeys) {
+  if (C > kRadixMinKeys) {
     // common leading bits (scores of one map share sign/exponent bits): start the
     // radix walk at the first differing bit so the histogram bins actually spread
     u64 kmin = ~0ull, kmax = 0ull;

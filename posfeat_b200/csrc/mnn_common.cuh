@@ -9,7 +9,7 @@
 namespace posfeat {
 
 // per-matrix maxima kept by the tensor-core matcher (float bit patterns of non-negative values)
-struct MatStats {
+struct __align__(16) MatStats {
   unsigned max_norm;      // max_j |y_j|
   unsigned max_norm_bf;   // max_j |y~_j|
   unsigned max_err;       // max_j |y~_j - y_j|

@@ -1011,30 +1011,40 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
           info = (m0 & 1u) | (m1 & 1u) << 1 | (m2 & 1u) << 2 | (m3 & 1u) << 3 |
                  ((m0 >> 16) & 1u) << 4 | ((m1 >> 16) & 1u) << 5 | ((m2 >> 16) & 1u) << 6 | ((m3 >> 16) & 1u) << 7 |
                  (e[q].x & 7u) << 8 | (e[q].y & 7u) << 11 | (e[q].z & 7u) << 14 | (e[q].w & 7u) << 17;
-        unsigned any = __ballot_sync(0xffffffffu, info != 0);
-        while (any) {
-          const int l = __ffs(any) - 1;
-          any &= any - 1;
-          const unsigned inf = __shfl_sync(0xffffffffu, info, l);
-          const unsigned ex = __shfl_sync(0xffffffffu, e[q].x, l), ey = __shfl_sync(0xffffffffu, e[q].y, l);
-          const unsigned ez = __shfl_sync(0xffffffffu, e[q].z, l), ew = __shfl_sync(0xffffffffu, e[q].w, l);
-          const int g0 = (v0 + q * 32 + l) * 4;
+        if (!__any_sync(0xffffffffu, info != 0)) continue;
+        // every lane appends the rows of its own hot groups: a warp scan of the per-lane row counts gives the slots
+        const int g0 = (v0 + q * 32 + lane) * 4;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if ((info >> k) & 1u) {
+            const int r0 = (g0 + k) * 8;
+            cnt += ((info >> (4 + k)) & 1u) ? max(0, min(8, d.NX - r0)) : (r0 + (int)((info >> (8 + 3 * k)) & 7u) < d.NX ? 1 : 0);
+          }
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        int pos = n + inc - cnt;
+        n += __shfl_sync(0xffffffffu, inc, 31);
+        if (cnt) {
+          const unsigned ew[4] = {e[q].x, e[q].y, e[q].z, e[q].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (!((inf >> k) & 1u)) continue;                    // warp uniform
+            if (!((info >> k) & 1u)) continue;
             const int r0 = (g0 + k) * 8;
-            const unsigned short ent = (unsigned short)((k == 0 ? ex : k == 1 ? ey : k == 2 ? ez : ew) & 0xffffu);   // max1: bounds every row of the group
-            if ((inf >> (4 + k)) & 1u) {                         // two or more rows of the group matter: take all 8
-              const int add = min(8, d.NX - r0);
-              if (add > 0) {
-                if (lane < add && n + lane < kCompCap) { myrows[n + lane] = r0 + lane; myent[n + lane] = ent; }
-                n += add;
-              }
+            const unsigned short ent = (unsigned short)(ew[k] & 0xffffu);        // max1: bounds every row of the group
+            if ((info >> (4 + k)) & 1u) {                                        // two or more rows of the group matter: all 8
+              for (int j = 0; j < 8 && r0 + j < d.NX; ++j, ++pos)
+                if (pos < kCompCap) { myrows[pos] = r0 + j; myent[pos] = ent; }
             } else {
-              const int r = r0 + (int)((inf >> (8 + 3 * k)) & 7u);
+              const int r = r0 + (int)((info >> (8 + 3 * k)) & 7u);
               if (r < d.NX) {
-                if (lane == 0 && n < kCompCap) { myrows[n] = r; myent[n] = ent; }
-                n += 1;
+                if (pos < kCompCap) { myrows[pos] = r; myent[pos] = ent; }
+                ++pos;
               }
             }
           }
@@ -1340,7 +1350,10 @@ __device__ __forceinline__ void rescore_row_lists(const RescoreListArgs& a, cons
   const float delta = 2.f * (d.xerr[prow] * __uint_as_float(ys.max_norm_bf) + xn * __uint_as_float(ys.max_err) +
                              kAccSlack * xn * ymax);
   const float band = 2.f * kEps32 * xn * ymax;
-  const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0);
+  const bool vec_ok = (ldy % 4 == 0) && (((uintptr_t)Y & 15) == 0) && ldy < (1ll << 31);
+  const int ld4 = (int)(ldy >> 2);                                   // row pitch in float4 units (vec_ok)
+  const float4* y4 = reinterpret_cast<const float4*>(Y) + lane;
+  const size_t rowg = (size_t)pair * d.NX + row;                      // index of the row's outputs
   __syncwarp();
 
   float m32 = -INFINITY;       // running float32 maximum over everything seen
@@ -1368,11 +1381,15 @@ __device__ __forceinline__ void rescore_row_lists(const RescoreListArgs& a, cons
     float pr[kChunk];
     if (vec_ok) {
       float4 yv[kChunk];
-      const float* ybase = Y + (int64_t)col0 * ldy;
+      // one 64-bit product for the chunk, then 32-bit row steps (the address arithmetic of eight independent
+      // 64-bit row offsets was a fifth of this kernel's instructions)
+      const float4* yp = y4 + (size_t)(unsigned)col0 * (size_t)ld4;
+      if (col0 + kChunk <= NY) {
 #pragma unroll
-      for (int r = 0; r < kChunk; ++r) {
-        const int rr = col0 + r < NY ? r : NY - 1 - col0;          // clamped: masked below
-        yv[r] = __ldg(reinterpret_cast<const float4*>(ybase + (int64_t)rr * ldy) + lane);
+        for (int r = 0; r < kChunk; ++r) yv[r] = __ldg(yp + r * ld4);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kChunk; ++r) yv[r] = __ldg(yp + min(r, NY - 1 - col0) * ld4);      // clamped: masked below
       }
 #pragma unroll
       for (int r = 0; r < kChunk; ++r)
@@ -1484,10 +1501,10 @@ __device__ __forceinline__ void rescore_row_lists(const RescoreListArgs& a, cons
     m32 = -INFINITY; besti = 0x7fffffff; best_s32 = 0.f;
     walk(thr, overflow);
   }
-  if ((lane & 3) == 0) a.best8[((size_t)pair * d.NX + row) * kChunk + myc] = best_s32;
+  if ((lane & 3) == 0) a.best8[rowg * kChunk + myc] = best_s32;
   if (lane == 0) {
     const int bj = besti == 0x7fffffff ? 0 : besti;
-    a.nn[(size_t)pair * d.NX + row] = bj;
+    a.nn[rowg] = bj;
     // threshold a competitor's group entry must reach to possibly beat this row at column bj
     const float xmax = __uint_as_float(xst.max_norm);
     const float eps_max = __uint_as_float(xst.max_err) * __uint_as_float(ys.max_norm_bf) + xmax * __uint_as_float(ys.max_err) +
@@ -1499,7 +1516,7 @@ __device__ __forceinline__ void rescore_row_lists(const RescoreListArgs& a, cons
     float thr_v = (vlow - eps_max) * scale - 1e-6f;
     if (thr_v > 0.f) thr_v *= kG8Slack;           // what a stored group entry may lack (see g8_reduce)
     atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
-    a.mutual[(size_t)pair * d.NX + row] = 1;
+    a.mutual[rowg] = 1;
   }
   if (a.dbg) {
     dbg_entries = (int)warp_sum((float)dbg_entries);

@@ -176,6 +176,25 @@ class PairPipeline:
         matches, nm = self.match(desc, prepared=prepared)
         return feats, matches, nm
 
+    def run_nosync(self, score: torch.Tensor, fmap: torch.Tensor):
+        """The whole path queued WITHOUT a host round trip: everything runs at n = num_pts (what the detector
+        returns whenever every image has that many survivors); the true n stays on the device.  Returns
+        (result, feats, matches, n_matches) where ``result`` is the detect_topk record to pass to
+        ``detect_finish`` once the caller wants n and the device status -- if that n differs from num_pts the
+        outputs are void and the call has to be redone with ``run``.  Needs a fixed ``num_pts`` >= 128.  This is
+        the form that can be captured in a CUDA graph (see GraphedPairPipeline)."""
+        num_pts = self.cfg["num_pts"]
+        if not num_pts or num_pts < MIN_PTS:
+            raise ValueError("run_nosync needs a fixed num_pts >= 128 (with num_pts=False the count decides the shapes)")
+        r = detect_topk(score, sync=False, **self.cfg)
+        kps = r["kps"]                                              # [b, cap, 2]; all rows valid iff n == cap
+        desc, prepared = self.sample_for_pairs(fmap, kps)
+        matches, nm = self.match(desc, prepared=prepared)
+        h, w = score.shape[2:]
+        feats = {"kps_n": kps, "kpt": denormalize_coords(kps, h, w), "kp_score": r["score"], "desc": desc,
+                 "idx": r["idx"], "n": r["cap"]}
+        return r, feats, matches, nm
+
     def _run_streams(self, score, fmap):
         dev = score.device
         G = self.streams
@@ -322,3 +341,48 @@ class PairPipeline:
     @staticmethod
     def d2h_bytes(n_images, n, P):
         return n_images * n * 2 * 4 + P * n * 2 * 8 + P * 4
+
+
+class GraphedPairPipeline:
+    """A PairPipeline call of fixed shape captured in a CUDA graph: the eight launches, two memsets and the small
+    tensor operations of detect -> sample -> match replay as ONE submission.  For a single small pair (BASELINE
+    config 1: 480x640, 4096 keypoints) the call is bound by launch latency and the host's wait for the keypoint
+    count, not by the kernels; the graph removes both (the count is read once, after the replay).
+
+        g = GraphedPairPipeline(PairPipeline(cfg), score.shape, fmap.shape)
+        feats, matches, nm = g(score, fmap)          # tensors of g: valid until the next call
+
+    Inputs are copied into the graph's static buffers (device-to-device).  When an image has fewer than num_pts
+    survivors the replayed result is void and the call is redone on the plain path, so the result never depends
+    on the graph."""
+
+    def __init__(self, pipe: PairPipeline, score_shape, fmap_shape, channels_last: bool = True, device=None):
+        require_cuda()
+        self.pipe = pipe
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.score = torch.zeros(tuple(score_shape), dtype=torch.float32, device=dev)
+        self.fmap = torch.zeros(tuple(fmap_shape), dtype=torch.float32, device=dev)
+        if channels_last:
+            self.fmap = self.fmap.contiguous(memory_format=torch.channels_last)
+        self.score.fill_(1.0)
+        self.score[..., ::2, ::2] = 2.0                      # a map with plenty of local maxima for the warm-up runs
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                # warm-up on the capture stream: workspaces, caches, attributes
+                pipe.run_nosync(self.score, self.fmap)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.rec, self.feats, self.matches, self.nm = pipe.run_nosync(self.score, self.fmap)
+        self.cap = self.rec["cap"]
+
+    def __call__(self, score: torch.Tensor, fmap: torch.Tensor):
+        self.score.copy_(score, non_blocking=True)
+        self.fmap.copy_(fmap, non_blocking=True)
+        self.graph.replay()
+        n = detect_finish(self.rec)                           # the one host round trip: device status and n
+        if n != self.cap:
+            return self.pipe.run(score, fmap)
+        return self.feats, self.matches, self.nm

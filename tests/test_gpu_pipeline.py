@@ -305,3 +305,32 @@ def test_matching_driver_on_device(tmp_path):
     for (a, b), m in got.items():
         za, zb = np.load(os.path.join(root, f"{a}.{T.METHOD}")), np.load(os.path.join(root, f"{b}.{T.METHOD}"))
         np.testing.assert_array_equal(m, O.mnn_matcher(za["descriptors"], zb["descriptors"], exact=True))
+
+
+def test_graphed_pipeline_equals_plain_call():
+    """The CUDA-graph form of one pipeline call (GraphedPairPipeline) returns the plain call's results, call after
+    call with different inputs, and falls back to the plain path when an image has fewer survivors than num_pts."""
+    from posfeat_b200.pairs import GraphedPairPipeline, PairPipeline
+    cfg = dict(CFG, num_pts=1500)
+    pipe = PairPipeline(cfg)
+    score, fmap = small_pairs(2, seed=31, H=320, W=416)
+    f_cl = fmap.cuda().contiguous(memory_format=torch.channels_last)
+    g = GraphedPairPipeline(pipe, score.shape, f_cl.shape)
+    for seed in (31, 32, 33):
+        score, fmap = small_pairs(2, seed=seed, H=320, W=416)
+        f_cl = fmap.cuda().contiguous(memory_format=torch.channels_last)
+        fa, ma, na = pipe.run(score.cuda(), f_cl)
+        fb, mb, nb = g(score.cuda(), f_cl)
+        assert fb["n"] == fa["n"] == 1500
+        assert torch.equal(fa["idx"], fb["idx"]) and torch.equal(fa["desc"], fb["desc"]) and torch.equal(na, nb)
+        assert torch.equal(fa["kpt"], fb["kpt"])
+        for i in range(2):
+            assert torch.equal(ma[i, :int(na[i])], mb[i, :int(nb[i])])
+    sparse = torch.full_like(score, 0.1)
+    sparse[:, :, 10:300:7, 10:400:9] = 2.0                    # ~1800 isolated maxima in image... fewer than num_pts after NMS in one image
+    sparse[1, :, 10:300:7, 10:400:9] = 0.2
+    sparse[1, :, 10:100:7, 10:100:9] = 2.0
+    fa, ma, na = pipe.run(sparse.cuda(), f_cl)
+    fb, mb, nb = g(sparse.cuda(), f_cl)
+    assert fa["n"] < 1500 and fb["n"] == fa["n"]
+    assert torch.equal(fa["idx"], fb["idx"]) and torch.equal(na, nb)
