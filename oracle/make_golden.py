@@ -418,9 +418,64 @@ def golden_disk():
     print("disk ok", float(out["const/loss"]), float(out["dyn/loss"]))
 
 
+def golden_disk_opts():
+    """DiskLoss with the settings that put gradient on the affinity or rescale the reward threshold
+    (match_grad, cor_detach, rescale_thr; losses/kploss.py:52-129, :152-182): one small shared input, one entry
+    per option set with loss, components and the gradients w.r.t. both score maps AND both descriptor maps."""
+    from losses.kploss import DiskLoss
+    g = gen(808)
+    torch.manual_seed(808)
+    b, h, w, d = 2, 48, 64, 16
+    base = dict(grid_size=8, loss_distance="cos", temperature_base=60, temperature_max=60,
+                epipolar_reward="constant_reward", reward_config=dict(reward_thr=2, rescale_thr=False),
+                cor_detach=True, good_reward=1, bad_reward=-0.25, kp_penalty=-0.001, match_grad=False)
+    kp1_0 = torch.randn(b, 1, h, w, generator=g)
+    kp2_0 = torch.randn(b, 1, h, w, generator=g)
+    xf1_0 = torch.randn(b, d, h // 4, w // 4, generator=g)
+    xf2_0 = xf1_0 + 0.3 * torch.randn(b, d, h // 4, w // 4, generator=g)
+    F1 = torch.tensor([[0., 0., 0.], [0., 0., -1.], [0., 1., 0.]]).repeat(b, 1, 1)
+    F1 = F1 + 0.01 * torch.randn(b, 3, 3, generator=g)            # not exactly a pure shift: the two distances differ
+    F2 = F1.transpose(1, 2).contiguous()
+    sampler = DiskLoss(base)
+    s1 = sampler.point_sample(kp1_0)
+    s2 = sampler.point_sample(kp2_0)
+    out = dict(kp1=kp1_0.numpy(), kp2=kp2_0.numpy(), xf1=xf1_0.numpy(), xf2=xf2_0.numpy(), F1=F1.numpy(), F2=F2.numpy(),
+               coord1=s1[0].numpy(), acc1=s1[2].numpy(), coord2=s2[0].numpy(), acc2=s2[2].numpy())
+    opts = {"mg": dict(match_grad=True), "mg_cd": dict(match_grad=True, cor_detach=False), "cd": dict(cor_detach=False),
+            "rs": dict(reward_config=dict(reward_thr=2, rescale_thr=True)),
+            "rs_dyn_mg": dict(reward_config=dict(reward_thr=2, rescale_thr=True), epipolar_reward="dynamic_reward", match_grad=True)}
+    for tag, o in opts.items():
+        cfg = dict(base, **o)
+        mod = DiskLoss(cfg)
+        kp1, kp2 = kp1_0.clone().requires_grad_(True), kp2_0.clone().requires_grad_(True)
+        xf1, xf2 = xf1_0.clone().requires_grad_(True), xf2_0.clone().requires_grad_(True)
+
+        def replay(kp_map, _kp1=kp1, _s=(s1, s2)):
+            # the recorded proposals / accept draws, with log-probabilities recomputed from THIS map (autograd)
+            coord, _, acc = _s[0] if kp_map is _kp1 else _s[1]
+            logits = pu.unfold(kp_map, 8)
+            bb, c, hh, ww, _ = logits.shape
+            idx = ((coord[..., 1].long() % 8) * 8 + (coord[..., 0].long() % 8)).reshape(bb, 1, hh, ww)
+            from torch.distributions import Bernoulli, Categorical
+            al = torch.gather(logits, -1, idx[..., None]).squeeze(-1)
+            logp = Categorical(logits=logits).log_prob(idx) + Bernoulli(logits=al).log_prob(acc.reshape(bb, 1, hh, ww).float())
+            return coord, logp, acc
+        mod.point_sample = replay
+        outputs = {"epoch": 0, "preds1": {"local_point": kp1, "local_map": xf1}, "preds2": {"local_point": kp2, "local_map": xf2}}
+        loss, comp = mod({"F1": F1, "F2": F2}, outputs, None)
+        loss.backward()
+        out[f"{tag}/loss"] = loss.detach().numpy()
+        for name, t in (("g_kp1", kp1), ("g_kp2", kp2), ("g_xf1", xf1), ("g_xf2", xf2)):
+            out[f"{tag}/{name}"] = (t.grad if t.grad is not None else torch.zeros_like(t)).numpy()
+        for k, v in comp.items():
+            out[f"{tag}/comp/{k}"] = np.asarray(v.detach().numpy() if torch.is_tensor(v) else v)
+    np.savez_compressed(os.path.join(OUT, "disk_opts.npz"), **out)
+    print("disk_opts ok", {t: float(out[f"{t}/loss"]) for t in opts})
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])                      # e.g. `python oracle/make_golden.py detect_ext`
-    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_prob, golden_preprocess, golden_disk):
+    for fn in (golden_detect, golden_detect_ext, golden_sample, golden_mnn, golden_corr, golden_prob, golden_preprocess, golden_disk, golden_disk_opts):
         if not only or fn.__name__[len("golden_"):] in only:
             fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

@@ -89,12 +89,12 @@ struct CorrTcParams {
 
 // ---- split: x -> hi = tf32(x), lo = x - hi, zero padded to [rows_pad][Dp] per batch (Dp = 32 * slices).
 // One thread per float4 of a padded row; a warp covers one 128-column row (or 4 rows of 32 columns).
-__global__ void corr_split_kernel(const float* __restrict__ src, int B, int rows, int D, int rows_pad, int Dp,
-                                  float* __restrict__ hi, float* __restrict__ lo) {
+__device__ __forceinline__ void corr_split_body(const float* __restrict__ src, int B, int rows, int D, int rows_pad, int Dp,
+                                                float* __restrict__ hi, float* __restrict__ lo, int blk, int nblk) {
   const int vpr = Dp >> 2;                                   // float4 per padded row
   const int64_t total = (int64_t)B * rows_pad * vpr;
   const bool vec_ok = (D & 3) == 0 && ((uintptr_t)src & 15) == 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blk * blockDim.x + threadIdx.x; i < total; i += (int64_t)nblk * blockDim.x) {
     const int cv = (int)(i % vpr);
     const int64_t rr = i / vpr;
     const int r = (int)(rr % rows_pad), b = (int)(rr / rows_pad);
@@ -123,15 +123,40 @@ __global__ void corr_split_kernel(const float* __restrict__ src, int B, int rows
   }
 }
 
-__global__ void corr_padv_kernel(const float* __restrict__ v, int vb, int m, int C, int m_pad, float4* __restrict__ v4) {
+__global__ void corr_split_kernel(const float* __restrict__ src, int B, int rows, int D, int rows_pad, int Dp,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  corr_split_body(src, B, rows, D, rows_pad, Dp, hi, lo, blockIdx.x, gridDim.x);
+}
+
+__device__ __forceinline__ void corr_padv_body(const float* __restrict__ v, int vb, int m, int C, int m_pad,
+                                               float4* __restrict__ v4, int blk, int nblk) {
   const int64_t total = (int64_t)vb * m_pad;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blk * blockDim.x + threadIdx.x; i < total; i += (int64_t)nblk * blockDim.x) {
     const int r = (int)(i % m_pad), b = (int)(i / m_pad);
     float t[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < m)
       for (int c = 0; c < C; ++c) t[c] = __ldg(v + ((int64_t)b * m + r) * C + c);
     v4[i] = make_float4(t[0], t[1], t[2], t[3]);
   }
+}
+
+__global__ void corr_padv_kernel(const float* __restrict__ v, int vb, int m, int C, int m_pad, float4* __restrict__ v4) {
+  corr_padv_body(v, vb, m, C, m_pad, v4, blockIdx.x, gridDim.x);
+}
+
+// forward operand preparation in ONE launch (the small dense problems -- coarse 30x40 maps -- are launch bound):
+// blocks [0, gq) split q, [gq, gq + gk) split k, the rest pad the value table
+struct CorrPrepArgs {
+  const float *q, *k, *v;
+  float *qh, *ql, *kh, *kl;
+  float4* v4;
+  int B, n, m, D, n_pad, m_pad, Dp, vb, C, gq, gk, gv;
+};
+__global__ void __launch_bounds__(256) corr_prep_fwd_kernel(const CorrPrepArgs a) {
+  const int b = blockIdx.x;
+  if (b < a.gq) corr_split_body(a.q, a.B, a.n, a.D, a.n_pad, a.Dp, a.qh, a.ql, b, a.gq);
+  else if (b < a.gq + a.gk) corr_split_body(a.k, a.B, a.m, a.D, a.m_pad, a.Dp, a.kh, a.kl, b - a.gq, a.gk);
+  else corr_padv_body(a.v, a.vb, a.m, a.C, a.m_pad, a.v4, b - a.gq - a.gk, a.gv);
 }
 
 // kMode 0: forward (online softmax expectation).  kMode 1: backward, first step -- the same contraction, but
@@ -723,12 +748,14 @@ int corr_tc_fwd(const float* q, const float* k, const float* v, int v_batched, i
   p.v4 = w.v4; p.v_batched = v_batched; p.part = w.part;
   const int Dp = p.atoms * 32;
   ProfScope prof(PROF_CORR_FWD, stream);
-  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.n_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(q, B, n, D, p.n_pad, Dp, w.qh, w.ql);
-  PF_LAUNCH_CHECK("corr_split_kernel(q)");
-  corr_split_kernel<<<(int)std::min<int64_t>(((int64_t)B * p.m_pad * (Dp / 4) + 255) / 256, 148 * 32), 256, 0, stream>>>(k, B, m, D, p.m_pad, Dp, w.kh, w.kl);
-  PF_LAUNCH_CHECK("corr_split_kernel(k)");
-  corr_padv_kernel<<<(int)std::min<int64_t>(((int64_t)vb * p.m_pad + 255) / 256, 148 * 8), 256, 0, stream>>>(v, vb, m, C, p.m_pad, w.v4);
-  PF_LAUNCH_CHECK("corr_padv_kernel");
+  {
+    CorrPrepArgs pa{q, k, v, w.qh, w.ql, w.kh, w.kl, w.v4, B, n, m, D, p.n_pad, p.m_pad, Dp, vb, C, 0, 0, 0};
+    pa.gq = (int)std::min<int64_t>(((int64_t)B * p.n_pad * (Dp / 4) + 255) / 256, 148 * 16);
+    pa.gk = (int)std::min<int64_t>(((int64_t)B * p.m_pad * (Dp / 4) + 255) / 256, 148 * 16);
+    pa.gv = (int)std::min<int64_t>(((int64_t)vb * p.m_pad + 255) / 256, 148 * 4);
+    corr_prep_fwd_kernel<<<pa.gq + pa.gk + pa.gv, 256, 0, stream>>>(pa);
+    PF_LAUNCH_CHECK("corr_prep_fwd_kernel");
+  }
   CUtensorMap mqh, mql, mkh, mkl;
   if (int e = make_map_f32(&mqh, w.qh, Dp, (int64_t)B * p.n_pad)) return e;
   if (int e = make_map_f32(&mql, w.ql, Dp, (int64_t)B * p.n_pad)) return e;

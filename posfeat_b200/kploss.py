@@ -13,9 +13,14 @@ What runs where
     log-sum-exp, two more (roles swapped) give per point the sums the loss and its gradient need.
     No [b,m,n] tensor is ever materialised (the reference holds about ten of them).
 
-Supported configuration: `match_grad: False`, `cor_detach: True`, `rescale_thr: False` (the shipped
-config); the affinity then carries no gradient and the loss is differentiable only with respect to the
-keypoint log-probabilities.  Other settings raise NotImplementedError.
+The fused path serves `match_grad: False`, `cor_detach: True`, `rescale_thr: False` (the shipped
+config): the affinity then carries no gradient and the loss is differentiable only with respect to the
+keypoint log-probabilities.  The other settings need what the fused kernels never produce -- gradients
+THROUGH the [b,m,n] affinity (`match_grad: True`, `cor_detach: False`) or the mean epipolar distance before
+the rewards (`rescale_thr: True`) -- and take `_forward_dense`: the same mathematics as [b,m,n] tensors with
+autograd (kploss.py:52-129, :158-182), descriptors still from the bilinear sampler kernel (with its backward
+kernel when the affinity carries gradient).  Ablation settings only: at the training shape (b=8, 4800 points)
+this path holds a handful of 737 MB tensors, which is exactly what the fused path avoids.
 """
 from __future__ import annotations
 
@@ -84,10 +89,10 @@ class DiskLoss(nn.Module):
         self.good_reward = configs["good_reward"]
         self.bad_reward = configs["bad_reward"]
         self.kp_penalty = configs["kp_penalty"]
-        if configs.get("match_grad") or not configs.get("cor_detach", True):
-            raise NotImplementedError("match_grad=True / cor_detach=False need gradients through the affinity")
-        if configs["reward_config"].get("rescale_thr"):
-            raise NotImplementedError("rescale_thr=True needs the mean epipolar distance before the rewards")
+        self.match_grad = bool(configs.get("match_grad"))
+        self.cor_detach = bool(configs.get("cor_detach", True))
+        self.rescale_thr = bool(configs["reward_config"].get("rescale_thr"))
+        self.dense = self.match_grad or not self.cor_detach or self.rescale_thr       # see _forward_dense
 
     def name(self):
         return self.__lossname__
@@ -130,6 +135,8 @@ class DiskLoss(nn.Module):
         lp1, lp2 = logp1.reshape(b, -1), logp2.reshape(b, -1)
         a1, a2 = acc1.reshape(b, -1), acc2.reshape(b, -1)
         cos = self.config["loss_distance"] == "cos"
+        if self.dense:
+            return self._forward_dense(inputs, xf1, xf2, coord1, coord2, lp1, lp2, a1, a2, h, w, T, cos)
         with torch.no_grad():
             f1 = sample_feat_by_coord(xf1, normalize_coords(coord1, h, w), cos).contiguous()
             f2 = sample_feat_by_coord(xf2, normalize_coords(coord2, h, w), cos).contiguous()
@@ -160,4 +167,60 @@ class DiskLoss(nn.Module):
                           "cor summin": torch.min(colsum.min(), rowsum.min()), "cor summax": torch.max(colsum.max(), rowsum.max()),
                           "n_kps": (a1.sum(-1, keepdim=True) + a2.sum(-1, keepdim=True)).float().mean(),
                           "n_pairs": psum_b.mean(), "temperature": rowsum.new_tensor(float(T))}
+        return loss, components
+
+    # ---- the settings the fused kernels do not serve: [b,m,n] tensors with autograd ---------------------------
+    def _reward_dense(self, inputs, coord1, coord2):
+        """constant_reward / dynamic_reward incl. rescale_thr (kploss.py:52-129) as [b,m,n] tensors, no gradient."""
+        with torch.no_grad():
+            l1 = _epipolar_lines(inputs["F1"], coord1)                       # [b,m,3]: lines of image-1 points in image 2
+            l2 = _epipolar_lines(inputs["F2"], coord2)                       # [b,n,3]
+            d12 = torch.abs(l1 @ homogenize(coord2).transpose(1, 2))         # [b,m,n] distance of point j to the line of i
+            d21 = torch.abs(l2 @ homogenize(coord1).transpose(1, 2)).transpose(1, 2)
+            thr = self.config["reward_config"]["reward_thr"]
+            if self.rescale_thr:
+                b = d12.shape[0]
+                m1 = d12.reshape(b, -1).mean(1, True)
+                m2 = d21.reshape(b, -1).mean(1, True)
+                low = torch.minimum(m1, m2).clamp(1e-6)
+                scale1, scale2 = m1 / low, m2 / low
+                thr1, thr2 = (thr * scale1).reshape(b, 1, 1), (thr * scale2).reshape(b, 1, 1)
+            else:
+                thr1 = thr2 = thr
+                scale1 = scale2 = d12.new_tensor(1.)
+            if self.dynamic:
+                reward = (torch.exp(-d12 / thr1) + torch.exp(-d21 / thr2) - 2 / torch.exp(torch.ones_like(d12)))
+                reward = reward.clamp(min=self.bad_reward)
+            else:
+                good = (d12 < thr1) & (d21 < thr2)
+                reward = self.good_reward * good + self.bad_reward * (~good)
+        return reward, scale1, scale2
+
+    def _forward_dense(self, inputs, xf1, xf2, coord1, coord2, lp1, lp2, a1, a2, h, w, T, cos):
+        b = xf1.shape[0]
+        with torch.set_grad_enabled(self.match_grad and torch.is_grad_enabled()):
+            f1 = sample_feat_by_coord(xf1, normalize_coords(coord1, h, w), cos)
+            f2 = sample_feat_by_coord(xf2, normalize_coords(coord2, h, w), cos)
+            affinity = -T * (1 - f1 @ f2.transpose(1, 2))                    # [b,m,n]
+        m, n = f1.shape[1], f2.shape[1]
+        logr = torch.log_softmax(affinity, dim=2)                            # Categorical(logits=affinity).logits
+        logc = torch.log_softmax(affinity, dim=1)                            # ... of the transposed affinity, transposed back
+        dense_logp = logr + logc
+        dense_p = torch.exp(dense_logp)                                      # = probs_I * probs_T
+        sample_p = dense_p.detach() if self.cor_detach else dense_p
+        reward, scale1, scale2 = self._reward_dense(inputs, coord1, coord2)
+        accept = (a1[:, :, None] & a2[:, None, :]).to(dense_p.dtype)
+        plogp = sample_p * (dense_logp + lp1[:, :, None] + lp2[:, None, :])
+        reinforce = (reward * plogp * accept).sum()                          # = (reward[mask] * plogp[mask]).sum()
+        kp_penalty = self.kp_penalty * (lp1[a1].sum() + lp2[a2].sum())
+        loss = -reinforce - kp_penalty
+        with torch.no_grad():
+            sp = sample_p.detach()
+            components = {"reinforce": reinforce.detach(), "kp_penalty": kp_penalty.detach(), "scale1": scale1, "scale2": scale2,
+                          "cor minmax": sp.reshape(b, -1).max(-1)[0].min(), "cor minmean": sp.reshape(b, -1).mean(-1).min(),
+                          "cor max": sp.max(), "cor mean": sp.mean(),
+                          "cor summin": torch.min(sp.sum(1).min(), sp.sum(2).min()),
+                          "cor summax": torch.max(sp.sum(1).max(), sp.sum(2).max()),
+                          "n_kps": (a1.sum(-1, keepdim=True) + a2.sum(-1, keepdim=True)).float().mean(),
+                          "n_pairs": sp.sum(-1).sum(-1).mean(), "temperature": sp.new_tensor(float(T))}
         return loss, components

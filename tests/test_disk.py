@@ -98,3 +98,42 @@ def test_disk_loss_vs_oracle_larger():
     np.testing.assert_allclose(-r2[..., 1], g2, rtol=0, atol=3e-4 * np.abs(g2).max())
     assert abs(r1[..., 2].sum() / B - comp["n_pairs"]) <= 3e-4 * comp["n_pairs"]
     assert abs(r1[..., 3].max() - comp["cor max"]) <= 3e-4 * comp["cor max"]
+
+
+OPTS = {"mg": dict(match_grad=True), "mg_cd": dict(match_grad=True, cor_detach=False), "cd": dict(cor_detach=False),
+        "rs": dict(reward_config=dict(reward_thr=2, rescale_thr=True)),
+        "rs_dyn_mg": dict(reward_config=dict(reward_thr=2, rescale_thr=True), epipolar_reward="dynamic_reward", match_grad=True)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(OPTS))
+def test_disk_loss_options_golden(golden, tag):
+    """match_grad / cor_detach / rescale_thr (losses/kploss.py:52-129, :152-182) against the reference's own run:
+    loss, components and the gradients w.r.t. both score maps and both descriptor maps."""
+    from posfeat_b200.kploss import DiskLoss
+    g = golden("disk_opts")
+    c = _case(g, tag)
+    cfg = dict(CFG, **OPTS[tag])
+    t = lambda x: torch.from_numpy(np.asarray(x)).cuda()
+    kp1, kp2 = t(g["kp1"]).requires_grad_(True), t(g["kp2"]).requires_grad_(True)
+    xf1, xf2 = t(g["xf1"]).requires_grad_(True), t(g["xf2"]).requires_grad_(True)
+    co1, co2, a1, a2 = t(g["coord1"]), t(g["coord2"]), t(g["acc1"]), t(g["acc2"])
+    lp1, lp2 = _logp_from_maps(kp1, co1, a1), _logp_from_maps(kp2, co2, a2)
+    inputs = {"F1": t(g["F1"]), "F2": t(g["F2"])}
+    outputs = {"epoch": 0, "preds1": {"local_point": kp1, "local_map": xf1}, "preds2": {"local_point": kp2, "local_map": xf2}}
+    mod = DiskLoss(cfg)
+    assert mod.dense
+    loss, comp = mod(inputs, outputs, None, samples=((co1, lp1, a1), (co2, lp2, a2)))
+    assert abs(float(loss) - float(c["loss"])) <= 2e-4 * abs(float(c["loss"]))
+    for k in COMPS + ["scale1", "scale2"]:
+        want = np.asarray(c["comp/" + k], dtype=np.float64)
+        got = np.asarray(comp[k].detach().cpu().numpy() if torch.is_tensor(comp[k]) else comp[k], dtype=np.float64)
+        np.testing.assert_allclose(got.reshape(want.shape), want, rtol=3e-4, atol=1e-7, err_msg=k)
+    loss.backward()
+    for name, tens in (("g_kp1", kp1), ("g_kp2", kp2), ("g_xf1", xf1), ("g_xf2", xf2)):
+        want = c[name]
+        got = tens.grad.cpu().numpy() if tens.grad is not None else np.zeros_like(want)
+        scale = max(np.abs(want).max(), 1e-12)
+        assert np.abs(got - want).max() <= 5e-4 * scale, (name, np.abs(got - want).max(), scale)
+    if "mg" in tag:
+        assert np.abs(c["g_xf1"]).max() > 0          # the descriptor maps do receive gradient with match_grad

@@ -24,7 +24,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --passes 2 --no-cpu --no-eager --no-extras > $OUT/${TAG}_ncu_launch_list.log 2>&1
 # full capture of one device-resident pass of the pair pipeline (8 pairs): every kernel of the hot path
 python tools/prof_pipeline.py 8 2 > $OUT/${TAG}_ncu_plain_pipe.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --launch-skip 9 --launch-count 9 -f -o $OUT/${TAG}_pipe_P8 \
+ncu --set full --clock-control none --import-source on -k 'regex:mnn_tc_kernel|tc_rescore|tc_verify|tc_compact|nms_quad|select_kernel|keypoint_outputs|sample_nhwc' \
+    --launch-skip 8 --launch-count 8 -f -o $OUT/${TAG}_pipe_P8 \
     python tools/prof_pipeline.py 8 2 > $OUT/${TAG}_ncu_full_pipe.log 2>&1
 # the training-side kernels (C4 shapes)
 python tools/prof_corr.py > $OUT/${TAG}_ncu_plain_corr.log 2>&1 &&
