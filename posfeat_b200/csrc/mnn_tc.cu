@@ -974,27 +974,22 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   const DirParams& d = a.d;
   if (c >= a.nchunks) return;
   const size_t slot = (size_t)pair * a.nchunks + c;
-  int total;
-  const int* rows;
-  if (kG8) {
-    const uint4* g = reinterpret_cast<const uint4*>(a.g8 + ((size_t)pair * d.pitch + c) * a.groups);
-    const int nvec = a.groups >> 2;                               // groups is a multiple of 32
-    // the first block of group entries is requested together with the threshold (almost every chunk has members):
-    // one memory round trip less on this kernel's dependent chain
-    uint4 e[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int v = q * 32 + lane;
-      e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    const int o = a.tmin[slot];
-    if (o == 0x7f7f7f7f) return;                                  // no row has its nearest neighbour in this chunk
-    const __half2 thr2 = __float2half2_rn(__half2float(__float2half_rd(ordered_int_to_float(o))));
-    int* myrows = &s_rows[warp * kCompCap];
-    unsigned short* myent = &s_ent[warp * kCompCap];
+  int total = 0;
+  const int* rows = nullptr;
+  const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
+  int* myrows = &s_rows[kG8 ? warp * kCompCap : 0];
+  unsigned short* myent = &s_ent[kG8 ? warp * kCompCap : 0];
+  const uint4* g = kG8 ? reinterpret_cast<const uint4*>(a.g8 + ((size_t)pair * d.pitch + c) * a.groups) : nullptr;
+  const int nvec = kG8 ? a.groups >> 2 : 0;                       // groups is a multiple of 32
+  // Competitor list of the chunk from its row of group entries: a group whose max1 reaches thr contributes its leader
+  // row, or all 8 rows when max2 reaches it too.  Every lane appends the rows of its own hot groups (a warp scan of the
+  // per-lane counts gives the slots).  mode 0: all rows; 1: only members (rows whose nearest neighbour lies in this
+  // chunk); 2: only non-members.  e0 holds the first block of entries when it was requested ahead.  Returns the
+  // number of rows (which may exceed the capacity: the caller then narrows the request).
+  auto build = [&](const __half2 thr2, const int mode, uint4 (&e)[4], bool have_first) -> int {
     int n = 0;
     for (int v0 = 0; v0 < nvec; v0 += 128) {
-      if (v0 > 0) {
+      if (v0 > 0 || !have_first) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int v = v0 + q * 32 + lane;
@@ -1012,16 +1007,25 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
                  ((m0 >> 16) & 1u) << 4 | ((m1 >> 16) & 1u) << 5 | ((m2 >> 16) & 1u) << 6 | ((m3 >> 16) & 1u) << 7 |
                  (e[q].x & 7u) << 8 | (e[q].y & 7u) << 11 | (e[q].z & 7u) << 14 | (e[q].w & 7u) << 17;
         if (!__any_sync(0xffffffffu, info != 0)) continue;
-        // every lane appends the rows of its own hot groups: a warp scan of the per-lane row counts gives the slots
         const int g0 = (v0 + q * 32 + lane) * 4;
-        int cnt = 0;
+        // bit 8k+j of `take`: row j of this lane's hot group k goes onto the list
+        unsigned take = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if ((info >> k) & 1u) {
-            const int r0 = (g0 + k) * 8;
-            cnt += ((info >> (4 + k)) & 1u) ? max(0, min(8, d.NX - r0)) : (r0 + (int)((info >> (8 + 3 * k)) & 7u) < d.NX ? 1 : 0);
+          if (!((info >> k) & 1u)) continue;
+          const int r0 = (g0 + k) * 8;
+          unsigned bits = ((info >> (4 + k)) & 1u) ? 0xffu : (1u << ((info >> (8 + 3 * k)) & 7u));
+          if (r0 + 8 > d.NX) bits &= r0 < d.NX ? (1u << (d.NX - r0)) - 1u : 0u;
+          if (mode != 0) {
+            for (unsigned bb = bits; bb; bb &= bb - 1) {
+              const int j = __ffs(bb) - 1;
+              const bool mem = (__ldg(nn + r0 + j) >> 3) == c;
+              if (mem != (mode == 1)) bits &= ~(1u << j);
+            }
           }
+          take |= bits << (8 * k);
         }
+        const int cnt = __popc(take);
         int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1030,35 +1034,39 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
         }
         int pos = n + inc - cnt;
         n += __shfl_sync(0xffffffffu, inc, 31);
-        if (cnt) {
-          const unsigned ew[4] = {e[q].x, e[q].y, e[q].z, e[q].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (!((info >> k) & 1u)) continue;
-            const int r0 = (g0 + k) * 8;
-            const unsigned short ent = (unsigned short)(ew[k] & 0xffffu);        // max1: bounds every row of the group
-            if ((info >> (4 + k)) & 1u) {                                        // two or more rows of the group matter: all 8
-              for (int j = 0; j < 8 && r0 + j < d.NX; ++j, ++pos)
-                if (pos < kCompCap) { myrows[pos] = r0 + j; myent[pos] = ent; }
-            } else {
-              const int r = r0 + (int)((info >> (8 + 3 * k)) & 7u);
-              if (r < d.NX) {
-                if (pos < kCompCap) { myrows[pos] = r; myent[pos] = ent; }
-                ++pos;
-              }
-            }
+        const unsigned ew[4] = {e[q].x, e[q].y, e[q].z, e[q].w};
+        for (unsigned tk = take; tk; tk &= tk - 1, ++pos) {
+          const int bit = __ffs(tk) - 1;
+          if (pos < kCompCap) {
+            myrows[pos] = (g0 + (bit >> 3)) * 8 + (bit & 7);
+            myent[pos] = (unsigned short)(ew[bit >> 3] & 0xffffu);          // max1: bounds every row of the group
           }
         }
       }
     }
     __syncwarp();
-    total = n;
+    return n;
+  };
+  __half2 thr_chunk = __float2half2_rn(0.f);
+  if (kG8) {
+    // the first block of group entries is requested together with the threshold (almost every chunk has members):
+    // one memory round trip less on this kernel's dependent chain
+    uint4 e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = q * 32 + lane;
+      e[q] = v < nvec ? __ldg(g + v) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int o = a.tmin[slot];
+    if (o == 0x7f7f7f7f) return;                                  // no row has its nearest neighbour in this chunk
+    thr_chunk = __float2half2_rn(__half2float(__float2half_rd(ordered_int_to_float(o))));
+    total = build(thr_chunk, 0, e, true);
     rows = myrows;
     if (a.dbg && lane == 0) {
       atomicAdd(a.dbg + 4, 1ull);
-      atomicAdd(a.dbg + 5, (unsigned long long)n);
-      atomicAdd(a.dbg + 6, n > kCompCap ? 1ull : 0ull);
-      atomicAdd(a.dbg + 7, n > 32 ? 1ull : 0ull);
+      atomicAdd(a.dbg + 5, (unsigned long long)total);
+      atomicAdd(a.dbg + 6, total > kCompCap ? 1ull : 0ull);
+      atomicAdd(a.dbg + 7, total > 32 ? 1ull : 0ull);
     }
     if (total == 0) return;
   } else {
@@ -1068,7 +1076,6 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   }
   const float* Xp = a.X + pair * a.strideX;
   const float* Yp = a.Y + pair * a.strideY;
-  const int32_t* nn = a.nn12 + (size_t)pair * d.NX;
   const float4* yv = &s_y[warp][0];
   const bool vec_x = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(Xp) & 15) == 0;   // 128-bit row loads
   const bool vec_y = (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Yp) & 15) == 0;
@@ -1106,6 +1113,16 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     }
   };
 
+  // a list over capacity (descriptors of neighbouring keypoints are correlated enough on real maps to put a few hundred
+  // rows above a weak member's threshold now and then) is narrowed instead of dropping the chunk into the exhaustive
+  // fallback (30 ms for one warp): first only the members are listed, and after they have been settled among
+  // themselves only the non-members that reach a SURVIVING member's threshold
+  bool narrowed = false;
+  if (kG8 && total > kCompCap) {
+    uint4 e[4];
+    total = build(thr_chunk, 1, e, false);
+    narrowed = true;
+  }
   if (kG8 && total <= kCompCap) {
     // Member-centric form.  Members (rows whose nearest neighbour lies in this chunk) are first settled among
     // themselves from the 8 values the rescoring kernel left for each of them -- in a well-matched pair a weak
@@ -1159,15 +1176,21 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, o));
+      bool give_up = false;
       if (tl < INFINITY) {
+        if (narrowed) {            // the list held the members only: now the non-members that can still matter
+          uint4 e[4];
+          total = build(__float2half2_rn(__half2float(__float2half_rd(tl))), 2, e, false);
+          give_up = total > kCompCap;
+        }
         bool staged = false;
-        for (int q0 = 0; q0 < total; q0 += 32) {
+        for (int q0 = 0; !give_up && q0 < total; q0 += 32) {
           const int q = q0 + lane;
           const int ir_l = q < total ? rows[q] : -1;
           bool need = false;
           if (ir_l >= 0) {
             const float e = __half2float(__ushort_as_half(ents[q]));
-            need = e >= tl && (__ldg(nn + ir_l) >> 3) != c;
+            need = e >= tl && (narrowed || (__ldg(nn + ir_l) >> 3) != c);
           }
           unsigned todo = __ballot_sync(0xffffffffu, need);
           if (todo && !staged) { stage_y(); staged = true; }
@@ -1182,8 +1205,13 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
           }
         }
       }
+      if (give_up) total = kCompCap + 1;      // still too many: the exhaustive path below decides everything anew
+      else {
       if (member && lost) a.mutual[(size_t)pair * d.NX + iq] = 0;
       return;
+      }
+    } else if (narrowed) {
+      total = kCompCap + 1;                    // more than 32 members and a list over capacity: exhaustive path
     }
     // more than 32 members (many rows share a nearest neighbour): the general paths below
   }
