@@ -345,7 +345,16 @@ def workload_mnn_sweep(dev, sizes=(1024, 4096, 16384, 65536)):
         ker = kernel_times(lambda: mnn_match(a, b, algo=2, want_nn21=False), iters)
         flops = 2.0 * n * n * 128
         tc = ker.get("mnn_tc")
-        rows.append({"N": n, "us_per_call": 1e3 * ms, "frac_of_bf16_peak_whole_call": flops / (ms * 1e-3) / 1e12 / pk["bf16"],
+        graph_us = None
+        if n <= 16384:                         # launch-bound sizes: the same call replayed as one CUDA graph
+            from posfeat_b200.matchers import GraphedMatcher
+            gm = GraphedMatcher(n, n, 128, algo=2, device=dev)
+            gm.a.copy_(a); gm.b.copy_(b)
+            gms, _ = cuda_time(gm.graph.replay, iters, warmup=2)
+            assert torch.equal(gm.matches[:int(gm.nm.item())], m[:int(nm.item())])
+            graph_us = 1e3 * gms
+            del gm
+        rows.append({"N": n, "us_per_call": 1e3 * ms, "cuda_graph_us_per_call": graph_us, "frac_of_bf16_peak_whole_call": flops / (ms * 1e-3) / 1e12 / pk["bf16"],
                      "tc_kernel_us": 1e3 * tc if tc else None,
                      "tc_kernel_frac_of_bf16_peak": flops / (tc * 1e-3) / 1e12 / pk["bf16"] if tc else None,
                      "kernel_us": {k: round(1e3 * v, 1) for k, v in ker.items()}, "matches": int(nm.item())})

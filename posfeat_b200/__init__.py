@@ -24,7 +24,8 @@ _LAZY = {
     "DiskLoss": "kploss", "EpipolarLoss_full": "epipolarloss", "GradAllReducer": "dist",
     "process": "extractor", "save_desc": "extractor", "FeatureExtractor": "extractor",
     "AsyncDescWriter": "extractor", "generate_kpts_single_noavg": "preprocess_utils",
-    "ratio_matcher": "matchers", "mutual_nn_ratio_matcher": "matchers",
+    "ratio_matcher": "matchers", "mutual_nn_ratio_matcher": "matchers", "GraphedMatcher": "matchers",
+    "PairPipeline": "pairs", "GraphedPairPipeline": "pairs",
 }
 
 

@@ -2,11 +2,14 @@
 device memory, streams and workspace caching."""
 from __future__ import annotations
 
+import threading
+
 import torch
 
 from . import _lib
 
 _workspaces = {}
+_scope = threading.local()
 lib = _lib.load
 check = _lib.check
 
@@ -35,7 +38,7 @@ def workspace(key: str, nbytes: int, device) -> torch.Tensor:
     and therefore see the same buffer."""
     d = torch.device(device)
     idx = d.index if d.index is not None else torch.cuda.current_device()
-    k = (key, idx, torch.cuda.current_stream(idx).cuda_stream)
+    k = (key, idx, torch.cuda.current_stream(idx).cuda_stream, getattr(_scope, "token", None))
     buf = _workspaces.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=d)
@@ -43,9 +46,41 @@ def workspace(key: str, nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+class workspace_scope:
+    """Scratch buffers private to one owner: inside the ``with`` block ``workspace()`` hands out buffers no other
+    caller sees.  A captured CUDA graph bakes the addresses of its scratch memory in, so every graph object captures
+    inside its own scope and keeps the scope alive (``close()`` releases the buffers) -- the shared grow-only cache
+    may replace a buffer at any later call."""
+
+    def __init__(self):
+        self.token = object()
+        self._prev = None
+
+    def __enter__(self):
+        self._prev = getattr(_scope, "token", None)
+        _scope.token = self.token
+        return self
+
+    def __exit__(self, *exc):
+        _scope.token = self._prev
+        return False
+
+    def close(self):
+        for k in [k for k in _workspaces if k[3] is self.token]:
+            del _workspaces[k]
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def release_workspaces():
-    """Drop every cached scratch buffer (e.g. after a one-off very large call)."""
-    _workspaces.clear()
+    """Drop every cached scratch buffer of the shared cache (e.g. after a one-off very large call); buffers that
+    belong to a live ``workspace_scope`` (a captured graph) stay."""
+    for k in [k for k in _workspaces if k[3] is None]:
+        del _workspaces[k]
 
 
 def stream_ptr(device=None) -> int:

@@ -1345,6 +1345,7 @@ struct RescoreListArgs {
   unsigned char* mutual;                  // [pairs][NX], set to 1 here
   int nchunks;
   unsigned long long* dbg;                // POSFEAT_MNN_DEBUG counters (NULL otherwise)
+  int mode;                               // bring-up timing (POSFEAT_TC_DEBUG bits 0x4000 / 0x8000), 0 otherwise
 };
 
 constexpr int kRlWarps = 2;
@@ -1565,6 +1566,247 @@ tc_rescore_lists_kernel(const RescoreListArgs a) {
   const int row = blockIdx.x * kRlWarps + w;
   if (row >= a.d.NX) return;
   rescore_row_lists(a, blockIdx.y, row, xs, w, lane);
+}
+
+// The same rescoring with the per-row control flow moved from a warp onto a LANE.  In the kernel above a row costs
+// ~420 warp instructions of which ~100 are the eight dot products: the rest is list walking, thresholds and outputs
+// executed by 32 lanes for one row (ncu: 57 % issue utilisation at the 32 warps per SM the registers allow -- the
+// kernel is bound by its own instruction count).  Here a warp owns 32 consecutive rows:
+//   A  lane = row: F = max of the lines' running maxima (slot 0), threshold, walk of the row's list entries (one
+//      32-byte sector = 4 slots per step); the candidate chunks go into a per-warp queue in shared memory;
+//   B  four queue entries at a time, eight lanes each: lane t of a group holds 16 of the 128 dimensions, 8 x 16 FMAs,
+//      a 7-shuffle transposing reduction leaves column t of the chunk on lane t; the group posts (maximum, winner,
+//      "two columns within the float32 band") and the owner lane of the row merges the posts in queue order;
+//   C  lane = row: nn12, the chunk threshold (atomicMin) and the mutual flag, coalesced.
+// Rows that need anything else -- an overflowed list, a queue over capacity, two columns within the float32 error
+// band (exact pass) -- are handed to rescore_row_lists unchanged (one row in several hundred).
+constexpr int kRqWarps = 4;
+constexpr int kRqCap = 6;               // queue slots per row
+constexpr int kRqGroups = 4;            // queue entries in flight per warp (8 lanes each)
+
+__device__ __noinline__ void rescore_row_lists_slow(const RescoreListArgs& a, const int pair, const int row,
+                                                    float (&xs)[kRlWarps][kD], const int lane) {
+  rescore_row_lists(a, pair, row, xs, 0, lane);
+}
+
+__global__ void __launch_bounds__(kRqWarps * 32, 5)
+tc_rescore_lists_rows_kernel(const RescoreListArgs a) {
+  __shared__ int s_cand[kRqWarps][kRqCap][32];
+  __shared__ int s_qc[kRqWarps][32 * kRqCap];               // flat queue: chunk ...
+  __shared__ unsigned char s_qo[kRqWarps][32 * kRqCap];     // ... and owner lane
+  __shared__ int s_po[kRqWarps][kRqGroups], s_pcol[kRqWarps][kRqGroups], s_pmulti[kRqWarps][kRqGroups];
+  __shared__ float s_pcm[kRqWarps][kRqGroups];
+  __shared__ __align__(16) float s_p8[kRqWarps][kRqGroups][kChunk];
+  __shared__ __align__(16) float s_x[kRqWarps][kRlWarps][kD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const DirParams& d = a.d;
+  const int row0 = (blockIdx.x * kRqWarps + w) * 32;
+  if (row0 >= d.NX) return;
+  const int row = row0 + lane;
+  const bool live = row < d.NX;
+  const size_t prow = (size_t)pair * d.NXpad + (live ? row : row0);
+  const int nlines = 4 * d.splits;
+  const uint2* lines = a.lists + prow * nlines * kListSlots;
+  const MatStats ys = d.ystats[2 * pair], xst = d.xstats[2 * pair];
+  const float ymax = __uint_as_float(ys.max_norm);
+  const float xn = d.xnorm[prow];
+  const float delta = 2.f * (d.xerr[prow] * __uint_as_float(ys.max_norm_bf) + xn * __uint_as_float(ys.max_err) +
+                             kAccSlack * xn * ymax);
+  const float band = 2.f * kEps32 * xn * ymax;
+
+  // ---- A: threshold and candidate queue of this lane's row
+  float F = -INFINITY;
+  bool slow = false;
+  int entries = 0;
+  for (int l = 0; l < nlines; ++l) {
+    const uint2 h = __ldg(lines + l * kListSlots);
+    slow |= (int)h.x >= kListSlots;                       // the list overflowed
+    entries += (int)h.x;
+    if ((int)h.x > 0) F = fmaxf(F, __uint_as_float(h.y));
+  }
+  const float thr = F - delta;
+  int ncand = 0;
+  if (live && !slow) {
+    // an entry names a tile quarter (8 chunks from chunk0) and the chunks of it that were within delta
+    auto consider = [&](unsigned ex, unsigned ey) {
+      if (__uint_as_float(ey) >= thr) {
+        for (unsigned mk = ex >> 24; mk; mk &= mk - 1) {
+          if (ncand < kRqCap) s_cand[w][ncand][lane] = (int)((ex & 0xffffffu) + __ffs(mk) - 1);
+          ++ncand;
+        }
+      }
+    };
+    for (int l = 0; l < nlines; ++l) {
+      const uint4* lp = reinterpret_cast<const uint4*>(lines + l * kListSlots);
+      uint4 v0 = __ldg(lp), v1 = __ldg(lp + 1);           // slots 0 (header), 1 | 2, 3: one sector
+      const int cnt = (int)v0.x;
+      if (cnt >= 1) consider(v0.z, v0.w);
+      if (cnt >= 2) consider(v1.x, v1.y);
+      if (cnt >= 3) consider(v1.z, v1.w);
+      for (int base = 4; base <= cnt; base += 4) {
+        v0 = __ldg(lp + (base >> 1)); v1 = __ldg(lp + (base >> 1) + 1);
+        consider(v0.x, v0.y);
+        if (cnt >= base + 1) consider(v0.z, v0.w);
+        if (cnt >= base + 2) consider(v1.x, v1.y);
+        if (cnt >= base + 3) consider(v1.z, v1.w);
+      }
+    }
+    slow = ncand > kRqCap;
+  }
+  if (!live) { slow = false; ncand = 0; }
+  // flat queue in row order
+  const int mine = slow ? 0 : ncand;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  for (int k = 0; k < mine; ++k) {
+    s_qc[w][incl - mine + k] = s_cand[w][k][lane];
+    s_qo[w][incl - mine + k] = (unsigned char)lane;
+  }
+  __syncwarp();
+
+  // ---- B: the queued (row, chunk) pairs, kRqGroups at a time
+  float m32 = -INFINITY;
+  int besti = 0x7fffffff;
+  bool amb = false;
+  {
+    const float* __restrict__ Y = a.Y + pair * a.strideY;
+    const int ld4 = (int)(a.ldy >> 2), ldx4 = (int)(a.ldx >> 2);     // the host selects this kernel only for aligned operands
+    const int t = lane & 7, gi = lane >> 3;
+    const float4* y4 = reinterpret_cast<const float4*>(Y) + t;
+    const float4* x4 = reinterpret_cast<const float4*>(a.X + pair * a.strideX) + t;
+    const int NY = d.NY;
+    const int niter = (a.mode & 0x8000) ? 0 : (total + kRqGroups - 1) / kRqGroups;
+    for (int it = 0; it < niter; ++it) {
+      const int idx = it * kRqGroups + gi;
+      const bool act = idx < total;
+      const int idc = act ? idx : total - 1;
+      const int o = s_qo[w][idc];
+      const int col0 = s_qc[w][idc] * kChunk;
+      float4 xv[4];
+      const float4* xp = x4 + (size_t)(unsigned)(row0 + o) * (size_t)ldx4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = __ldg(xp + 8 * i);
+      const float4* yp = y4 + (size_t)(unsigned)col0 * (size_t)ld4;
+      const int rlast = NY - 1 - col0;                     // rows past the end are clamped: masked below
+      float pr[kChunk];
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) {
+        const float4* yr = yp + min(r, rlast) * ld4;
+        float4 yv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yv[i] = __ldg(yr + 8 * i);
+        float acc = xv[0].x * yv[0].x;
+        acc = fmaf(xv[0].y, yv[0].y, acc); acc = fmaf(xv[0].z, yv[0].z, acc); acc = fmaf(xv[0].w, yv[0].w, acc);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+          acc = fmaf(xv[i].x, yv[i].x, acc); acc = fmaf(xv[i].y, yv[i].y, acc);
+          acc = fmaf(xv[i].z, yv[i].z, acc); acc = fmaf(xv[i].w, yv[i].w, acc);
+        }
+        pr[r] = acc;
+      }
+      float q4[4], q2[2], sc;
+      {
+        const bool hi = t & 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float got = __shfl_xor_sync(0xffffffffu, hi ? pr[r] : pr[r + 4], 4);
+          q4[r] = (hi ? pr[r + 4] : pr[r]) + got;
+        }
+      }
+      {
+        const bool hi = t & 2;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float got = __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 2);
+          q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
+        }
+      }
+      {
+        const bool hi = t & 1;
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 1);
+        sc = (hi ? q2[1] : q2[0]) + got;                  // lane t: column col0 + t
+      }
+      if (col0 + t >= NY) sc = -INFINITY;
+      float cm = sc;
+#pragma unroll
+      for (int sh = 4; sh >= 1; sh >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, sh));
+      const float band_o = __shfl_sync(0xffffffffu, band, o);
+      const unsigned near = (__ballot_sync(0xffffffffu, sc >= cm - band_o) >> (lane & 24)) & 0xffu;
+      const unsigned at = (__ballot_sync(0xffffffffu, sc == cm) >> (lane & 24)) & 0xffu;
+      s_p8[w][gi][t] = sc;
+      if (t == 0) {
+        s_po[w][gi] = act ? o : -1;
+        s_pcm[w][gi] = cm;
+        s_pcol[w][gi] = col0 + __ffs(at) - 1;
+        s_pmulti[w][gi] = (near & (near - 1)) != 0;
+      }
+      __syncwarp();
+      // the owner merges the posts of its row in queue order (two entries of one row may be in flight together)
+#pragma unroll
+      for (int g2 = 0; g2 < kRqGroups; ++g2) {
+        if (s_po[w][g2] == lane) {
+          const float c2 = s_pcm[w][g2];
+          amb |= s_pmulti[w][g2] != 0 || (c2 <= m32 ? c2 >= m32 - band : m32 >= c2 - band);
+          if (c2 > m32) {
+            m32 = c2;
+            besti = s_pcol[w][g2];
+            float4* dst = reinterpret_cast<float4*>(a.best8 + ((size_t)pair * d.NX + row) * kChunk);
+            dst[0] = *reinterpret_cast<const float4*>(&s_p8[w][g2][0]);
+            dst[1] = *reinterpret_cast<const float4*>(&s_p8[w][g2][4]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  slow |= amb;                         // two columns within the float32 error band: the exact pass decides
+
+  // ---- C: outputs of the rows settled by the float32 pass
+  if (live && !slow) {
+    const size_t rowg = (size_t)pair * d.NX + row;
+    const int bj = besti == 0x7fffffff ? 0 : besti;
+    if (besti == 0x7fffffff) {          // no candidate at all (cannot happen with a well-formed list): defined outputs
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) a.best8[rowg * kChunk + c] = 0.f;
+    }
+    a.nn[rowg] = bj;
+    const float xmax = __uint_as_float(xst.max_norm);
+    const float eps_max = __uint_as_float(xst.max_err) * __uint_as_float(ys.max_norm_bf) + xmax * __uint_as_float(ys.max_err) +
+                          kAccSlack * xmax * ymax;
+    const float mm = xmax * ymax;
+    const float scale = mm > 0.f ? 1.f / mm : 1.f;
+    const float vlow = m32 - 0.5f * band;
+    float thr_v = (vlow - eps_max) * scale - 1e-6f;
+    if (thr_v > 0.f) thr_v *= kG8Slack;
+    atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
+    a.mutual[rowg] = 1;
+  }
+  if (a.dbg) {
+    const bool fast = live && !slow;
+    const int nrows = __popc(__ballot_sync(0xffffffffu, fast));
+    const int nc = (int)warp_sum(fast ? (float)ncand : 0.f), ne = (int)warp_sum(fast ? (float)entries : 0.f);
+    const int nslow = __popc(__ballot_sync(0xffffffffu, slow));
+    if (lane == 0) {
+      atomicAdd(a.dbg + 0, (unsigned long long)nrows);
+      atomicAdd(a.dbg + 2, (unsigned long long)nc);
+      atomicAdd(a.dbg + 3, (unsigned long long)ne);
+      atomicAdd(a.dbg + 9, (unsigned long long)nslow);
+    }
+  }
+  // ---- everything else: the general per-row routine
+  unsigned rest = __ballot_sync(0xffffffffu, slow);
+  while (rest) {
+    const int o = __ffs(rest) - 1;
+    rest &= rest - 1;
+    __syncwarp();
+    rescore_row_lists_slow(a, pair, row0 + o, s_x[w], lane);
+  }
 }
 
 // ordered compaction of the rows flagged mutual (ascending i), one CTA per pair
@@ -1842,11 +2084,19 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     const bool dbg_on = getenv("POSFEAT_MNN_DEBUG") != nullptr;
     if (dbg_on) PF_CUDA(cudaMemsetAsync(w.dbg, 0, sizeof(unsigned long long) * 16, stream));
     RescoreListArgs ra{p.d[0], w.lists, A, lda, strideA, Bm, ldb, strideB, nn12, w.best8, w.tmin, w.mutual, nchunks,
-                       dbg_on ? w.dbg : nullptr};
+                       dbg_on ? w.dbg : nullptr, p.debug & 0xc000};
     prof_begin(PROF_MNN_RESCORE, stream);
-    tc_rescore_lists_kernel<<<dim3((unsigned)((N + kRlWarps - 1) / kRlWarps), (unsigned)P), kRlWarps * 32, 0, stream>>>(ra);
+    static const bool rows_env = getenv("POSFEAT_MNN_RESCORE_WARP") == nullptr;      // A/B switch: the warp-per-row kernel
+    // the row-group kernel reads 16-byte vectors: operands that are not aligned for them take the warp-per-row kernel
+    const bool rows_form = rows_env && lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 &&
+                           (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0 && lda < (1ll << 31) && ldb < (1ll << 31);
+    if (rows_form)
+      tc_rescore_lists_rows_kernel<<<dim3((unsigned)((N + kRqWarps * 32 - 1) / (kRqWarps * 32)), (unsigned)P), kRqWarps * 32, 0, stream>>>(ra);
+    else
+      tc_rescore_lists_kernel<<<dim3((unsigned)((N + kRlWarps - 1) / kRlWarps), (unsigned)P), kRlWarps * 32, 0, stream>>>(ra);
     prof_end(PROF_MNN_RESCORE, stream);
     PF_LAUNCH_CHECK("tc_rescore_lists_kernel");
+    if (p.debug & 0x2000) return POSFEAT_OK;   // bring-up timing: stop after the rescoring kernel (no results)
     VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, nullptr, nullptr, w.best8, w.mutual, nchunks, w.tmin, w.g8, Np / 8,
                   dbg_on ? w.dbg : nullptr};
     prof_begin(PROF_MNN_VERIFY, stream);
@@ -1858,11 +2108,11 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     prof_end(PROF_MNN_COMPACT, stream);
     PF_LAUNCH_CHECK("tc_compact_flags_kernel");
     if (dbg_on) {   // diagnostics only: synchronises
-      unsigned long long h[9];
+      unsigned long long h[10];
       PF_CUDA(cudaMemcpyAsync(h, w.dbg, sizeof(h), cudaMemcpyDeviceToHost, stream));
       PF_CUDA(cudaStreamSynchronize(stream));
-      fprintf(stderr, "posfeat mnn lists: P=%d N=%d M=%d splits=%d | rows %llu overflow %llu exact-pass %llu candidates %llu list-entries %llu | "
-                      "chunks %llu competitors %llu overflow-chunks %llu long-chunks(>32) %llu\n", P, N, M, s0, h[0], h[1], h[8],
+      fprintf(stderr, "posfeat mnn lists: P=%d N=%d M=%d splits=%d | rows %llu overflow %llu exact-pass %llu general-path %llu candidates %llu list-entries %llu | "
+                      "chunks %llu competitors %llu overflow-chunks %llu long-chunks(>32) %llu\n", P, N, M, s0, h[0], h[1], h[8], h[9],
               h[2], h[3], h[4], h[5], h[6], h[7]);
     }
     return POSFEAT_OK;

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace
+from ._runtime import check, lib, map_ptr, require_cuda, stream_ptr, workspace, workspace_scope
 from .preprocess_utils import MIN_PTS, denormalize_coords, detect_finish, detect_topk, sample_l2norm
 
 
@@ -368,14 +368,16 @@ class GraphedPairPipeline:
         self.score[..., ::2, ::2] = 2.0                      # a map with plenty of local maxima for the warm-up runs
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):                                # warm-up on the capture stream: workspaces, caches, attributes
-                pipe.run_nosync(self.score, self.fmap)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
-            self.rec, self.feats, self.matches, self.nm = pipe.run_nosync(self.score, self.fmap)
+        self._scratch = workspace_scope()                     # the graph's scratch memory is its own while it lives
+        with self._scratch:
+            with torch.cuda.stream(side):
+                for _ in range(2):                            # warm-up on the capture stream: workspaces, caches, attributes
+                    pipe.run_nosync(self.score, self.fmap)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.rec, self.feats, self.matches, self.nm = pipe.run_nosync(self.score, self.fmap)
         self.cap = self.rec["cap"]
 
     def __call__(self, score: torch.Tensor, fmap: torch.Tensor):

@@ -151,6 +151,59 @@ def test_mnn_list_overflow_and_duplicates():
     assert assert_matches_exact(v, -v, m[:int(k)].cpu().numpy(), want, rg, cg) == 0
 
 
+def test_mnn_competitor_list_over_capacity(monkeypatch, capfd):
+    """Column chunks whose competitor list exceeds the verification kernel's capacity (256 rows): the list is
+    narrowed -- members first, then only the non-members that reach a surviving member's threshold -- and only a
+    list that is still too long, or more than 32 members, takes the exhaustive path.  Four constructed columns:
+      c0    a weak (0.8) and a strong (0.99) member + 400 rows at 0.85 that prefer their own columns: strong member wins
+      c2000 as c0 plus one non-member at 0.995 (above the strong member) that prefers its own column:
+            the column's nearest row is not a member -> no match for the column
+      c4000 one member at 0.8 + 400 non-members at 0.85 (narrowed list still over capacity -> exhaustive): no match
+      c6000 40 members at 0.90..0.939 + 300 non-members at 0.92 (over 32 members): the best member wins."""
+    import posfeat_b200 as P
+    g = torch.Generator().manual_seed(77)
+    D, M = 128, 8192
+    cols = torch.nn.functional.normalize(torch.randn(M, D, generator=g), dim=1)
+
+    def at(y, p, n):                     # n unit rows with similarity p to the unit vector y
+        u = torch.randn(n, D, generator=g)
+        u = torch.nn.functional.normalize(u - (u @ y)[:, None] * y[None], dim=1)
+        return p * y[None] + (1 - p * p) ** 0.5 * u
+
+    special = {0, 2000 // 8, 4000 // 8, 6000 // 8}
+    rows, free = [], iter(j for j in range(100, M, 5) if j // 8 not in special)      # columns for rows that prefer "their own"
+
+    def with_own_columns(r):
+        for x in r:
+            cols[next(free)] = torch.nn.functional.normalize(x + 0.003 * torch.randn(D, generator=g), dim=0)
+        rows.append(r)
+
+    for c in (0, 2000):
+        rows.append(at(cols[c], 0.8, 1)); rows.append(at(cols[c], 0.99, 1))
+        with_own_columns(at(cols[c], 0.85, 400))
+    with_own_columns(at(cols[2000], 0.995, 1))
+    rows.append(at(cols[4000], 0.8, 1)); with_own_columns(at(cols[4000], 0.85, 400))
+    rows.append(torch.cat([at(cols[6000], 0.90 + 0.001 * k, 1) for k in range(40)]))
+    with_own_columns(at(cols[6000], 0.92, 300))
+    rows.append(torch.nn.functional.normalize(torch.randn(1000, D, generator=g), dim=1))      # background
+    a = torch.cat(rows)
+    a = a[torch.randperm(a.shape[0], generator=g)].contiguous()
+    want, nn12, nn21, rg, cg = O.mnn_blocked_f64(a.numpy(), cols.numpy())
+    monkeypatch.setenv("POSFEAT_MNN_DEBUG", "1")
+    capfd.readouterr()
+    m, k, n12, _ = P.mnn_match(a.cuda(), cols.cuda(), algo=2, want_nn21=False)
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    monkeypatch.delenv("POSFEAT_MNN_DEBUG")
+    assert "overflow-chunks" in err and int(err.split("overflow-chunks")[1].split()[0]) >= 4, err
+    assert check_argmax_exact(a.numpy(), cols.numpy(), n12.cpu().numpy(), nn12) == 0
+    got = m[:int(k)].cpu().numpy()
+    assert assert_matches_exact(a, cols, got, want, rg, cg) == 0
+    matched_cols = set(got[:, 1].tolist())
+    assert 0 in matched_cols and 6000 in matched_cols and 2000 not in matched_cols and 4000 not in matched_cols
+    assert [(nn12 == c).sum() for c in (0, 2000, 4000, 6000)] == [2, 2, 1, 40]          # the construction holds
+
+
 def _pipeline_case(H, W, cfg, seed, P=1):
     g = torch.Generator().manual_seed(seed)
     score = torch.nn.functional.softplus(torch.randn(2 * P, 1, H, W, generator=g))

@@ -334,3 +334,20 @@ def test_graphed_pipeline_equals_plain_call():
     fb, mb, nb = g(sparse.cuda(), f_cl)
     assert fa["n"] < 1500 and fb["n"] == fa["n"]
     assert torch.equal(fa["idx"], fb["idx"]) and torch.equal(na, nb)
+
+
+def test_graphed_matcher_equals_plain_call():
+    """GraphedMatcher (the five launches of a matches-only call replayed as one CUDA graph) returns mnn_matcher's
+    list, call after call with different descriptors, for device and host inputs; a wrong shape is refused."""
+    import posfeat_b200 as P
+    gm = P.GraphedMatcher(1500, 1300)
+    for seed in (1, 2, 3):
+        g = torch.Generator().manual_seed(seed)
+        a = torch.nn.functional.normalize(torch.randn(1500, 128, generator=g), dim=1)
+        b = torch.nn.functional.normalize(a[torch.randperm(1500, generator=g)[:1300]] + 0.3 * torch.randn(1300, 128, generator=g), dim=1)
+        want = O.mnn_matcher(a.numpy(), b.numpy(), exact=True)
+        np.testing.assert_array_equal(gm(a.cuda(), b.cuda()), want)
+        np.testing.assert_array_equal(gm(a, b), want)                     # host tensors: copied into the static buffers
+        np.testing.assert_array_equal(P.mnn_matcher(a.cuda(), b.cuda()), want)
+    with pytest.raises(ValueError):
+        gm(a[:100].cuda(), b.cuda())

@@ -32,6 +32,21 @@ def timeit(fn, iters=20):
     return 1e3 * e0.elapsed_time(e1) / iters
 
 
+def timeit_graph(fn, iters=50):
+    """Device time of one call: the call captured as a CUDA graph and replayed (no host launch overhead)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
+    return timeit(gr.replay, iters)
+
+
 # grid <-> grid expectation of Preprocess_Line2Window (n = m = 512 points per image, temperature 20)
 qg = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=-1).cuda().requires_grad_(True)
 kg = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=-1).cuda().requires_grad_(True)
@@ -80,7 +95,8 @@ for name, (h, w) in (("dense_coarse_30x40", (30, 40)), ("dense_fine_120x160", (1
     r = {"case": name, "B": B, "n": n, "hw": h * w, "max_abs_err_vs_torch": err,
          "ours_fwd_us": timeit(ours_fwd), "torch_fwd_us": timeit(ref_fwd),
          "ours_fwd_bwd_us": timeit(ours_fb), "torch_fwd_bwd_us": timeit(ref_fb)}
-    r["ours_fwd_tflops_fp32"] = flops / (r["ours_fwd_us"] * 1e-6) / 1e12
+    r["ours_fwd_graph_us"], r["torch_fwd_graph_us"] = timeit_graph(ours_fwd), timeit_graph(ref_fwd)
+    r["ours_fwd_tflops_fp32"] = flops / (r["ours_fwd_graph_us"] * 1e-6) / 1e12
     print(json.dumps(r), flush=True)
 
 # window on the fine map
