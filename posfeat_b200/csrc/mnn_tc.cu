@@ -905,6 +905,7 @@ struct VerifyArgs {
   const unsigned* g8;        // [pairs][pitch][groups]
   int groups;
   unsigned long long* dbg;   // POSFEAT_MNN_DEBUG counters (NULL otherwise)
+  int mode;                  // bring-up timing (POSFEAT_TC_DEBUG bits 0x10000 / 0x20000 / 0x40000 / 0x80000), 0 otherwise
 };
 
 // float32 similarities of one row x (float4 per lane) to the 8 columns of a chunk staged in
@@ -960,6 +961,10 @@ constexpr int kVerWarps = 1;
 // kG8: the competitor list is built here, in shared memory, from the chunk's row of group entries (one coalesced
 // read of groups * 4 bytes, 4 KB at N = 8192) instead of by a scan kernel over a table: a group whose max1 reaches
 // the chunk's threshold contributes its leader row, or all of its 8 rows when max2 reaches the threshold too.
+// Measured and dropped: evaluating the non-member rows four at a time (eight lanes per row, 7-shuffle reduction, a
+// third of the instructions) or requesting four rows ahead -- both need more than 64 registers or spill, and the
+// kernel is bound by the warps in flight: 24 / 20 CTAs per SM cost 10 % / 25 % on well-matched pairs
+// (tools/verify_debug_sweep.py: 150 -> 166 -> 189 us per 64 pairs) and gain at most 5 % on unrelated ones.
 template <bool kG8>
 __global__ void __launch_bounds__(kVerWarps * 32, 32)
 tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
@@ -1060,6 +1065,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     const int o = a.tmin[slot];
     if (o == 0x7f7f7f7f) return;                                  // no row has its nearest neighbour in this chunk
     thr_chunk = __float2half2_rn(__half2float(__float2half_rd(ordered_int_to_float(o))));
+    if (a.mode & 0x80000) return;               // bring-up timing: threshold + first block of group entries only
     total = build(thr_chunk, 0, e, true);
     rows = myrows;
     if (a.dbg && lane == 0) {
@@ -1123,6 +1129,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
     total = build(thr_chunk, 1, e, false);
     narrowed = true;
   }
+  if (kG8 && (a.mode & 0x10000)) return;       // bring-up timing: threshold + group-entry scan + list only
   if (kG8 && total <= kCompCap) {
     // Member-centric form.  Members (rows whose nearest neighbour lies in this chunk) are first settled among
     // themselves from the 8 values the rescoring kernel left for each of them -- in a well-matched pair a weak
@@ -1147,7 +1154,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
       nmem += __popc(bal);
     }
     __syncwarp();
-    if (nmem == 0) return;
+    if (nmem == 0 || (a.mode & 0x40000)) return;       // (bring-up timing: members collected, nothing settled)
     if (nmem <= 32) {
       const bool member = lane < nmem;
       const int iq = member ? mi[lane] : -1, jq = member ? mj[lane] : -1;
@@ -1177,6 +1184,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tl = fminf(tl, __shfl_xor_sync(0xffffffffu, tl, o));
       bool give_up = false;
+      if (a.mode & 0x20000) tl = INFINITY;       // bring-up timing: no non-member is evaluated
       if (tl < INFINITY) {
         if (narrowed) {            // the list held the members only: now the non-members that can still matter
           uint4 e[4];
@@ -1194,6 +1202,7 @@ tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
           }
           unsigned todo = __ballot_sync(0xffffffffu, need);
           if (todo && !staged) { stage_y(); staged = true; }
+          if (a.dbg && lane == 0) atomicAdd(a.dbg + 10, (unsigned long long)__popc(todo));
           while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -1345,7 +1354,6 @@ struct RescoreListArgs {
   unsigned char* mutual;                  // [pairs][NX], set to 1 here
   int nchunks;
   unsigned long long* dbg;                // POSFEAT_MNN_DEBUG counters (NULL otherwise)
-  int mode;                               // bring-up timing (POSFEAT_TC_DEBUG bits 0x4000 / 0x8000), 0 otherwise
 };
 
 constexpr int kRlWarps = 2;
@@ -1568,36 +1576,51 @@ tc_rescore_lists_kernel(const RescoreListArgs a) {
   rescore_row_lists(a, blockIdx.y, row, xs, w, lane);
 }
 
-// The same rescoring with the per-row control flow moved from a warp onto a LANE.  In the kernel above a row costs
-// ~420 warp instructions of which ~100 are the eight dot products: the rest is list walking, thresholds and outputs
-// executed by 32 lanes for one row (ncu: 57 % issue utilisation at the 32 warps per SM the registers allow -- the
-// kernel is bound by its own instruction count).  Here a warp owns 32 consecutive rows:
-//   A  lane = row: F = max of the lines' running maxima (slot 0), threshold, walk of the row's list entries (one
-//      32-byte sector = 4 slots per step); the candidate chunks go into a per-warp queue in shared memory;
-//   B  four queue entries at a time, eight lanes each: lane t of a group holds 16 of the 128 dimensions, 8 x 16 FMAs,
-//      a 7-shuffle transposing reduction leaves column t of the chunk on lane t; the group posts (maximum, winner,
-//      "two columns within the float32 band") and the owner lane of the row merges the posts in queue order;
-//   C  lane = row: nn12, the chunk threshold (atomicMin) and the mutual flag, coalesced.
-// Rows that need anything else -- an overflowed list, a queue over capacity, two columns within the float32 error
-// band (exact pass) -- are handed to rescore_row_lists unchanged (one row in several hundred).
+// Large calls move the per-row control flow from a warp onto a LANE and order the arithmetic by column chunk (below).
+// In the kernel above a row costs ~420 warp instructions of which ~100 are the eight dot products: the rest is list
+// walking, thresholds and outputs executed by 32 lanes for one row (ncu: 57 % issue utilisation at the 32 warps per
+// SM the registers allow), and every (row, candidate chunk) streams 4 KB of Y out of L2.  With fewer than ~64k rows
+// in a call there are not enough 32-row warps to fill the machine and the kernel above stays the faster one
+// (4096 rows: 13 us against 46 us for a lane-per-row kernel).
 constexpr int kRqWarps = 4;
-constexpr int kRqCap = 6;               // queue slots per row
-constexpr int kRqGroups = 4;            // queue entries in flight per warp (8 lanes each)
+constexpr int kRqCap = 6;               // candidates per row the float32 pass handles; more: general routine
+constexpr int kRqGroups = 4;            // bucket entries in flight per warp (8 lanes each)
 
 __device__ __noinline__ void rescore_row_lists_slow(const RescoreListArgs& a, const int pair, const int row,
                                                     float (&xs)[kRlWarps][kD], const int lane) {
   rescore_row_lists(a, pair, row, xs, 0, lane);
 }
 
-__global__ void __launch_bounds__(kRqWarps * 32, 5)
-tc_rescore_lists_rows_kernel(const RescoreListArgs a) {
-  __shared__ int s_cand[kRqWarps][kRqCap][32];
-  __shared__ int s_qc[kRqWarps][32 * kRqCap];               // flat queue: chunk ...
-  __shared__ unsigned char s_qo[kRqWarps][32 * kRqCap];     // ... and owner lane
-  __shared__ int s_po[kRqWarps][kRqGroups], s_pcol[kRqWarps][kRqGroups], s_pmulti[kRqWarps][kRqGroups];
-  __shared__ float s_pcm[kRqWarps][kRqGroups];
-  __shared__ __align__(16) float s_p8[kRqWarps][kRqGroups][kChunk];
+// ------------------------------------------------------------------ rescoring by COLUMN CHUNK (large calls)
+// A chunk of 8 columns is a candidate of ~8-11 rows, so the work ordered by chunk reads every chunk of Y once (by row
+// it is 3 GB per 64 pairs of 8192 out of L2):
+//   1  tc_rescore_enum_kernel    lane = row: F = max of the lines' running maxima, threshold, list walk; every candidate (row, k-th
+//                                candidate of the row) is appended to its chunk's bucket (one atomicAdd);
+//   2  tc_rescore_chunk_kernel   warp = chunk: Y chunk staged in shared memory, bucket entries four at a time
+//                                (eight lanes per row: lane t holds 16 of the 128 dimensions, 8 x 16 FMAs, a 7-shuffle
+//                                transposing reduction leaves column t of the chunk on lane t), one 48-byte record
+//                                per entry: the 8 float32 similarities, their maximum, its column, "two columns
+//                                within the float32 band";
+//   3  tc_rescore_merge_kernel   lane = row: merges the row's records in list order, writes nn12 / best8 / chunk
+//                                threshold / mutual flag.
+// Rows the float32 pass cannot settle, overflowed lists, rows with more than kRqCap candidates and rows that hit a
+// full bucket go through rescore_row_lists (in kernel 1 or 3): one row in several hundred.
+constexpr int kBucketCap = 64;           // entries per chunk bucket (the comp array of the table form is reused: kCompCap ints)
+constexpr int kRecFloats = 12;           // s8[8], cm, column, multi, pad
+static_assert(kBucketCap <= kCompCap, "bucket storage is the table form's competitor array");
+
+struct RescoreBucketArgs {
+  RescoreListArgs r;
+  int* bcnt;                              // [pairs][nchunks], zeroed per call
+  unsigned* bucket;                       // [pairs][nchunks][kCompCap] (first kBucketCap used): row | k << 28
+  float* rec;                             // [pairs][NX][kRqCap][kRecFloats]
+  int* rowinfo;                           // [pairs][NX]: number of candidates, or -1 = settled by the general routine
+};
+
+__global__ void __launch_bounds__(kRqWarps * 32, 8)
+tc_rescore_enum_kernel(const __grid_constant__ RescoreBucketArgs b) {
   __shared__ __align__(16) float s_x[kRqWarps][kRlWarps][kD];
+  const RescoreListArgs& a = b.r;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.y;
   const DirParams& d = a.d;
@@ -1608,38 +1631,63 @@ tc_rescore_lists_rows_kernel(const RescoreListArgs a) {
   const size_t prow = (size_t)pair * d.NXpad + (live ? row : row0);
   const int nlines = 4 * d.splits;
   const uint2* lines = a.lists + prow * nlines * kListSlots;
-  const MatStats ys = d.ystats[2 * pair], xst = d.xstats[2 * pair];
+  const MatStats ys = d.ystats[2 * pair];
   const float ymax = __uint_as_float(ys.max_norm);
   const float xn = d.xnorm[prow];
   const float delta = 2.f * (d.xerr[prow] * __uint_as_float(ys.max_norm_bf) + xn * __uint_as_float(ys.max_err) +
                              kAccSlack * xn * ymax);
-  const float band = 2.f * kEps32 * xn * ymax;
-
-  // ---- A: threshold and candidate queue of this lane's row
   float F = -INFINITY;
   bool slow = false;
   int entries = 0;
-  for (int l = 0; l < nlines; ++l) {
-    const uint2 h = __ldg(lines + l * kListSlots);
-    slow |= (int)h.x >= kListSlots;                       // the list overflowed
-    entries += (int)h.x;
-    if ((int)h.x > 0) F = fmaxf(F, __uint_as_float(h.y));
+  // four lines per row (no column split: every large call): the first sector of each line -- header and three
+  // entries -- is requested up front, eight loads in flight instead of a chain of round trips
+  const bool four = nlines == 4;
+  uint4 f0[4], f1[4];
+  if (four) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const uint4* lp = reinterpret_cast<const uint4*>(lines + l * kListSlots);
+      f0[l] = __ldg(lp); f1[l] = __ldg(lp + 1);
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      slow |= (int)f0[l].x >= kListSlots;
+      entries += (int)f0[l].x;
+      if ((int)f0[l].x > 0) F = fmaxf(F, __uint_as_float(f0[l].y));
+    }
+  } else {
+    for (int l = 0; l < nlines; ++l) {
+      const uint2 h = __ldg(lines + l * kListSlots);
+      slow |= (int)h.x >= kListSlots;                     // the list overflowed
+      entries += (int)h.x;
+      if ((int)h.x > 0) F = fmaxf(F, __uint_as_float(h.y));
+    }
   }
   const float thr = F - delta;
   int ncand = 0;
+  int cand[kRqCap];
+#pragma unroll
+  for (int k = 0; k < kRqCap; ++k) cand[k] = 0;
   if (live && !slow) {
-    // an entry names a tile quarter (8 chunks from chunk0) and the chunks of it that were within delta
     auto consider = [&](unsigned ex, unsigned ey) {
       if (__uint_as_float(ey) >= thr) {
         for (unsigned mk = ex >> 24; mk; mk &= mk - 1) {
-          if (ncand < kRqCap) s_cand[w][ncand][lane] = (int)((ex & 0xffffffu) + __ffs(mk) - 1);
+          const int chunk = (int)((ex & 0xffffffu) + __ffs(mk) - 1);
+#pragma unroll
+          for (int k = 0; k < kRqCap; ++k) if (k == ncand) cand[k] = chunk;      // (registers: no dynamic indexing)
           ++ncand;
         }
       }
     };
     for (int l = 0; l < nlines; ++l) {
       const uint4* lp = reinterpret_cast<const uint4*>(lines + l * kListSlots);
-      uint4 v0 = __ldg(lp), v1 = __ldg(lp + 1);           // slots 0 (header), 1 | 2, 3: one sector
+      uint4 v0, v1;                                       // slots 0 (header), 1 | 2, 3: one sector
+      if (four) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q == l) { v0 = f0[q]; v1 = f1[q]; }
+      } else {
+        v0 = __ldg(lp); v1 = __ldg(lp + 1);
+      }
       const int cnt = (int)v0.x;
       if (cnt >= 1) consider(v0.z, v0.w);
       if (cnt >= 2) consider(v1.x, v1.y);
@@ -1652,141 +1700,25 @@ tc_rescore_lists_rows_kernel(const RescoreListArgs a) {
         if (cnt >= base + 3) consider(v1.z, v1.w);
       }
     }
-    slow = ncand > kRqCap;
+    slow |= ncand > kRqCap;
+    if (!slow) {
+      // the bucket slots of all candidates are requested together (an atomic with a result is a memory round trip)
+      int* bc = b.bcnt + (size_t)pair * a.nchunks;
+      unsigned* bk = b.bucket + (size_t)pair * a.nchunks * kCompCap;
+      int pos[kRqCap];
+#pragma unroll
+      for (int k = 0; k < kRqCap; ++k) pos[k] = k < ncand ? atomicAdd(bc + cand[k], 1) : 0;
+#pragma unroll
+      for (int k = 0; k < kRqCap; ++k) {
+        if (k < ncand) {
+          if (pos[k] < kBucketCap) bk[(size_t)cand[k] * kCompCap + pos[k]] = (unsigned)row | ((unsigned)k << 28);
+          else slow = true;                                // bucket full: the general routine takes the row
+        }
+      }
+    }
   }
   if (!live) { slow = false; ncand = 0; }
-  // flat queue in row order
-  const int mine = slow ? 0 : ncand;
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  for (int k = 0; k < mine; ++k) {
-    s_qc[w][incl - mine + k] = s_cand[w][k][lane];
-    s_qo[w][incl - mine + k] = (unsigned char)lane;
-  }
-  __syncwarp();
-
-  // ---- B: the queued (row, chunk) pairs, kRqGroups at a time
-  float m32 = -INFINITY;
-  int besti = 0x7fffffff;
-  bool amb = false;
-  {
-    const float* __restrict__ Y = a.Y + pair * a.strideY;
-    const int ld4 = (int)(a.ldy >> 2), ldx4 = (int)(a.ldx >> 2);     // the host selects this kernel only for aligned operands
-    const int t = lane & 7, gi = lane >> 3;
-    const float4* y4 = reinterpret_cast<const float4*>(Y) + t;
-    const float4* x4 = reinterpret_cast<const float4*>(a.X + pair * a.strideX) + t;
-    const int NY = d.NY;
-    const int niter = (a.mode & 0x8000) ? 0 : (total + kRqGroups - 1) / kRqGroups;
-    for (int it = 0; it < niter; ++it) {
-      const int idx = it * kRqGroups + gi;
-      const bool act = idx < total;
-      const int idc = act ? idx : total - 1;
-      const int o = s_qo[w][idc];
-      const int col0 = s_qc[w][idc] * kChunk;
-      float4 xv[4];
-      const float4* xp = x4 + (size_t)(unsigned)(row0 + o) * (size_t)ldx4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xv[i] = __ldg(xp + 8 * i);
-      const float4* yp = y4 + (size_t)(unsigned)col0 * (size_t)ld4;
-      const int rlast = NY - 1 - col0;                     // rows past the end are clamped: masked below
-      float pr[kChunk];
-#pragma unroll
-      for (int r = 0; r < kChunk; ++r) {
-        const float4* yr = yp + min(r, rlast) * ld4;
-        float4 yv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) yv[i] = __ldg(yr + 8 * i);
-        float acc = xv[0].x * yv[0].x;
-        acc = fmaf(xv[0].y, yv[0].y, acc); acc = fmaf(xv[0].z, yv[0].z, acc); acc = fmaf(xv[0].w, yv[0].w, acc);
-#pragma unroll
-        for (int i = 1; i < 4; ++i) {
-          acc = fmaf(xv[i].x, yv[i].x, acc); acc = fmaf(xv[i].y, yv[i].y, acc);
-          acc = fmaf(xv[i].z, yv[i].z, acc); acc = fmaf(xv[i].w, yv[i].w, acc);
-        }
-        pr[r] = acc;
-      }
-      float q4[4], q2[2], sc;
-      {
-        const bool hi = t & 4;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float got = __shfl_xor_sync(0xffffffffu, hi ? pr[r] : pr[r + 4], 4);
-          q4[r] = (hi ? pr[r + 4] : pr[r]) + got;
-        }
-      }
-      {
-        const bool hi = t & 2;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const float got = __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 2);
-          q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
-        }
-      }
-      {
-        const bool hi = t & 1;
-        const float got = __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 1);
-        sc = (hi ? q2[1] : q2[0]) + got;                  // lane t: column col0 + t
-      }
-      if (col0 + t >= NY) sc = -INFINITY;
-      float cm = sc;
-#pragma unroll
-      for (int sh = 4; sh >= 1; sh >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, sh));
-      const float band_o = __shfl_sync(0xffffffffu, band, o);
-      const unsigned near = (__ballot_sync(0xffffffffu, sc >= cm - band_o) >> (lane & 24)) & 0xffu;
-      const unsigned at = (__ballot_sync(0xffffffffu, sc == cm) >> (lane & 24)) & 0xffu;
-      s_p8[w][gi][t] = sc;
-      if (t == 0) {
-        s_po[w][gi] = act ? o : -1;
-        s_pcm[w][gi] = cm;
-        s_pcol[w][gi] = col0 + __ffs(at) - 1;
-        s_pmulti[w][gi] = (near & (near - 1)) != 0;
-      }
-      __syncwarp();
-      // the owner merges the posts of its row in queue order (two entries of one row may be in flight together)
-#pragma unroll
-      for (int g2 = 0; g2 < kRqGroups; ++g2) {
-        if (s_po[w][g2] == lane) {
-          const float c2 = s_pcm[w][g2];
-          amb |= s_pmulti[w][g2] != 0 || (c2 <= m32 ? c2 >= m32 - band : m32 >= c2 - band);
-          if (c2 > m32) {
-            m32 = c2;
-            besti = s_pcol[w][g2];
-            float4* dst = reinterpret_cast<float4*>(a.best8 + ((size_t)pair * d.NX + row) * kChunk);
-            dst[0] = *reinterpret_cast<const float4*>(&s_p8[w][g2][0]);
-            dst[1] = *reinterpret_cast<const float4*>(&s_p8[w][g2][4]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-  slow |= amb;                         // two columns within the float32 error band: the exact pass decides
-
-  // ---- C: outputs of the rows settled by the float32 pass
-  if (live && !slow) {
-    const size_t rowg = (size_t)pair * d.NX + row;
-    const int bj = besti == 0x7fffffff ? 0 : besti;
-    if (besti == 0x7fffffff) {          // no candidate at all (cannot happen with a well-formed list): defined outputs
-#pragma unroll
-      for (int c = 0; c < kChunk; ++c) a.best8[rowg * kChunk + c] = 0.f;
-    }
-    a.nn[rowg] = bj;
-    const float xmax = __uint_as_float(xst.max_norm);
-    const float eps_max = __uint_as_float(xst.max_err) * __uint_as_float(ys.max_norm_bf) + xmax * __uint_as_float(ys.max_err) +
-                          kAccSlack * xmax * ymax;
-    const float mm = xmax * ymax;
-    const float scale = mm > 0.f ? 1.f / mm : 1.f;
-    const float vlow = m32 - 0.5f * band;
-    float thr_v = (vlow - eps_max) * scale - 1e-6f;
-    if (thr_v > 0.f) thr_v *= kG8Slack;
-    atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
-    a.mutual[rowg] = 1;
-  }
+  if (live) b.rowinfo[(size_t)pair * d.NX + row] = slow ? -1 : ncand;
   if (a.dbg) {
     const bool fast = live && !slow;
     const int nrows = __popc(__ballot_sync(0xffffffffu, fast));
@@ -1799,8 +1731,184 @@ tc_rescore_lists_rows_kernel(const RescoreListArgs a) {
       atomicAdd(a.dbg + 9, (unsigned long long)nslow);
     }
   }
-  // ---- everything else: the general per-row routine
   unsigned rest = __ballot_sync(0xffffffffu, slow);
+  while (rest) {
+    const int o = __ffs(rest) - 1;
+    rest &= rest - 1;
+    __syncwarp();
+    rescore_row_lists_slow(a, pair, row0 + o, s_x[w], lane);
+  }
+}
+
+constexpr int kRcWarps = 4;
+__global__ void __launch_bounds__(kRcWarps * 32, 6)
+tc_rescore_chunk_kernel(const __grid_constant__ RescoreBucketArgs b) {
+  __shared__ __align__(16) float4 s_y[kRcWarps][kChunk * 32];
+  const RescoreListArgs& a = b.r;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const int c = blockIdx.x * kRcWarps + w;
+  if (c >= a.nchunks) return;
+  const DirParams& d = a.d;
+  const int n_raw = b.bcnt[(size_t)pair * a.nchunks + c];
+  const unsigned* bk = b.bucket + ((size_t)pair * a.nchunks + c) * kCompCap;
+  const int NY = d.NY, col0 = c * kChunk;
+  const unsigned ent_first = __ldg(bk + (lane >> 3));        // requested with the count and the chunk (valid memory either way)
+  {
+    const float4* y4 = reinterpret_cast<const float4*>(a.Y + pair * a.strideY) + lane;
+    const int ld4 = (int)(a.ldy >> 2);
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) s_y[w][r * 32 + lane] = __ldg(y4 + (size_t)min(col0 + r, NY - 1) * ld4);   // past the end: masked below
+  }
+  __syncwarp();
+  const int n = min(n_raw, kBucketCap);
+  if (n == 0) return;
+  const float ymax = __uint_as_float(d.ystats[2 * pair].max_norm);
+  const int t = lane & 7, gi = lane >> 3;
+  const int ldx4 = (int)(a.ldx >> 2);
+  const float4* x4 = reinterpret_cast<const float4*>(a.X + pair * a.strideX) + t;
+  const float4* ys4 = &s_y[w][t];
+  // software pipeline: the entries and rows of the next batch are requested before the current one is reduced
+  unsigned ent_n = gi < n ? ent_first : __ldg(bk + n - 1);
+  float4 xn4[4];
+  float xnorm_n;
+  {
+    const int row = (int)(ent_n & 0x0fffffffu);
+    const float4* xp = x4 + (size_t)(unsigned)row * (size_t)ldx4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xn4[i] = __ldg(xp + 8 * i);
+    xnorm_n = __ldg(d.xnorm + (size_t)pair * d.NXpad + row);
+  }
+  for (int e0 = 0; e0 < n; e0 += kRqGroups) {
+    const int e = e0 + gi;
+    const bool act = e < n;
+    const unsigned ent = ent_n;
+    const int row = (int)(ent & 0x0fffffffu), k = (int)(ent >> 28);
+    float4 xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = xn4[i];
+    const float band = 2.f * kEps32 * xnorm_n * ymax;
+    if (e0 + kRqGroups < n) {
+      const int en = e0 + kRqGroups + gi;
+      ent_n = __ldg(bk + (en < n ? en : n - 1));
+      const int rown = (int)(ent_n & 0x0fffffffu);
+      const float4* xp = x4 + (size_t)(unsigned)rown * (size_t)ldx4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xn4[i] = __ldg(xp + 8 * i);
+      xnorm_n = __ldg(d.xnorm + (size_t)pair * d.NXpad + rown);
+    }
+    float pr[kChunk];
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) {
+      float4 yv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) yv[i] = ys4[r * 32 + 8 * i];
+      float acc = xv[0].x * yv[0].x;
+      acc = fmaf(xv[0].y, yv[0].y, acc); acc = fmaf(xv[0].z, yv[0].z, acc); acc = fmaf(xv[0].w, yv[0].w, acc);
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        acc = fmaf(xv[i].x, yv[i].x, acc); acc = fmaf(xv[i].y, yv[i].y, acc);
+        acc = fmaf(xv[i].z, yv[i].z, acc); acc = fmaf(xv[i].w, yv[i].w, acc);
+      }
+      pr[r] = acc;
+    }
+    float q4[4], q2[2], sc;
+    {
+      const bool hi = t & 4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? pr[r] : pr[r + 4], 4);
+        q4[r] = (hi ? pr[r + 4] : pr[r]) + got;
+      }
+    }
+    {
+      const bool hi = t & 2;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float got = __shfl_xor_sync(0xffffffffu, hi ? q4[r] : q4[r + 2], 2);
+        q2[r] = (hi ? q4[r + 2] : q4[r]) + got;
+      }
+    }
+    {
+      const bool hi = t & 1;
+      const float got = __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 1);
+      sc = (hi ? q2[1] : q2[0]) + got;                  // lane t: column col0 + t
+    }
+    if (col0 + t >= NY) sc = -INFINITY;
+    float cm = sc;
+#pragma unroll
+    for (int sh = 4; sh >= 1; sh >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, sh));
+    const unsigned near = (__ballot_sync(0xffffffffu, sc >= cm - band) >> (lane & 24)) & 0xffu;
+    const unsigned at = (__ballot_sync(0xffffffffu, sc == cm) >> (lane & 24)) & 0xffu;
+    if (act) {
+      float* rec = b.rec + (((size_t)pair * d.NX + row) * kRqCap + k) * kRecFloats;
+      rec[t] = sc;
+      if (t == 0) {
+        rec[8] = cm;
+        rec[9] = __int_as_float(col0 + __ffs(at) - 1);
+        rec[10] = __int_as_float((near & (near - 1)) != 0 ? 1 : 0);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRqWarps * 32, 8)
+tc_rescore_merge_kernel(const __grid_constant__ RescoreBucketArgs b) {
+  __shared__ __align__(16) float s_x[kRqWarps][kRlWarps][kD];
+  const RescoreListArgs& a = b.r;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  const DirParams& d = a.d;
+  const int row0 = (blockIdx.x * kRqWarps + w) * 32;
+  if (row0 >= d.NX) return;
+  const int row = row0 + lane;
+  const bool live = row < d.NX;
+  const size_t rowg = (size_t)pair * d.NX + (live ? row : row0);
+  const int info = live ? b.rowinfo[rowg] : -1;
+  const MatStats ys = d.ystats[2 * pair], xst = d.xstats[2 * pair];
+  const float ymax = __uint_as_float(ys.max_norm);
+  const float band = 2.f * kEps32 * d.xnorm[(size_t)pair * d.NXpad + (live ? row : row0)] * ymax;
+  float m32 = -INFINITY;
+  int besti = 0x7fffffff, bestk = 0;
+  bool amb = false;
+  const float* rec = b.rec + rowg * kRqCap * kRecFloats;
+  // the first record (most rows have exactly one) is requested together with the row's info, not after it; the
+  // loads are of initialised or stale-but-mapped workspace memory and only used when info says so
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(rec + 8));
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(rec)), s1 = __ldg(reinterpret_cast<const float4*>(rec) + 1);
+  for (int k = 0; k < info; ++k) {
+    const float4 h = k == 0 ? h0 : __ldg(reinterpret_cast<const float4*>(rec + k * kRecFloats + 8));
+    const float c2 = h.x;
+    amb |= __float_as_int(h.z) != 0 || (c2 <= m32 ? c2 >= m32 - band : m32 >= c2 - band);
+    if (c2 > m32) { m32 = c2; besti = __float_as_int(h.y); bestk = k; }
+  }
+  if (info >= 0 && !amb) {
+    float4* dst = reinterpret_cast<float4*>(a.best8 + rowg * kChunk);
+    if (besti == 0x7fffffff) {          // no candidate at all (cannot happen with a well-formed list): defined outputs
+      dst[0] = make_float4(0.f, 0.f, 0.f, 0.f); dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      if (bestk == 0) { dst[0] = s0; dst[1] = s1; }
+      else {
+        const float4* src = reinterpret_cast<const float4*>(rec + bestk * kRecFloats);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+      }
+    }
+    const int bj = besti == 0x7fffffff ? 0 : besti;
+    a.nn[rowg] = bj;
+    const float xmax = __uint_as_float(xst.max_norm);
+    const float eps_max = __uint_as_float(xst.max_err) * __uint_as_float(ys.max_norm_bf) + xmax * __uint_as_float(ys.max_err) +
+                          kAccSlack * xmax * ymax;
+    const float mm = xmax * ymax;
+    const float scale = mm > 0.f ? 1.f / mm : 1.f;
+    const float vlow = m32 - 0.5f * band;
+    float thr_v = (vlow - eps_max) * scale - 1e-6f;
+    if (thr_v > 0.f) thr_v *= kG8Slack;
+    atomicMin(a.tmin + (size_t)pair * a.nchunks + (bj >> 3), float_to_ordered_int(thr_v));
+    a.mutual[rowg] = 1;
+  }
+  // two columns within the float32 error band: the exact pass of the general routine decides
+  unsigned rest = __ballot_sync(0xffffffffu, info >= 0 && amb);
+  if (a.dbg && lane == 0 && rest) atomicAdd(a.dbg + 9, (unsigned long long)__popc(rest));
   while (rest) {
     const int o = __ffs(rest) - 1;
     rest &= rest - 1;
@@ -2084,21 +2192,29 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     const bool dbg_on = getenv("POSFEAT_MNN_DEBUG") != nullptr;
     if (dbg_on) PF_CUDA(cudaMemsetAsync(w.dbg, 0, sizeof(unsigned long long) * 16, stream));
     RescoreListArgs ra{p.d[0], w.lists, A, lda, strideA, Bm, ldb, strideB, nn12, w.best8, w.tmin, w.mutual, nchunks,
-                       dbg_on ? w.dbg : nullptr, p.debug & 0xc000};
+                       dbg_on ? w.dbg : nullptr};
     prof_begin(PROF_MNN_RESCORE, stream);
-    static const bool rows_env = getenv("POSFEAT_MNN_RESCORE_WARP") == nullptr;      // A/B switch: the warp-per-row kernel
-    // the row-group kernel reads 16-byte vectors: operands that are not aligned for them take the warp-per-row kernel
-    const bool rows_form = rows_env && lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 &&
-                           (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0 && lda < (1ll << 31) && ldb < (1ll << 31);
-    if (rows_form)
-      tc_rescore_lists_rows_kernel<<<dim3((unsigned)((N + kRqWarps * 32 - 1) / (kRqWarps * 32)), (unsigned)P), kRqWarps * 32, 0, stream>>>(ra);
-    else
+    // large calls: the chunk-ordered form (16-byte vector loads: aligned operands only; the records live in the table
+    // form's first table, 2 * pitch bytes per row); POSFEAT_MNN_RESCORE_WARP=1 keeps the warp-per-row kernel for A/B runs
+    static const bool bucket_env = getenv("POSFEAT_MNN_RESCORE_WARP") == nullptr;
+    const bool bucket_form = bucket_env && (size_t)P * N >= 65536 && N < (1 << 28) &&
+                             lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 &&
+                             (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0 && lda < (1ll << 31) && ldb < (1ll << 31) &&
+                             (size_t)w.pitch[0] * sizeof(__half) >= sizeof(float) * kRqCap * kRecFloats;
+    if (bucket_form) {
+      PF_CUDA(cudaMemsetAsync(w.comp_cnt, 0, sizeof(int) * (size_t)P * nchunks, stream));
+      RescoreBucketArgs ba{ra, w.comp_cnt, (unsigned*)w.comp, (float*)w.table[0], (int*)w.best};
+      const dim3 grows((unsigned)((N + kRqWarps * 32 - 1) / (kRqWarps * 32)), (unsigned)P);
+      tc_rescore_enum_kernel<<<grows, kRqWarps * 32, 0, stream>>>(ba);
+      tc_rescore_chunk_kernel<<<dim3((unsigned)((nchunks + kRcWarps - 1) / kRcWarps), (unsigned)P), kRcWarps * 32, 0, stream>>>(ba);
+      tc_rescore_merge_kernel<<<grows, kRqWarps * 32, 0, stream>>>(ba);
+    } else
       tc_rescore_lists_kernel<<<dim3((unsigned)((N + kRlWarps - 1) / kRlWarps), (unsigned)P), kRlWarps * 32, 0, stream>>>(ra);
     prof_end(PROF_MNN_RESCORE, stream);
     PF_LAUNCH_CHECK("tc_rescore_lists_kernel");
     if (p.debug & 0x2000) return POSFEAT_OK;   // bring-up timing: stop after the rescoring kernel (no results)
     VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, nullptr, nullptr, w.best8, w.mutual, nchunks, w.tmin, w.g8, Np / 8,
-                  dbg_on ? w.dbg : nullptr};
+                  dbg_on ? w.dbg : nullptr, p.debug & 0xf0000};
     prof_begin(PROF_MNN_VERIFY, stream);
     tc_verify_kernel<true><<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
     prof_end(PROF_MNN_VERIFY, stream);
@@ -2108,12 +2224,12 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     prof_end(PROF_MNN_COMPACT, stream);
     PF_LAUNCH_CHECK("tc_compact_flags_kernel");
     if (dbg_on) {   // diagnostics only: synchronises
-      unsigned long long h[10];
+      unsigned long long h[11];
       PF_CUDA(cudaMemcpyAsync(h, w.dbg, sizeof(h), cudaMemcpyDeviceToHost, stream));
       PF_CUDA(cudaStreamSynchronize(stream));
       fprintf(stderr, "posfeat mnn lists: P=%d N=%d M=%d splits=%d | rows %llu overflow %llu exact-pass %llu general-path %llu candidates %llu list-entries %llu | "
-                      "chunks %llu competitors %llu overflow-chunks %llu long-chunks(>32) %llu\n", P, N, M, s0, h[0], h[1], h[8], h[9],
-              h[2], h[3], h[4], h[5], h[6], h[7]);
+                      "chunks %llu competitors %llu overflow-chunks %llu long-chunks(>32) %llu non-member-evaluations %llu\n", P, N, M, s0, h[0], h[1], h[8], h[9],
+              h[2], h[3], h[4], h[5], h[6], h[7], h[10]);
     }
     return POSFEAT_OK;
   }
@@ -2144,7 +2260,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
   tc_scan_kernel<<<dim3((N + scan_rows - 1) / scan_rows, P), 256, sizeof(__half) * w.pitch[0], stream>>>(sa);
   prof_end(PROF_MNN_SCAN, stream);
   PF_LAUNCH_CHECK("tc_scan_kernel");
-  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.best8, w.mutual, nchunks, nullptr, nullptr, 0, nullptr};
+  VerifyArgs va{p.d[0], A, lda, strideA, Bm, ldb, strideB, nn12, w.comp_cnt, w.comp, w.best8, w.mutual, nchunks, nullptr, nullptr, 0, nullptr, 0};
   prof_begin(PROF_MNN_VERIFY, stream);
   tc_verify_kernel<false><<<dim3((nchunks + kVerWarps - 1) / kVerWarps, P), kVerWarps * 32, 0, stream>>>(va, getenv("POSFEAT_VERIFY_DEBUG") ? 1 : 0);
   prof_end(PROF_MNN_VERIFY, stream);
