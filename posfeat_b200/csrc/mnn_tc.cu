@@ -952,7 +952,8 @@ __device__ __forceinline__ double warp_exact_dot(const float* __restrict__ xr, c
   return acc;
 }
 
-constexpr int kVerWarps = 1;
+constexpr int kVerWarps = 1;            // (4-warp CTAs: the CTA launch cost drops 43 -> 33 us per 64 pairs, but a CTA then lives as
+                                        // long as its longest chunk: 152 -> 159 us on matched pairs, 502 -> 582 us on unrelated ones)
 // One WARP per (chunk c of Y columns, pair).  R = competitor rows of the chunk (a superset of
 // the members, the rows whose nearest neighbour lies in c).  The competitors' similarities to
 // the chunk's 8 columns are evaluated in float32; a member loses its match if another
@@ -966,7 +967,7 @@ constexpr int kVerWarps = 1;
 // kernel is bound by the warps in flight: 24 / 20 CTAs per SM cost 10 % / 25 % on well-matched pairs
 // (tools/verify_debug_sweep.py: 150 -> 166 -> 189 us per 64 pairs) and gain at most 5 % on unrelated ones.
 template <bool kG8>
-__global__ void __launch_bounds__(kVerWarps * 32, 32)
+__global__ void __launch_bounds__(kVerWarps * 32, 32 / kVerWarps)
 tc_verify_kernel(const VerifyArgs a, const int getenv_dbg) {
   __shared__ __align__(16) float4 s_y[kVerWarps][kChunk * 32];   // the 8 columns of the chunk
   __shared__ float s_e[kVerWarps][32][kChunk];                    // competitor matrix of short lists
