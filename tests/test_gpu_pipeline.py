@@ -351,3 +351,34 @@ def test_graphed_matcher_equals_plain_call():
         np.testing.assert_array_equal(P.mnn_matcher(a.cuda(), b.cuda()), want)
     with pytest.raises(ValueError):
         gm(a[:100].cuda(), b.cuda())
+
+
+def test_graph_objects_own_their_scratch_memory():
+    """A captured graph has the addresses of its scratch memory baked in: every graph object captures inside its own
+    workspace scope, so a later, larger call on the shared grow-only cache (or release_workspaces) cannot pull the
+    memory from under it, and two live graphs never share scratch."""
+    import posfeat_b200 as P
+    from posfeat_b200 import _runtime
+    g = torch.Generator().manual_seed(9)
+    mk = lambda n: torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=1)
+    a1, b1, a2, b2 = mk(1500), mk(1300), mk(3000), mk(2500)
+    b1[:1000] = torch.nn.functional.normalize(a1[:1000] + 0.2 * torch.randn(1000, 128, generator=g), dim=1)
+    b2[:2000] = torch.nn.functional.normalize(a2[:2000] + 0.2 * torch.randn(2000, 128, generator=g), dim=1)
+    w1, w2 = O.mnn_matcher(a1.numpy(), b1.numpy(), exact=True), O.mnn_matcher(a2.numpy(), b2.numpy(), exact=True)
+    g1 = P.GraphedMatcher(1500, 1300)
+    g2 = P.GraphedMatcher(3000, 2500)                      # larger: would have replaced a shared buffer
+    np.testing.assert_array_equal(g1(a1.cuda(), b1.cuda()), w1)
+    np.testing.assert_array_equal(g2(a2.cuda(), b2.cuda()), w2)
+    big = mk(9000)
+    P.mnn_matcher(big.cuda(), big.cuda())                  # grows the shared cache
+    _runtime.release_workspaces()
+    torch.cuda.empty_cache()
+    junk = torch.full((64 << 20,), 0x7f, dtype=torch.uint8, device="cuda")     # reuse whatever was freed
+    np.testing.assert_array_equal(g1(a1.cuda(), b1.cuda()), w1)
+    np.testing.assert_array_equal(g2(a2.cuda(), b2.cuda()), w2)
+    keys = [k for k in _runtime._workspaces if k[3] is not None]
+    assert len({k[3] for k in keys}) == 2                  # one private scope per graph object
+    del g1, junk
+    import gc
+    gc.collect()
+    assert len({k[3] for k in _runtime._workspaces if k[3] is not None}) == 1

@@ -17,7 +17,7 @@ METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dr
            "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,"
            "smsp__inst_executed.sum")
 for name in ("bench_n1.json", "bench_reference_arm.json", "bench_n1_table_form.json", "time_detect_cfgs.txt", "time_nms.txt",
-             "diag_mnn.txt", "tc_debug_sweep.txt", "sweep_mnn.jsonl", "time_ratio.jsonl", "time_corr.jsonl", "time_disk.jsonl",
+             "diag_mnn.txt", "tc_debug_sweep.txt", "verify_debug_sweep.txt", "sweep_mnn.jsonl", "time_ratio.jsonl", "time_corr.jsonl", "time_disk.jsonl",
              "h2d_ceiling_n1.json", "ncu_launch_list_bench.csv", "train_n1.json", "train_n2.json", "train_n8.json",
              "bench_n2.json", "bench_n4.json", "bench_n8.json", "h2d_ceiling_n2.json", "h2d_ceiling_n8.json"):
     a = os.path.join(src, f"{tag}_{name}")

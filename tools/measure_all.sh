@@ -14,6 +14,7 @@ python tools/time_detect_cfgs.py > $OUT/${TAG}_time_detect_cfgs.txt 2>&1
 python tools/time_nms.py > $OUT/${TAG}_time_nms.txt 2>&1
 python tools/diag_mnn.py > /dev/null 2> $OUT/${TAG}_diag_mnn.txt
 python tools/tc_debug_sweep.py 0 64 128 256 384 > $OUT/${TAG}_tc_debug_sweep.txt 2>&1
+python tools/verify_debug_sweep.py > $OUT/${TAG}_verify_debug_sweep.txt 2>&1
 python tools/time_ratio.py > $OUT/${TAG}_time_ratio.jsonl 2> $OUT/${TAG}_time_ratio.err
 python tools/time_corr.py > $OUT/${TAG}_time_corr.jsonl 2> $OUT/${TAG}_time_corr.err
 python tools/time_disk.py > $OUT/${TAG}_time_disk.jsonl 2> $OUT/${TAG}_time_disk.err
@@ -25,7 +26,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # full capture of one device-resident pass of the pair pipeline (8 pairs): every kernel of the hot path
 python tools/prof_pipeline.py 8 2 > $OUT/${TAG}_ncu_plain_pipe.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:mnn_tc_kernel|tc_rescore|tc_verify|tc_compact|nms_quad|select_kernel|keypoint_outputs|sample_nhwc' \
-    --launch-skip 8 --launch-count 8 -f -o $OUT/${TAG}_pipe_P8 \
+    --launch-skip 10 --launch-count 10 -f -o $OUT/${TAG}_pipe_P8 \
     python tools/prof_pipeline.py 8 2 > $OUT/${TAG}_ncu_full_pipe.log 2>&1
 # the training-side kernels (C4 shapes)
 python tools/prof_corr.py > $OUT/${TAG}_ncu_plain_corr.log 2>&1 &&
