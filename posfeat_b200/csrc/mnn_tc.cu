@@ -2221,7 +2221,7 @@ int mnn_tc(const float* A, int64_t strideA, int N, int64_t lda, const float* Bm,
     prof_begin(PROF_MNN_RESCORE, stream);
     // large calls: the chunk-ordered form (16-byte vector loads: aligned operands only; the records live in the table
     // form's first table, 2 * pitch bytes per row); POSFEAT_MNN_RESCORE_WARP=1 keeps the warp-per-row kernel for A/B runs
-    static const bool bucket_env = getenv("POSFEAT_MNN_RESCORE_WARP") == nullptr;
+    const bool bucket_env = getenv("POSFEAT_MNN_RESCORE_WARP") == nullptr;
     const bool bucket_form = bucket_env && (size_t)P * N >= 65536 && N < (1 << 28) &&
                              lda % 4 == 0 && ldb % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 &&
                              (((uintptr_t)A | (uintptr_t)Bm) & 15) == 0 && lda < (1ll << 31) && ldb < (1ll << 31) &&

@@ -204,6 +204,48 @@ def test_mnn_competitor_list_over_capacity(monkeypatch, capfd):
     assert [(nn12 == c).sum() for c in (0, 2000, 4000, 6000)] == [2, 2, 1, 40]          # the construction holds
 
 
+def test_mnn_batched_chunk_ordered_rescoring(monkeypatch):
+    """A batched matches-only call of >= 64k rows takes the chunk-ordered rescoring (enumerate -> chunk buckets ->
+    merge); smaller calls and POSFEAT_MNN_RESCORE_WARP=1 take the warp-per-row kernel.  Both against the float64
+    oracle on well-matched, noisy and unrelated pairs of one batch, ragged sizes included (N, M not multiples of 8 or
+    of the tile), and against each other bit for bit."""
+    from posfeat_b200 import _lib
+    from posfeat_b200._runtime import check, lib, stream_ptr, workspace
+    L = lib()
+    for N, M, P in ((8192, 8192, 9), (7001, 9003, 10)):
+        A = torch.stack([unit_desc(N, 128, 300 + i) for i in range(P)])
+        B = torch.stack([unit_desc(M, 128, 400 + i, base=A[i] if (i % 3 != 2 and M <= N) else None, noise=(0.1, 0.6, 0.0)[i % 3])
+                         for i in range(P)])
+        if M > N:                                 # noisy copies in the first N columns of two pairs out of three
+            for i in range(P):
+                if i % 3 != 2:
+                    B[i, :N] = unit_desc(N, 128, 500 + i, base=A[i], noise=(0.1, 0.6)[i % 3])
+        Ac, Bc = A.cuda(), B.cuda()
+        outs = []
+        for env in (None, "1"):
+            if env:
+                monkeypatch.setenv("POSFEAT_MNN_RESCORE_WARP", env)
+            nn12 = torch.empty((P, N), dtype=torch.int32, device="cuda")
+            matches = torch.empty((P, N, 2), dtype=torch.int64, device="cuda")
+            nm = torch.empty(P, dtype=torch.int32, device="cuda")
+            ws = workspace("mnn", L.posfeat_mnn_batched_workspace_bytes(P, N, M, 128, 2), Ac.device)
+            check(L.posfeat_mnn_batched_f32(Ac.data_ptr(), Ac.stride(0), N, Ac.stride(1), Bc.data_ptr(), Bc.stride(0), M,
+                                            Bc.stride(1), 128, P, 2, nn12.data_ptr(), None, matches.data_ptr(), nm.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), stream_ptr(Ac.device)))
+            torch.cuda.synchronize()
+            if env:
+                monkeypatch.delenv("POSFEAT_MNN_RESCORE_WARP")
+            outs.append((nn12.cpu().numpy(), matches.cpu().numpy(), nm.cpu().numpy()))
+        np.testing.assert_array_equal(outs[0][0], outs[1][0])
+        np.testing.assert_array_equal(outs[0][2], outs[1][2])
+        for i in range(P):
+            k = int(outs[0][2][i])
+            np.testing.assert_array_equal(outs[0][1][i, :k], outs[1][1][i, :k])
+            want, o12, _, rg, cg = O.mnn_blocked_f64(A[i].numpy(), B[i].numpy())
+            assert check_argmax_exact(A[i].numpy(), B[i].numpy(), outs[0][0][i], o12) == 0
+            assert assert_matches_exact(A[i], B[i], outs[0][1][i, :k], want, rg, cg) == 0
+
+
 def _pipeline_case(H, W, cfg, seed, P=1):
     g = torch.Generator().manual_seed(seed)
     score = torch.nn.functional.softplus(torch.randn(2 * P, 1, H, W, generator=g))
