@@ -263,6 +263,17 @@ int posfeat_corr_expect_bwd_f32(const float* q, const float* k, const float* v, 
 int posfeat_compute_prob_f32(const float* f1, const float* f2, int B, int m, int n, int D, int mode,
                              float scale, float* prob, float* sim, void* stream);
 
+/* scale * F.normalize(x, p=2, dim=1, eps) of a descriptor map, written channels-last in one pass: the operation
+ * Preprocess_Line2Window applies to both fine maps before the line search and the window expectation
+ * (losses/preprocess.py:56-57 via preprocess_utils.py:40-53 / :118-160, which normalise inside).  x: B images of D
+ * channels at stride sc (floats), the H*W pixels of a channel contiguous (NCHW), image stride sb; out: [B][HW][D];
+ * norm (optional for the forward call): [B][HW], the L2 norms -- the backward call needs them.  Backward: g is the
+ * gradient of out ([B][HW][D]), gx receives the gradient of x at the strides of x. */
+int posfeat_normalize_scale_fwd_f32(const float* x, int B, int D, int HW, int64_t sb, int64_t sc, float scale, float eps,
+                                    float* out, float* norm, void* stream);
+int posfeat_normalize_scale_bwd_f32(const float* g, const float* x, const float* norm, int B, int D, int HW, int64_t sb,
+                                    int64_t sc, float scale, float eps, float* gx, void* stream);
+
 /* DiskLoss dense affinity, losses/kploss.py:158-182 (second training stage): with A = T*<q_i,k_j> - T,
  * p_ij = softmax_j(A)_ij * softmax_i(A)_ij and log p_ij the sum of the two log-softmaxes, computes per row i
  *   rows_out[b,i] = { sum_j acc r p (log p + logp_i + logp_j),  sum_j acc r p,  sum_j p,  max_j p }

@@ -19,7 +19,7 @@ _LAZY = {
     "mnn_match": "preprocess_utils", "sample_l2norm": "preprocess_utils",
     "mutual_nn_matcher": "matchers",
     "get_expected_correspondence_locs": "preprocess", "compute_prob": "preprocess",
-    "get_expected_correspondence_within_window": "preprocess",
+    "get_expected_correspondence_within_window": "preprocess", "normalize_scale_channels_last": "preprocess",
     "Preprocess_Line2Window": "preprocess",
     "DiskLoss": "kploss", "EpipolarLoss_full": "epipolarloss", "GradAllReducer": "dist",
     "process": "extractor", "save_desc": "extractor", "FeatureExtractor": "extractor",

@@ -59,6 +59,8 @@ SIGNATURES = {
     "posfeat_corr_expect_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _sz, _vp]),
     "posfeat_compute_prob_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "posfeat_normalize_scale_fwd_f32": (_i, [_vp, _i, _i, _i, _i64, _i64, _f, _f, _vp, _vp, _vp]),
+    "posfeat_normalize_scale_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i64, _f, _f, _vp, _vp]),
     "posfeat_window_expect_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _i, _i,
                                            _vp, _vp, _vp, _vp, _vp]),
     "posfeat_dual_softmax_reward_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -84,6 +84,47 @@ def sample_feat_by_coord_grad(x, coord_n, norm=False):
     return F.normalize(raw, p=2, dim=2) if norm else raw
 
 
+# ------------------------------------------------- scale * normalize, channels-last
+class NormalizeScale(torch.autograd.Function):
+    """scale * F.normalize(x, p=2, dim=1) of a [B,D,h,w] map, returned channels-last, in one pass each way
+    (csrc/normalize.cu) instead of ~5 tensor operations forwards and ~10 backwards over the whole map."""
+
+    @staticmethod
+    def forward(ctx, x, scale, eps):
+        require_cuda()
+        xd = x.detach()
+        B, D, h, w = xd.shape
+        out = torch.empty((B, D, h, w), dtype=torch.float32, device=xd.device, memory_format=torch.channels_last)
+        norm = torch.empty((B, h * w), dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            check(lib().posfeat_normalize_scale_fwd_f32(xd.data_ptr(), B, D, h * w, xd.stride(0), xd.stride(1), float(scale),
+                                                        float(eps), out.data_ptr(), norm.data_ptr(), stream_ptr(xd.device)))
+        ctx.save_for_backward(xd, norm)
+        ctx.scale, ctx.eps = float(scale), float(eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, norm = ctx.saved_tensors
+        B, D, h, w = x.shape
+        g = g.detach().to(torch.float32).contiguous(memory_format=torch.channels_last)     # a no-op after our own kernels
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib().posfeat_normalize_scale_bwd_f32(g.data_ptr(), x.data_ptr(), norm.data_ptr(), B, D, h * w, x.stride(0),
+                                                        x.stride(1), ctx.scale, ctx.eps, gx.data_ptr(), stream_ptr(x.device)))
+        return gx, None, None
+
+
+def normalize_scale_channels_last(x, scale=1.0, eps=1e-12):
+    """``(scale * F.normalize(x, p=2, dim=1, eps=eps)).contiguous(memory_format=torch.channels_last)`` -- what
+    Preprocess_Line2Window hands to the line-search and window kernels.  Contiguous float32 NCHW maps on the device
+    take the fused kernels; anything else the tensor expression."""
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 1024
+            and x.shape[0] <= 65535 and x.numel() > 0):
+        return NormalizeScale.apply(x, scale, eps)
+    return (scale * F.normalize(x, p=2.0, dim=1, eps=eps)).contiguous(memory_format=torch.channels_last)
+
+
 # ----------------------------------------------------------- dense expectation
 class CorrExpect(torch.autograd.Function):
     """out[b,i,:] = sum_j softmax_j(scale * <q_i,k_j>) v[j,:]   (C <= 4, D <= 128)."""
@@ -444,8 +485,8 @@ class Preprocess_Line2Window(nn.Module):
         feat2g_std = (o2[..., 2:] - feat2g_corloc_n ** 2).clamp(min=1e-6).sqrt().sum(-1)
 
         # channels innermost: the line and window kernels then read whole descriptors (converted once here)
-        m2 = (T * F.normalize(xf2, p=2.0, dim=1)).contiguous(memory_format=torch.channels_last)
-        m1 = (T * F.normalize(xf1, p=2.0, dim=1)).contiguous(memory_format=torch.channels_last)
+        m2 = normalize_scale_channels_last(xf2, T)
+        m1 = normalize_scale_channels_last(xf1, T)
         if self.config["use_line_search"]:
             j1, j2 = jitter if jitter is not None else (None, None)
             ws = self.config["window_size"]

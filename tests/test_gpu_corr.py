@@ -310,3 +310,39 @@ def test_epipolar_line_search_vs_torch():
     assert float(agree.float().sum() / ok.float().sum()) > 0.99
     np.testing.assert_allclose(exp_[agree].cpu().numpy(), exp[agree].cpu().numpy(), rtol=0, atol=1e-5)
     np.testing.assert_allclose(std_[agree].cpu().numpy(), std[agree].cpu().numpy(), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 128, 30, 40), (3, 128, 17, 23), (1, 96, 5, 7), (2, 32, 1, 1)])
+def test_normalize_scale_channels_last(shape):
+    """The fused scale * F.normalize(x, dim=1) -> channels_last pass of Preprocess_Line2Window (csrc/normalize.cu)
+    against the tensor expression it replaces: values to 2 ulp (the norm is summed in another order), gradient
+    against a float64 run of the expression; a zero descriptor (norm below eps) takes the constant-denominator branch."""
+    import torch.nn.functional as F
+    from posfeat_b200.preprocess import normalize_scale_channels_last
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    x[0, :, 0, 0] = 0.0                                   # |x| < eps
+    x[-1, :, -1, -1] *= 1e-3
+    T = 60.0
+    xc = x.cuda().requires_grad_(True)
+    out = normalize_scale_channels_last(xc, T)
+    assert out.is_contiguous(memory_format=torch.channels_last) and out.shape == xc.shape
+    want = T * F.normalize(x.cuda(), p=2.0, dim=1)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.cpu().numpy(), rtol=3e-7, atol=1e-30)
+    w = torch.randn(*shape, generator=g).cuda()
+    (out * w).sum().backward()
+    x64 = x.double().cuda().requires_grad_(True)
+    ((T * F.normalize(x64, p=2.0, dim=1)) * w.double()).sum().backward()
+    ref = x64.grad.cpu().numpy()
+    got = xc.grad.cpu().numpy()
+    # the zero descriptor: d/dx (x / eps) = 1 / eps, 6e13 here -- compared on its own, relatively
+    np.testing.assert_allclose(got[0, :, 0, 0], ref[0, :, 0, 0], rtol=1e-6)
+    got[0, :, 0, 0] = ref[0, :, 0, 0] = 0.0
+    scale = np.abs(ref).max(axis=1, keepdims=True)      # per pixel: the gradient is a difference of terms of this size
+    assert np.abs(got - ref).max() <= 1e-30 + (2e-6 * scale).max()
+    assert (np.abs(got - ref) <= 2e-6 * scale + 1e-30).all()
+    # non-contiguous input: the tensor expression, same values
+    xs = x.cuda()[:, :, ::1, :].transpose(2, 3).contiguous().transpose(2, 3)
+    assert not xs.is_contiguous() or shape[2] == 1 or shape[3] == 1
+    np.testing.assert_allclose(normalize_scale_channels_last(xs, T).cpu().numpy(), want.cpu().numpy(), rtol=3e-7, atol=1e-30)

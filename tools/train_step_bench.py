@@ -95,7 +95,9 @@ def build_step(dev):
         q = PP.sample_feat_by_coord_grad(xf1, c1n, True)
         dense = 0.0
         for fm in (xc2, xf2):
-            e = PP.get_expected_correspondence_locs(q, torch.nn.functional.normalize(fm, dim=1) * 20.0)
+            # (the package's one-pass scale * normalize -> channels_last; the keys of the dense expectation are then a
+            # view of it, and the gradient comes back in the same layout: no copies either way)
+            e = PP.get_expected_correspondence_locs(q, PP.normalize_scale_channels_last(fm, 20.0))
             cost = point_to_line_distance(pr["coord1"], denormalize_coords(e, H, W), inputs["F1"])
             dense = dense + cost.clamp(max=0.5 * H).mean()
         return loss + 0.1 * dense
