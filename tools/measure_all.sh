@@ -30,7 +30,7 @@ ncu --set full --clock-control none --import-source on -k 'regex:mnn_tc_kernel|t
     python tools/prof_pipeline.py 8 2 > $OUT/${TAG}_ncu_full_pipe.log 2>&1
 # the training-side kernels (C4 shapes)
 python tools/prof_corr.py > $OUT/${TAG}_ncu_plain_corr.log 2>&1 &&
-ncu --set full --clock-control none -k regex:corr --launch-skip 6 --launch-count 12 -f -o $OUT/${TAG}_corr \
+ncu --set full --clock-control none -k 'regex:corr|normalize_scale' --launch-skip 7 --launch-count 14 -f -o $OUT/${TAG}_corr \
     python tools/prof_corr.py > $OUT/${TAG}_ncu_full_corr.log 2>&1
 python tools/prof_window.py > $OUT/${TAG}_ncu_plain_window.log 2>&1 &&
 ncu --set full --clock-control none -k 'regex:window|line_search' --launch-skip 3 --launch-count 3 -f -o $OUT/${TAG}_window \
