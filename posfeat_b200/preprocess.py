@@ -115,6 +115,52 @@ class NormalizeScale(torch.autograd.Function):
         return gx, None, None
 
 
+class SampleAndNormalize(torch.autograd.Function):
+    """(sample_feat_by_coord(x, coord, norm=False), scale * F.normalize(x, dim=1) channels-last) of one map as ONE
+    autograd node: the backward pass writes the dense gradient of the normalisation and scatters the sampling
+    gradient into the same buffer -- no zero-filled map, no map-sized addition to merge the two paths."""
+
+    @staticmethod
+    def forward(ctx, x, coord_n, scale, eps):
+        require_cuda()
+        xd = x.detach()
+        coord = _f32c(coord_n)
+        B, D, h, w = xd.shape
+        raw = sample_l2norm(xd, coord, False)
+        out = torch.empty((B, D, h, w), dtype=torch.float32, device=xd.device, memory_format=torch.channels_last)
+        norm = torch.empty((B, h * w), dtype=torch.float32, device=xd.device)
+        with torch.cuda.device(xd.device):
+            check(lib().posfeat_normalize_scale_fwd_f32(xd.data_ptr(), B, D, h * w, xd.stride(0), xd.stride(1), float(scale),
+                                                        float(eps), out.data_ptr(), norm.data_ptr(), stream_ptr(xd.device)))
+        ctx.save_for_backward(xd, norm, coord)
+        ctx.scale, ctx.eps = float(scale), float(eps)
+        return raw, out
+
+    @staticmethod
+    def backward(ctx, g_raw, g_out):
+        x, norm, coord = ctx.saved_tensors
+        B, D, h, w = x.shape
+        L = lib()
+        with torch.cuda.device(x.device):
+            if g_out is not None:
+                g = g_out.detach().to(torch.float32).contiguous(memory_format=torch.channels_last)
+                gx = torch.empty_like(x)
+                check(L.posfeat_normalize_scale_bwd_f32(g.data_ptr(), x.data_ptr(), norm.data_ptr(), B, D, h * w, x.stride(0),
+                                                        x.stride(1), ctx.scale, ctx.eps, gx.data_ptr(), stream_ptr(x.device)))
+            else:
+                gx = torch.zeros_like(x)
+            if g_raw is not None:
+                gr = _f32c(g_raw)
+                check(L.posfeat_sample_bwd_f32(gr.data_ptr(), B, D, h, w, gx.stride(0), gx.stride(1), gx.stride(2), gx.stride(3),
+                                               coord.data_ptr(), coord.shape[1], gx.data_ptr(), stream_ptr(x.device)))
+        return gx, None, None, None
+
+
+def _fused_map_ok(x):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 512
+            and x.shape[0] <= 65535 and x.numel() > 0)
+
+
 def normalize_scale_channels_last(x, scale=1.0, eps=1e-12):
     """``(scale * F.normalize(x, p=2, dim=1, eps=eps)).contiguous(memory_format=torch.channels_last)`` -- what
     Preprocess_Line2Window hands to the line-search and window kernels.  Contiguous float32 NCHW maps on the device
@@ -471,8 +517,16 @@ class Preprocess_Line2Window(nn.Module):
         coord1 = denormalize_coords(c1n, h1i, w1i)
         coord2 = denormalize_coords(c2n, h2i, w2i)
 
-        f1 = sample_feat_by_coord_grad(xf1, c1n, cos)           # :56-57
-        f2 = sample_feat_by_coord_grad(xf2, c2n, cos)
+        # :56-57 and the normalised maps of :84-106, one autograd node per map when the fused kernels apply
+        fused = _fused_map_ok(xf1) and _fused_map_ok(xf2)
+        if fused:
+            r1, m1 = SampleAndNormalize.apply(xf1, c1n, T, 1e-12)
+            r2, m2 = SampleAndNormalize.apply(xf2, c2n, T, 1e-12)
+            f1 = F.normalize(r1, p=2, dim=2) if cos else r1
+            f2 = F.normalize(r2, p=2, dim=2) if cos else r2
+        else:
+            f1 = sample_feat_by_coord_grad(xf1, c1n, cos)
+            f2 = sample_feat_by_coord_grad(xf2, c2n, cos)
 
         # grid <-> grid softmax expectations (:59-63, :76-81) without the [b,m,n] tensors
         o1 = corr_expect(f1, f2, torch.cat([coord2, c2n ** 2], -1), T)      # rows: softmax over image-2 points
@@ -485,8 +539,9 @@ class Preprocess_Line2Window(nn.Module):
         feat2g_std = (o2[..., 2:] - feat2g_corloc_n ** 2).clamp(min=1e-6).sqrt().sum(-1)
 
         # channels innermost: the line and window kernels then read whole descriptors (converted once here)
-        m2 = normalize_scale_channels_last(xf2, T)
-        m1 = normalize_scale_channels_last(xf1, T)
+        if not fused:
+            m2 = normalize_scale_channels_last(xf2, T)
+            m1 = normalize_scale_channels_last(xf1, T)
         if self.config["use_line_search"]:
             j1, j2 = jitter if jitter is not None else (None, None)
             ws = self.config["window_size"]
