@@ -813,9 +813,13 @@ static CorrTcBwdWs carve_corr_tc_bwd(void* base, int B, int n, int m, int D, int
   return w;
 }
 
-// The backward path launches ten kernels; below ~8M logits the SIMT kernels finish sooner (measured).
+// The backward path launches ten kernels; below ~2M logits the SIMT kernels finish sooner.  (The crossover was first
+// measured at 8M with an eager, host-bound caller; in the training step -- eager and as a CUDA graph -- the grid<->grid
+// problems of 2M logits and the coarse dense one of 4.9M are 2x faster here: 3.49 -> 3.28 ms per graphed step.
+// POSFEAT_CORR_TC_BWD_LOG2 moves the threshold for A/B runs.)
 bool corr_tc_bwd_eligible(int B, int n, int m, int D, int C) {
-  return corr_tc_eligible(B, n, m, D, C) && (int64_t)B * n * m >= (1 << 23);
+  static const int lg = [] { const char* e = getenv("POSFEAT_CORR_TC_BWD_LOG2"); return e ? atoi(e) : 21; }();
+  return corr_tc_eligible(B, n, m, D, C) && (int64_t)B * n * m >= ((int64_t)1 << lg);
 }
 
 size_t corr_tc_bwd_workspace_bytes(int B, int n, int m, int D, int C) {
