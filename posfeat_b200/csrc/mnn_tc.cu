@@ -1360,8 +1360,9 @@ struct RescoreListArgs {
 constexpr int kRlWarps = 2;
 // One row by one warp: float32 pass over the candidate chunks, exact pass when two columns come within the float32
 // error band, exhaustive walk when a list overflowed.  (A variant working on four rows per warp in lockstep, eight
-// lanes per row, measured SLOWER -- 613 vs 392 us per 64 pairs: the kernel moves 4.6 KB per row, 2.4 GB per step at
-// 6 TB/s out of L2, so it is bound by L2 bandwidth, not by the number of rows in flight.)
+// lanes per row, measured SLOWER -- 613 vs 392 us per 64 pairs.  ncu on this kernel: ~420-560 warp instructions per
+// row of which ~100 are the dot products, 57 % issue utilisation at the 32 warps per SM its registers allow, L2 at
+// 30 %: it is bound by its own instruction count and by latency, which is what the chunk-ordered form below attacks.)
 __device__ __forceinline__ void rescore_row_lists(const RescoreListArgs& a, const int pair, const int row,
                                                   float (&xs)[kRlWarps][kD], const int w, const int lane) {
   const DirParams& d = a.d;
