@@ -127,12 +127,37 @@ def homography_errors(kp_a: np.ndarray, kp_b: np.ndarray, matches: np.ndarray, h
     return np.sqrt(np.sum((kp_b[matches[:, 1], :2] - proj) ** 2, axis=1))
 
 
+def homography_hits(kp_a, kp_b, matches, n_matches, homography, thresholds) -> "torch.Tensor":
+    """The scoring of one pair (evaluation.py:73-90) on tensors, in float64, on whatever device they live on:
+    ``mean(dist <= t)`` for every threshold t, where dist is the reprojection distance of the first ``n_matches`` rows of
+    ``matches`` under the ground-truth homography.  With the matches already on the device (``mnn_match``) only
+    ``len(thresholds)`` numbers per pair cross the host link instead of the (K, 2) int64 match list.  No matches: zeros
+    (the reference's ``dist = [inf]``)."""
+    dev = matches.device
+    k = int(n_matches)
+    thr = torch.as_tensor(list(thresholds), dtype=torch.float64, device=dev)
+    if k == 0:
+        return torch.zeros_like(thr)
+    Hm = torch.as_tensor(np.asarray(homography, dtype=np.float64), device=dev)
+    a = torch.as_tensor(kp_a, device=dev)[matches[:k, 0], :2].to(torch.float64)
+    b = torch.as_tensor(kp_b, device=dev)[matches[:k, 1], :2].to(torch.float64)
+    x, y = a[:, 0], a[:, 1]
+    px = Hm[0, 0] * x + Hm[0, 1] * y + Hm[0, 2]
+    py = Hm[1, 0] * x + Hm[1, 1] * y + Hm[1, 2]
+    pw = Hm[2, 0] * x + Hm[2, 1] * y + Hm[2, 2]
+    dist = torch.sqrt((b[:, 0] - px / pw) ** 2 + (b[:, 1] - py / pw) ** 2)
+    return (dist[:, None] <= thr[None, :]).to(torch.float64).mean(0)
+
+
 def hpatches_benchmark(seq_names: Sequence[str], features_root: str, method: str, homographies: Callable[[str, int], np.ndarray],
                        rank: int = 0, world: int = 1, thresholds: Sequence[int] = tuple(range(1, 16)), extension: str = "ppm",
-                       matcher: Optional[Callable] = None, device=None, top_k: Optional[int] = None):
+                       matcher: Optional[Callable] = None, device=None, top_k: Optional[int] = None,
+                       score_on_device: bool = False):
     """benchmark_features (evaluation.py:40-96) sharded by sequence: returns on rank 0 the reference's
     (i_err, v_err, [seq_type, n_feats, n_matches]) accumulated over all ranks (None on the other ranks).
-    ``homographies(seq, k)`` supplies H_1_k (the reference reads ``<dataset>/<seq>/H_1_<k>``)."""
+    ``homographies(seq, k)`` supplies H_1_k (the reference reads ``<dataset>/<seq>/H_1_<k>``).
+    ``score_on_device``: match with ``mnn_match`` and score with ``homography_hits`` on the device -- the match list
+    never leaves it, 15 numbers and a count per pair do."""
     pairs = hpatches_pairs(seq_names, extension)
     acc = {"i": {t: 0.0 for t in thresholds}, "v": {t: 0.0 for t in thresholds}}
     rows = []
@@ -150,8 +175,31 @@ def hpatches_benchmark(seq_names: Sequence[str], features_root: str, method: str
             feats.insert(0, kp1.shape[0])
         rows.append((seq, k, seq[0], feats, int(m.shape[0])))
 
-    match_pairs(pairs, features_root, method, rank, world, group_key=lambda p: p[0].split("/")[0], device=device,
-                matcher=matcher, top_k=top_k, on_result=score)
+    if score_on_device:
+        from .preprocess_utils import mnn_match
+
+        def device_matcher(a, b):
+            m, nm, _, _ = mnn_match(a, b, want_nn21=False)
+            return m, int(nm.item())
+
+        def score_dev(pair, res, kp1, kp2):
+            m, k = res
+            seq, kk = pair[0].split("/")[0], int(pair[1].split("/")[1].split(".")[0])
+            hits = homography_hits(kp1, kp2, m, k, homographies(seq, kk), thresholds).cpu().numpy()
+            kind = "i" if seq[0] == "i" else "v"
+            for t, h in zip(thresholds, hits):
+                acc[kind][t] += float(h)
+            feats = [kp2.shape[0]]
+            if seq not in seen_ref:
+                seen_ref.add(seq)
+                feats.insert(0, kp1.shape[0])
+            rows.append((seq, kk, seq[0], feats, k))
+
+        match_pairs(pairs, features_root, method, rank, world, group_key=lambda p: p[0].split("/")[0], device=device,
+                    matcher=matcher or device_matcher, top_k=top_k, on_result=score_dev)
+    else:
+        match_pairs(pairs, features_root, method, rank, world, group_key=lambda p: p[0].split("/")[0], device=device,
+                    matcher=matcher, top_k=top_k, on_result=score)
     parts = gather_objects((acc, rows))
     if parts is None:
         return None

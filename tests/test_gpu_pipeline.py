@@ -300,6 +300,10 @@ def test_matching_driver_on_device(tmp_path):
     for t in ri:
         assert abs(res[0][t] - ri[t]) < 1e-12 and abs(res[1][t] - rv[t]) < 1e-12
     np.testing.assert_array_equal(res[2][2], rmatches)
+    dev = MD.hpatches_benchmark(T.SEQS, root, T.METHOD, T._homography, score_on_device=True)     # matches never leave the device
+    for t in ri:
+        assert abs(dev[0][t] - ri[t]) < 1e-12 and abs(dev[1][t] - rv[t]) < 1e-12
+    np.testing.assert_array_equal(dev[2][2], rmatches)
     pairs = MD.hpatches_pairs(T.SEQS[:2])
     got = MD.match_pairs(pairs, root, T.METHOD)
     for (a, b), m in got.items():

@@ -163,3 +163,44 @@ def test_hpatches_benchmark_two_ranks_equals_one(tmp_path):
         assert abs(one[0][t] - two[0][t]) < 1e-9 and abs(one[1][t] - two[1][t]) < 1e-9
     for a, b in zip(one[2], two[2]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_homography_hits_equals_host_scoring():
+    """homography_hits (tensor form of evaluation.py:73-90, float64) gives the hit fractions of the numpy scoring,
+    threshold by threshold, incl. the empty match list."""
+    from posfeat_b200 import matching_driver as MD
+    rng = np.random.default_rng(4)
+    kp1 = rng.uniform(0, 600, size=(300, 2)).astype(np.float32)
+    Hm = _homography("v_test", 3)
+    ph = np.concatenate([kp1, np.ones((300, 1))], 1) @ Hm.T
+    kp2 = (ph[:, :2] / ph[:, 2:] + rng.normal(0, 3.0, size=(300, 2))).astype(np.float32)
+    m = np.stack([rng.permutation(300)[:200], rng.permutation(300)[:200]], 1).astype(np.int64)
+    m[:120, 1] = m[:120, 0]                                   # 120 true correspondences, 80 random ones
+    thr = tuple(range(1, 16))
+    dist = MD.homography_errors(kp1, kp2, m, Hm)
+    want = np.array([np.mean(dist <= t) for t in thr])
+    got = MD.homography_hits(kp1, kp2, torch.from_numpy(m), 200, Hm, thr).numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-15)
+    assert got[-1] > 0.5 and got[0] < got[-1]
+    pad = torch.cat([torch.from_numpy(m), torch.full((50, 2), -1, dtype=torch.int64)])        # rows past n_matches are ignored
+    np.testing.assert_allclose(MD.homography_hits(kp1, kp2, pad, 200, Hm, thr).numpy(), want, rtol=0, atol=1e-15)
+    assert float(MD.homography_hits(kp1, kp2, torch.zeros((0, 2), dtype=torch.int64), 0, Hm, thr).sum()) == 0.0
+
+
+def test_hpatches_benchmark_device_scoring_path_equals_host_path(tmp_path):
+    """score_on_device=True (matches kept as tensors, hit fractions computed by homography_hits) accumulates the same
+    benchmark as the host path -- here with the oracle as the tensor-returning matcher, on the CPU."""
+    from posfeat_b200 import matching_driver as MD
+    root = str(tmp_path)
+    _write_features(root)
+
+    def tensor_matcher(a, b):
+        m = torch.from_numpy(_oracle_matcher(a, b))
+        return m, m.shape[0]
+
+    host = MD.hpatches_benchmark(SEQS, root, METHOD, _homography, matcher=_oracle_matcher, device="cpu")
+    dev = MD.hpatches_benchmark(SEQS, root, METHOD, _homography, matcher=tensor_matcher, device="cpu", score_on_device=True)
+    for t in host[0]:
+        assert abs(host[0][t] - dev[0][t]) < 1e-12 and abs(host[1][t] - dev[1][t]) < 1e-12
+    np.testing.assert_array_equal(host[2][2], dev[2][2])
+    np.testing.assert_array_equal(host[2][1], dev[2][1])
