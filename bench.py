@@ -166,7 +166,7 @@ def pixel_matches(idx2, m):
     return {(int(idx2[0][i]), int(idx2[1][j])) for i, j in m}
 
 
-def time_cpu_reference(score, fmap, budget_s=15.0, max_pairs=24):
+def time_cpu_reference(score, fmap, budget_s=15.0, max_pairs=64):
     """Bounded sample of the same workload on the host cores: the first pairs of the batch, one at a time,
     as the reference's scripts run them (batch_size 1)."""
     import torch
